@@ -1,0 +1,119 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
+//
+// Target log densities with the reference's LogpGrad call shape
+//   void(const VectorXd& x, double& logp, VectorXd& grad)   (concepts.hpp:258-262)
+// restated on std::vector<double>.  std_normal follows
+// examples/walnutpie_api.cpp:39-43 / tests/test_util.hpp:78-82; the diagonal
+// Gaussian generalises examples/examples.cpp:20-31 (`ill_normal`) to an
+// arbitrary precision vector; the funnel and the logistic regression are the
+// SURVEY.md §8(d) definitions (not in the reference repo).
+// All sums are plain left-to-right fp64 loops.
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <vector>
+
+namespace oracle {
+
+using Vec = std::vector<double>;
+
+enum TargetKind : int { kStdNormal = 0, kDiagGaussian = 1, kFunnel = 2,
+                        kLogistic = 3 };
+
+struct StdNormal {
+  void operator()(const Vec& x, double& lp, Vec& g) const {
+    g.resize(x.size());
+    double s = 0.0;
+    for (std::size_t i = 0; i < x.size(); ++i) {
+      s += x[i] * x[i];
+      g[i] = -x[i];
+    }
+    lp = -0.5 * s;
+  }
+};
+
+// logp = -1/2 sum_d x_d^2 * prec_d ; grad_d = -(x_d * prec_d)
+struct DiagGaussian {
+  Vec prec;  // 1 / sigma_d^2
+  void operator()(const Vec& x, double& lp, Vec& g) const {
+    g.resize(x.size());
+    double s = 0.0;
+    for (std::size_t i = 0; i < x.size(); ++i) {
+      double t = x[i] * prec[i];
+      s += x[i] * t;
+      g[i] = -t;
+    }
+    lp = -0.5 * s;
+  }
+};
+
+// Neal's funnel: v = x_0 ~ N(0, 3^2); x_i | v ~ N(0, e^v), i >= 1
+// logp = -v^2/18 - (D-1)/2 v - 1/2 e^{-v} sum_i x_i^2
+struct Funnel {
+  void operator()(const Vec& x, double& lp, Vec& g) const {
+    const std::size_t D = x.size();
+    g.resize(D);
+    const double v = x[0];
+    const double ev = std::exp(-v);
+    double ss = 0.0;
+    for (std::size_t i = 1; i < D; ++i) {
+      ss += x[i] * x[i];
+      g[i] = -(x[i] * ev);
+    }
+    const double half_dm1 = 0.5 * static_cast<double>(D - 1);
+    const double q = 0.5 * ev * ss;
+    lp = -(v * v) / 18.0 - half_dm1 * v - q;
+    g[0] = -v / 9.0 - half_dm1 + q;
+  }
+};
+
+// Bayesian logistic regression, prior theta ~ N(0, I):
+// logp = sum_n [y_n z_n - softplus(z_n)] - 1/2 |theta|^2,  z = X theta
+// grad = X^T (y - sigmoid(z)) - theta.     X row-major [N][D].
+struct Logistic {
+  std::size_t N = 0, D = 0;
+  const double* X = nullptr;
+  const double* y = nullptr;
+  void operator()(const Vec& x, double& lp, Vec& g) const {
+    g.assign(D, 0.0);
+    double ll = 0.0;
+    for (std::size_t n = 0; n < N; ++n) {
+      const double* row = X + n * D;
+      double z = 0.0;
+      for (std::size_t d = 0; d < D; ++d) z += row[d] * x[d];
+      // softplus(z) = max(z,0) + log1p(exp(-|z|))
+      double sp = (z > 0 ? z : 0.0) + std::log1p(std::exp(-std::fabs(z)));
+      double sig = z >= 0 ? 1.0 / (1.0 + std::exp(-z))
+                          : std::exp(z) / (1.0 + std::exp(z));
+      ll += y[n] * z - sp;
+      double r = y[n] - sig;
+      for (std::size_t d = 0; d < D; ++d) g[d] += row[d] * r;
+    }
+    double ss = 0.0;
+    for (std::size_t d = 0; d < D; ++d) {
+      ss += x[d] * x[d];
+      g[d] -= x[d];
+    }
+    lp = ll - 0.5 * ss;
+  }
+};
+
+// the C form of the plug-in (walnutpy.cpp:127-132)
+typedef int (*LOGP_CFUNC)(std::size_t n, const double* theta, double* grad,
+                          double* lp, void* data);
+
+struct CFuncTarget {
+  LOGP_CFUNC fn = nullptr;
+  void* data = nullptr;
+  void operator()(const Vec& x, double& lp, Vec& g) const {
+    g.resize(x.size());
+    int rc = fn(x.size(), x.data(), g.data(), &lp, data);
+    if (rc != 0) {
+      throw std::runtime_error("logp failed with code " + std::to_string(rc));
+    }
+  }
+};
+
+}  // namespace oracle
