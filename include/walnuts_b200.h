@@ -1,0 +1,234 @@
+/* walnuts_b200 — C-ABI of the B200-native WALNUTS sampler (libwalnuts_b200.so).
+ *
+ * Drop-in boundary for the hot path of flatironinstitute/walnuts: the same
+ * `extern "C"` surface as the reference's libwalnutpy
+ * (python/src/walnutpie/walnutpy.cpp), plus the device-model entry point and a
+ * session API that keeps thousands of chains resident in HBM.  Plain pointers
+ * and sizes only.  File:line citations are relative to /root/reference.
+ *
+ * Error convention (python/src/walnutpie/errors.hpp:10-72): return 0 on
+ * success, -1 on failure with *err set; free with walnutpie_destroy_error.
+ */
+#ifndef WALNUTS_B200_H
+#define WALNUTS_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error objects: errors.hpp:10-24 ------------------------------------ */
+typedef enum { wb200_generic = 0, wb200_config = 1, wb200_interrupt = 2 } WalnutpyErrorType;
+typedef struct WalnutpyError WalnutpyError;
+
+/* walnutpy.cpp:371-389 */
+const char* walnutpie_get_error_message(const WalnutpyError* err);
+int walnutpie_get_error_type(const WalnutpyError* err);
+void walnutpie_destroy_error(WalnutpyError* err);
+/* walnutpy.cpp:224-225 */
+char walnutpie_separator_char(void);
+
+/* ---- callbacks: walnutpy.cpp:127-132, handlers.hpp:15 -------------------- */
+typedef int (*LOGP_CFUNC)(size_t theta_size, const double* theta, double* grad,
+                          double* lp, void* data);
+typedef void (*PRINT_CALLBACK)(const char* msg, size_t len, bool bad);
+
+/* ---- device model descriptor (replaces `LOGP_CFUNC logp_c, void* data`) ---
+ * kind 0  standard normal                  examples/walnutpie_api.cpp:39-43
+ * kind 1  diagonal Gaussian, data0 = precision[D] (1/sigma_d^2), host fp64
+ * kind 2  Neal's funnel (x0 ~ N(0,9), x_i | x0 ~ N(0, exp(x0)))
+ * kind 3  Bayesian logistic regression, data0 = X[N][D] row-major host fp64,
+ *         data1 = y[N] host fp64 in {0,1}, prior N(0, I)
+ */
+typedef struct {
+  int kind;
+  int D;
+  size_t N;
+  const void* data0;
+  const void* data1;
+} WalnutModelDesc;
+
+/* The 26 tuning arguments of walnutpie_sample_cfunc (walnutpy.cpp:134-149),
+ * same names, same meaning, same defaults as pyfunc.py:51-82. */
+typedef struct {
+  int min_warmup_iter, max_warmup_iter;
+  int min_sampling_iter, max_sampling_iter;
+  int max_trajectory_doublings, max_step_halvings, min_micro_steps;
+  double max_hamiltonian_error;
+  double step_size_converge_tol, mass_converge_tol, rhat_converge_tol;
+  double mass_init_count, mass_additive_smoothing, max_macro_steps_target;
+  double step_size_init;
+  double step_accept_rate_target, step_learning_rate, step_gradient_decay;
+  double step_sq_gradient_decay, step_stabilization, step_learn_rate_decay;
+  int publish_stride;   /* WarmupConfig::publish_stride, config.hpp:639 (0 -> 5) */
+} WalnutTuning;
+
+/* Reference defaults (config.hpp:626-640, :947-953; step_size_init as pyfunc.py:74) */
+void walnuts_b200_default_tuning(WalnutTuning* t);
+
+/* ---- one-shot entry point: replaces walnutpie_sample_cfunc (walnutpy.cpp:134)
+ * for a device model.  Everything after (logp_c, data) keeps the reference's
+ * order and meaning; host buffers in and out:
+ *   inits            nullable [C][D]; else N(0, init_radius^2) (walnutpy.cpp:186-190)
+ *   init_inv_metric  nullable [C][D]; used as the initial MASS, bug-compatible
+ *                    with walnutpy.cpp:64-70
+ *   out              [C][max_sampling_iter + save_warmup*max_warmup_iter][D]
+ *   final_lengths    [2C] warm-up lengths then sampling lengths
+ */
+int walnutpie_sample_device(
+    const WalnutModelDesc* model, int num_params, const double* inits,
+    size_t num_chains, unsigned int seed, unsigned int id, double init_radius,
+    const double* init_inv_metric, int min_warmup_iter, int max_warmup_iter,
+    int min_sampling_iter, int max_sampling_iter, int max_trajectory_doublings,
+    int max_step_halvings, int min_micro_steps, double max_hamiltonian_error,
+    double step_size_converge_tol, double mass_converge_tol,
+    double rhat_converge_tol, double mass_init_count,
+    double mass_additive_smoothing, double max_macro_steps_target,
+    double step_size_init, double step_accept_rate_target,
+    double step_learning_rate, double step_gradient_decay,
+    double step_sq_gradient_decay, double step_stabilization,
+    double step_learn_rate_decay, bool save_warmup, double* out,
+    size_t out_size, int* final_lengths, double* stepsize_out,
+    double* inv_metric_out, int refresh, PRINT_CALLBACK print,
+    WalnutpyError** err);
+
+/* walnutpie_sample_cfunc / walnutpie_sample_bridgestan (walnutpy.cpp:134, :227):
+ * exported for link compatibility; a host callback cannot feed a device batch,
+ * so both fail with a `generic` error that names walnutpie_sample_device. */
+int walnutpie_sample_cfunc(
+    LOGP_CFUNC logp_c, void* data, int num_params, const double* inits,
+    size_t num_chains, unsigned int seed, unsigned int id, double init_radius,
+    const double* init_inv_metric, int min_warmup_iter, int max_warmup_iter,
+    int min_sampling_iter, int max_sampling_iter, int max_trajectory_doublings,
+    int max_step_halvings, int min_micro_steps, double max_hamiltonian_error,
+    double step_size_converge_tol, double mass_converge_tol,
+    double rhat_converge_tol, double mass_init_count,
+    double mass_additive_smoothing, double max_macro_steps_target,
+    double step_size_init, double step_accept_rate_target,
+    double step_learning_rate, double step_gradient_decay,
+    double step_sq_gradient_decay, double step_stabilization,
+    double step_learn_rate_decay, bool save_warmup, double* out,
+    size_t out_size, int* final_lengths, double* stepsize_out,
+    double* inv_metric_out, int refresh, PRINT_CALLBACK print,
+    WalnutpyError** err);
+
+/* ---- summaries: walnutpy.cpp:333-369.  `draws` is HOST, ROW-MAJOR
+ * [num_draws][num_params] with chains stacked (what summary.py:30 passes);
+ * computed on the device. */
+int walnutpie_ess(const double* draws, int num_draws, int num_params,
+                  const int* lengths, int num_chains, double* out,
+                  WalnutpyError** err);
+int walnutpie_r_hat(const double* draws, int num_draws, int num_params,
+                    const int* lengths, int num_chains, double* out,
+                    WalnutpyError** err);
+int walnutpie_mcse(const double* draws, int num_draws, int num_params,
+                   const int* lengths, int num_chains, double* out,
+                   WalnutpyError** err);
+
+/* ---- session API: chains stay resident in HBM -----------------------------
+ * The pieces walnutpie::walnuts<RNG>() (api.hpp:33-69) is made of, batched:
+ * create = per-chain RNG streams + AdaptiveWalnuts state (api.hpp:46-58),
+ * warmup = AdaptiveWalnuts::operator() x n (adaptive_walnuts.hpp:234-251),
+ * freeze = AdaptiveWalnuts::sampler() (adaptive_walnuts.hpp:263-271),
+ * sample = WalnutsSampler::operator() x n (walnuts.hpp:682-692).
+ * Chain `c` of a session uses the Philox stream of global chain id
+ * chain_offset + c, so results do not depend on how chains are sharded. */
+typedef struct wb200_session wb200_session;
+
+int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
+                         unsigned int seed, unsigned int chain_offset,
+                         const WalnutTuning* tuning, int device,
+                         wb200_session** out, WalnutpyError** err);
+void wb200_session_destroy(wb200_session* s);
+
+/* positions/mass/steps are HOST [C][D] / [C][D] / [C]; any may be NULL:
+ * positions -> N(0, init_radius^2) per chain (Philox kind 2);
+ * mass      -> (1-s)|grad logp(theta0)| + s, s = mass_additive_smoothing
+ *              (config.hpp:360-370);
+ * steps     -> step_size_init refined by the doubling / sqrt(1/2) search of
+ *              util.hpp:285-303 on the device (Philox kind 3). */
+int wb200_session_init(wb200_session* s, const double* positions,
+                       double init_radius, const double* mass,
+                       const double* steps, WalnutpyError** err);
+
+/* Reserve device storage for `capacity` draws per chain; trace != 0 also
+ * records lp, depth, step size and (warm-up) the metric used per iteration. */
+int wb200_session_reserve_draws(wb200_session* s, long long capacity, int trace,
+                                WalnutpyError** err);
+
+/* n warm-up iterations for every chain; store != 0 appends the draws */
+int wb200_session_warmup(wb200_session* s, int n_iter, int store,
+                         WalnutpyError** err);
+/* freeze step / inverse mass / min_micro (adaptive_walnuts.hpp:263-271) */
+int wb200_session_freeze(wb200_session* s, WalnutpyError** err);
+int wb200_session_sample(wb200_session* s, int n_iter, int store,
+                         WalnutpyError** err);
+/* block until the session's stream is idle */
+int wb200_session_sync(wb200_session* s, WalnutpyError** err);
+
+/* Cross-chain convergence statistics, evaluated on the device.
+ * warm-up (adapt.hpp:186-224): out[0] = max_m ||(M_m - gm)/gm||_2,
+ *   out[1] = max_m (eps_m - gs)/gs;  sums_io: if non-NULL, DEVICE buffer of
+ *   (D + 2) doubles {sum log M[D], sum log eps, count} that the caller may
+ *   all-reduce (NCCL) between the two phases: phase 0 fills it from the local
+ *   chains, phase 1 consumes the (reduced) sums and writes out[0..1].
+ * sampling (sampler.hpp:132-151): moments = {sum mu, sum mu^2, sum var, count}. */
+int wb200_session_warmup_sums(wb200_session* s, double* sums_device,
+                              WalnutpyError** err);
+int wb200_session_warmup_deviation(wb200_session* s, const double* sums_device,
+                                   double* out_host2, WalnutpyError** err);
+int wb200_session_lp_moments(wb200_session* s, double* moments_host4,
+                             WalnutpyError** err);
+
+/* Read-back (host buffers).  draws: [C][count][D] from row `first`. */
+int wb200_session_get_draws(wb200_session* s, long long first, long long count,
+                            double* out, WalnutpyError** err);
+int wb200_session_get_trace(wb200_session* s, long long first, long long count,
+                            double* lp, int* depth, double* step,
+                            double* inv_mass, WalnutpyError** err);
+int wb200_session_get_state(wb200_session* s, double* theta, double* inv_mass,
+                            double* step, int* min_micro,
+                            unsigned long long* grad_evals, WalnutpyError** err);
+/* raw device pointers for zero-copy consumers (torch / NCCL): draws are
+ * [C][capacity][ld] with ld = row stride in doubles */
+int wb200_session_device_draws(wb200_session* s, double** draws, long long* capacity,
+                               int* ld, long long* rows_written);
+/* total gradient evaluations so far (sum over chains) and launch count */
+int wb200_session_counters(wb200_session* s, unsigned long long* grad_evals,
+                           unsigned long long* macro_steps,
+                           unsigned long long* kernel_launches,
+                           WalnutpyError** err);
+/* last kernel's device time in ms (CUDA events on the session stream) */
+int wb200_session_last_kernel_ms(wb200_session* s, float* ms);
+
+/* Fixed-step leapfrog orbit (walnuts.hpp:329-332) for parity checks:
+ * theta/rho/inv_mass HOST [C][D]; advances `num_steps` micro-steps. */
+int wb200_orbit(const WalnutModelDesc* model, size_t num_chains,
+                const double* theta, const double* rho, const double* inv_mass,
+                double step, int num_steps, double* theta_out, double* rho_out,
+                double* grad_out, double* logp_out, double* joint_out,
+                WalnutpyError** err);
+
+/* device-side Philox (for the generator known-answer tests) */
+int wb200_philox(const uint32_t* ctr_key6, size_t n, uint32_t* out4,
+                 WalnutpyError** err);
+int wb200_philox_normals(unsigned int seed, unsigned int chain, unsigned int iter,
+                         unsigned int kind, size_t n, double* out,
+                         WalnutpyError** err);
+
+/* device summaries on DEVICE draws [C][capacity][ld] (equal lengths):
+ * per-dimension R-hat, ESS, MCSE, pooled mean and variance (summary.hpp) */
+int wb200_device_summary(const double* draws_device, size_t num_chains,
+                         long long capacity, long long first, long long count,
+                         int D, int ld, double* rhat, double* ess, double* mcse,
+                         double* mean, double* var, WalnutpyError** err);
+
+const char* walnuts_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WALNUTS_B200_H */

@@ -1,0 +1,328 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+ * fixed-step leapfrog orbits: <= 1e-12 relative, fp64;
+ * identically seeded (Philox) trajectories agree until the first
+   rounding-induced branch flip -- asserted as: every chain agrees over a
+   stated prefix, and the large majority over the whole run;
+ * posterior moments within Monte Carlo standard error.
+Element-wise arithmetic on the device mirrors the oracle operation by operation;
+only cross-element sums differ (summation order), so tolerances are tight.
+"""
+import numpy as np
+import pytest
+
+from oracle.binding import Target, default_config
+
+pytestmark = pytest.mark.gpu
+
+ORBIT_RTOL = 1e-12
+
+
+def rel_err(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+# ---- generator ---------------------------------------------------------------
+def test_device_philox_known_answers(wb):
+    from walnuts_b200 import _ffi
+    q = np.array([[0, 0, 0, 0, 0, 0], [0xFFFFFFFF] * 6,
+                  [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0]],
+                 dtype=np.uint32)
+    out = np.zeros((3, 4), np.uint32)
+    _ffi.philox(q, 3, out)
+    assert out.tolist() == [[0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8],
+                            [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD],
+                            [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]]
+
+
+def test_device_normals_match_oracle_stream(wb, oracle):
+    from walnuts_b200 import _ffi
+    for n in (1, 2, 7, 1000):
+        dev = np.zeros(n)
+        _ffi.philox_normals(123, 45, 6, 0, n, dev)
+        ora = oracle.philox_normals(123, 45, 6, 0, n)
+        # same Philox words; log / sincos differ between libm and CUDA by <= a few ulp
+        np.testing.assert_allclose(dev, ora, rtol=1e-13, atol=1e-15)
+
+
+# ---- fixed-step orbits -------------------------------------------------------
+ORBIT_CASES = [
+    ("std_normal", 100, 0.37, 64),
+    ("diag_gaussian", 1000, 0.2, 50),
+    ("funnel", 100, 0.05, 40),
+    ("std_normal", 1, 0.5, 10),
+    ("diag_gaussian", 513, 0.1, 33),   # odd dimension: padded lane
+    ("funnel", 2, 0.1, 20),
+    ("diag_gaussian", 2000, 0.1, 16),
+    ("std_normal", 4096, 0.1, 8),      # maximum supported dimension
+]
+
+
+def make_model(wb, kind, D, rng):
+    if kind == "diag_gaussian":
+        var = 10.0 ** (4 * np.arange(D) / max(D - 1, 1))
+        return wb.models.diag_gaussian(var), Target(kind, D, prec=1 / var)
+    return getattr(wb.models, kind)(D), Target(kind, D)
+
+
+@pytest.mark.parametrize("kind,D,step,nsteps", ORBIT_CASES)
+def test_fixed_step_orbit_matches_oracle(wb, oracle, kind, D, step, nsteps):
+    rng = np.random.default_rng(D + nsteps)
+    model, target = make_model(wb, kind, D, rng)
+    C = 5
+    inv_mass = rng.uniform(0.5, 2.0, (C, D))
+    if kind == "diag_gaussian":
+        inv_mass *= 10.0 ** (4 * np.arange(D) / max(D - 1, 1))
+    theta = rng.normal(size=(C, D)) * (0.3 if kind == "funnel" else 1.0)
+    rho = rng.normal(size=(C, D)) / np.sqrt(inv_mass)
+    for sign in (+1, -1):
+        th, rh, g, lp, jt = wb.orbit(model, theta, rho, inv_mass, sign * step, nsteps)
+        for c in range(C):
+            o = oracle.orbit(target, theta[c], rho[c], inv_mass[c], sign * step, nsteps)
+            scale = max(np.max(np.abs(o[0])), 1e-30)
+            assert np.max(np.abs(th[c] - o[0])) / scale <= ORBIT_RTOL
+            assert np.max(np.abs(rh[c] - o[1])) / max(np.max(np.abs(o[1])), 1e-30) <= ORBIT_RTOL
+            assert np.max(np.abs(g[c] - o[2])) / max(np.max(np.abs(o[2])), 1e-30) <= ORBIT_RTOL
+            assert abs(lp[c] - o[3]) <= ORBIT_RTOL * max(abs(o[3]), 1.0)
+            assert abs(jt[c] - o[4]) <= ORBIT_RTOL * max(abs(o[4]), 1.0)
+        if kind != "funnel":
+            # element-wise dynamics: not merely close, identical
+            o = oracle.orbit(target, theta[0], rho[0], inv_mass[0], sign * step, nsteps)
+            np.testing.assert_array_equal(th[0], o[0])
+            np.testing.assert_array_equal(rh[0], o[1])
+
+
+def test_orbit_reversibility_and_zero_steps(wb):
+    """size-independent properties at the full c2 size: zero steps is the identity,
+    forward then backward returns to the start (leapfrog is time-reversible)."""
+    D, C = 1000, 64
+    rng = np.random.default_rng(3)
+    model = wb.models.ill_conditioned_gaussian(D)
+    var = 1e4 ** (np.arange(D) / (D - 1))
+    theta = rng.normal(size=(C, D)) * np.sqrt(var)
+    inv_mass = np.tile(var, (C, 1))
+    rho = rng.normal(size=(C, D)) / np.sqrt(inv_mass)
+    th0, rh0, *_ = wb.orbit(model, theta, rho, inv_mass, 0.3, 0)
+    np.testing.assert_array_equal(th0, theta)
+    np.testing.assert_array_equal(rh0, rho)
+    th1, rh1, *_ = wb.orbit(model, theta, rho, inv_mass, 0.3, 25)
+    th2, rh2, *_ = wb.orbit(model, th1, rh1, inv_mass, -0.3, 25)
+    assert np.max(np.abs(th2 - theta) / np.sqrt(var)) < 1e-11
+    assert np.max(np.abs(rh2 - rho) * np.sqrt(var)) < 1e-11
+
+
+# ---- identically seeded trajectories ----------------------------------------
+TRAJ_CASES = [
+    # kind, D, chains, tuning overrides, n_warmup, n_sampling
+    ("std_normal", 100, 6, dict(), 60, 60),
+    ("diag_gaussian", 10, 8, dict(max_trajectory_doublings=8), 80, 80),
+    ("diag_gaussian", 1000, 3, dict(max_trajectory_doublings=10), 40, 30),
+    ("funnel", 11, 8, dict(max_step_halvings=8, max_trajectory_doublings=7), 60, 60),
+    ("std_normal", 5, 8, dict(min_micro_steps=2, max_macro_steps_target=3.0), 60, 60),
+    ("diag_gaussian", 300, 4, dict(), 30, 30),          # 128-thread groups
+    ("std_normal", 37, 5, dict(max_step_halvings=1), 40, 40),  # odd D, no halving
+]
+
+
+def first_divergence(a, b, rtol):
+    """index of the first row where a and b differ by more than rtol (or len)."""
+    scale = np.maximum(np.max(np.abs(b), axis=-1), 1e-300)
+    bad = np.max(np.abs(a - b), axis=-1) / scale > rtol
+    idx = np.flatnonzero(bad)
+    return int(idx[0]) if idx.size else len(a)
+
+
+@pytest.mark.parametrize("kind,D,C,over,nw,ns", TRAJ_CASES)
+def test_seeded_trajectories_match_oracle(wb, oracle, kind, D, C, over, nw, ns):
+    rng = np.random.default_rng(1000 + D)
+    model, target = make_model(wb, kind, D, rng)
+    seed = 777
+    positions = rng.normal(size=(C, D))
+    mass = rng.uniform(0.5, 2.0, (C, D))
+    steps = rng.uniform(0.2, 0.6, C)
+    cfg = default_config(**over)
+    with wb.Session(model, C, seed=seed, **over) as s:
+        s.init(positions=positions, mass=mass, steps=steps)
+        s.reserve(nw + ns, trace=True)
+        s.warmup(nw, store=True).freeze().sample(ns, store=True).sync()
+        draws = s.draws(0, nw + ns)
+        tr = s.trace(0, nw + ns)
+        st = s.state()
+    full, prefix = 0, []
+    rtol = 1e-9
+    for c in range(C):
+        o = oracle.run_chain(target, cfg, seed, c, positions[c], mass[c], steps[c], nw, ns,
+                             rng_policy=1)
+        ref_draws = np.concatenate([o["warmup_draws"], o["draws"]])
+        k = first_divergence(draws[c], ref_draws, rtol)
+        prefix.append(k)
+        if k == nw + ns:
+            full += 1
+            ref_depth = np.concatenate([o["warmup_depth"], o["depth"]])
+            np.testing.assert_array_equal(tr["depth"][c], ref_depth)
+            np.testing.assert_allclose(tr["lp"][c], np.concatenate([o["warmup_lp"], o["lp"]]),
+                                       rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(tr["step"][c, :nw], o["warmup_step"], rtol=1e-10)
+            np.testing.assert_allclose(tr["inv_mass"][c, :nw], o["warmup_inv_mass"], rtol=1e-9)
+            np.testing.assert_allclose(st["inv_mass"][c], o["inv_mass"], rtol=1e-9)
+            assert st["step"][c] == pytest.approx(o["step"], rel=1e-10)
+            assert st["min_micro"][c] == o["min_micro"]
+            assert int(st["grad_evals"][c]) == o["grad_evals"]
+    print(f"\n[{kind} D={D}] first-divergence iteration per chain: {prefix} "
+          f"(run length {nw + ns})")
+    # every chain agrees over the first iterations; most agree to the end
+    assert min(prefix) >= 5
+    assert full >= (C + 1) // 2
+
+
+def test_fixed_parameter_sampler_is_bit_exact_for_gaussians(wb, oracle):
+    """With frozen tuning, Gaussian dynamics are purely element-wise, so the draws
+    equal the oracle's bit for bit as long as no accept/U-turn decision flips."""
+    D, C, n = 50, 6, 40
+    rng = np.random.default_rng(8)
+    var = rng.uniform(0.5, 4.0, D)
+    model, target = wb.models.diag_gaussian(var), Target("diag_gaussian", D, prec=1 / var)
+    positions = rng.normal(size=(C, D))
+    inv_mass = rng.uniform(0.5, 2.0, (C, D))
+    with wb.Session(model, C, seed=5, max_trajectory_doublings=6) as s:
+        s.init(positions=positions, mass=1 / inv_mass, steps=np.full(C, 0.45))
+        s.reserve(n, trace=True)
+        s.freeze().sample(n, store=True).sync()
+        draws = s.draws(0, n)
+        im_used = s.state()["inv_mass"]
+    exact = 0
+    for c in range(C):
+        o = oracle.run_sampler(target, 5, c, positions[c], im_used[c], 0.45, 6, 5, 1, 0.5, n,
+                               rng_policy=1)
+        exact += int(np.array_equal(draws[c], o["draws"]))
+    assert exact >= C - 1
+
+
+# ---- posterior moments -------------------------------------------------------
+@pytest.mark.parametrize("kind,D,C", [("std_normal", 100, 512), ("diag_gaussian", 64, 512)])
+def test_posterior_moments_match_truth_and_oracle(wb, oracle, kind, D, C):
+    rng = np.random.default_rng(D)
+    model, target = make_model(wb, kind, D, rng)
+    var = 1.0 / target.prec if kind == "diag_gaussian" else np.ones(D)
+    nw, ns = 150, 100
+    with wb.Session(model, C, seed=2024, max_trajectory_doublings=8) as s:
+        s.init(init_radius=2.0)
+        s.reserve(ns)
+        s.warmup(nw).freeze().sample(ns).sync()
+        summ = s.summary(0, ns)
+        draws = s.draws(0, ns)
+    # analytic truth within MCSE (z < 5 over D dims x 2 moments)
+    z_mean = np.abs(summ["mean"]) / summ["mcse"]
+    assert np.max(z_mean) < 5.0, np.max(z_mean)
+    ess = summ["ess"]
+    var_se = var * np.sqrt(2.0 / np.minimum(ess, C * ns))
+    assert np.max(np.abs(summ["variance"] - var) / var_se) < 6.0
+    assert np.max(summ["r_hat"]) < 1.05
+    # the CPU oracle run (8 chains, same settings) agrees within combined MCSE
+    cfg = default_config(min_warmup_iter=nw, max_warmup_iter=nw, min_sampling_iter=ns,
+                         max_sampling_iter=ns, max_trajectory_doublings=8)
+    pos = oracle.init_positions(8, D, 9, 2.0)
+    mass, steps = oracle.init_mass_step(target, pos, 9, 1.0)
+    cpu = oracle.walnuts(target, cfg, 9, pos, mass, steps)
+    chains = [cpu["out"][c, :ns] for c in range(8)]
+    cpu_mean = np.mean(np.concatenate(chains), axis=0)
+    cpu_mcse = oracle.mcse(chains)
+    z = np.abs(summ["mean"] - cpu_mean) / np.sqrt(summ["mcse"] ** 2 + cpu_mcse ** 2)
+    assert np.max(z) < 5.0, np.max(z)
+    # device summaries equal the oracle's on the same draws
+    sub = [draws[c] for c in range(16)]
+    np.testing.assert_allclose(wb.ess(sub), oracle.ess(sub), rtol=1e-8)
+    np.testing.assert_allclose(wb.r_hat(sub), oracle.r_hat(sub), rtol=1e-10)
+    np.testing.assert_allclose(wb.mcse(sub), oracle.mcse(sub), rtol=1e-8)
+
+
+def test_funnel_moments_match_oracle_within_mcse(wb, oracle):
+    D, C, nw, ns = 11, 1024, 200, 200
+    over = dict(max_step_halvings=8, max_trajectory_doublings=8)
+    with wb.Session(wb.models.funnel(D), C, seed=31, **over) as s:
+        s.init(init_radius=1.0)
+        s.reserve(ns)
+        s.warmup(nw).freeze().sample(ns).sync()
+        summ = s.summary(0, ns)
+    target = Target("funnel", D)
+    cfg = default_config(min_warmup_iter=nw, max_warmup_iter=nw, min_sampling_iter=4 * ns,
+                         max_sampling_iter=4 * ns, **over)
+    pos = oracle.init_positions(8, D, 4, 1.0)
+    mass, steps = oracle.init_mass_step(target, pos, 4, 1.0)
+    cpu = oracle.walnuts(target, cfg, 4, pos, mass, steps)
+    chains = [cpu["out"][c, :4 * ns] for c in range(8)]
+    cpu_mean = np.mean(np.concatenate(chains), axis=0)
+    cpu_mcse = oracle.mcse(chains)
+    z = np.abs(summ["mean"] - cpu_mean) / np.sqrt(summ["mcse"] ** 2 + cpu_mcse ** 2)
+    assert np.max(z) < 5.0, z
+
+
+# ---- summaries on the reference's golden data -------------------------------
+def test_device_summaries_on_reference_golden_vectors(wb):
+    """tests/summary_test.cpp:1073-1083, :1182-1192, :866-879 through the C-ABI."""
+    from tests.ar1_data import AR1_CHAINS
+    ess = wb.ess(AR1_CHAINS)
+    assert ess[0] == pytest.approx(96.256789181, abs=1e-5)
+    assert ess[1] == pytest.approx(7.315045989, abs=1e-5)
+    m = wb.mcse(AR1_CHAINS)
+    assert m[0] == pytest.approx(0.096327220756986, abs=1e-7)
+    assert m[1] == pytest.approx(0.250085871061602, abs=1e-7)
+    ragged = [np.array([[1, 5], [3, 3], [2, 4]], float),
+              np.array([[4, 2], [6, 4], [5, 3], [7, 5]], float)]
+    np.testing.assert_allclose(wb.r_hat(ragged),
+                               [np.sqrt(1 + 147 / 32), np.sqrt(1 + 3 / 32)], rtol=1e-14)
+    with pytest.raises(ValueError, match="at least two chains"):
+        wb.r_hat([np.arange(10.0).reshape(5, 2)])
+    with pytest.raises(ValueError, match="at least 3 draws"):
+        wb.ess([np.array([[1.0, 2.0], [3.0, 4.0]])])
+
+
+# ---- the reference's behavioural tests through the drop-in entry point -------
+@pytest.mark.parametrize("MIN,MAX", [(10, 12), (77, 77), (10, 30)])
+def test_warmup_requested_iter(wb, MIN, MAX):  # python/tests/test_pyfunc.py:38-50
+    fit = wb.walnuts_device(wb.models.std_normal(2), min_warmup_iter=MIN, max_warmup_iter=MAX,
+                            min_sampling_iter=1, max_sampling_iter=1, save_warmup=True)
+    for chain in fit:
+        assert MIN <= len(chain.warmup.warmup_draws) <= MAX
+
+
+@pytest.mark.parametrize("MIN,MAX", [(10, 12), (77, 77), (10, 30)])
+def test_sampling_requested_iter(wb, MIN, MAX):  # test_pyfunc.py:53-64
+    fit = wb.walnuts_device(wb.models.std_normal(2), min_sampling_iter=MIN,
+                            max_sampling_iter=MAX, min_warmup_iter=100, max_warmup_iter=100)
+    for chain in fit:
+        assert MIN <= len(chain) <= MAX
+
+
+def test_seed_works(wb):  # test_pyfunc.py:89-125
+    kw = dict(min_warmup_iter=400, max_warmup_iter=400, save_warmup=True, save_inv_metric=True)
+    m = wb.models.std_normal(4)
+    fit1 = wb.walnuts_device(m, seed=1234, **kw)
+    fit2 = wb.walnuts_device(m, seed=1234, **kw)
+    fit3 = wb.walnuts_device(m, seed=452, **kw)
+    for c1, c2 in zip(fit1, fit2, strict=True):
+        n = min(c1.shape[0], c2.shape[0])
+        np.testing.assert_array_equal(c1[:n], c2[:n])
+        assert c1.warmup.stepsize == c2.warmup.stepsize
+        np.testing.assert_array_equal(c1.warmup.inv_metric, c2.warmup.inv_metric)
+        np.testing.assert_array_equal(c1.warmup.warmup_draws, c2.warmup.warmup_draws)
+    assert not np.array_equal(fit1[0][:10], fit3[0][:10])
+
+
+def test_results_do_not_depend_on_sharding(wb):
+    """Chains are keyed by global id: 8 chains in one session == 2 sessions of 4
+    with chain_offset 0 and 4 (what each rank of a multi-GPU run holds)."""
+    D, n = 20, 30
+    m = wb.models.ill_conditioned_gaussian(D, 100.0)
+
+    def run(C, off):
+        with wb.Session(m, C, seed=9, chain_offset=off) as s:
+            s.init(init_radius=2.0)
+            s.reserve(n)
+            s.warmup(40).freeze().sample(n).sync()
+            return s.draws(0, n)
+
+    whole = run(8, 0)
+    np.testing.assert_array_equal(whole[:4], run(4, 0))
+    np.testing.assert_array_equal(whole[4:], run(4, 4))

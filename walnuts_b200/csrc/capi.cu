@@ -1,0 +1,415 @@
+// extern "C" surface of libwalnuts_b200.so (see include/walnuts_b200.h).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../host/config.hpp"
+#include "engine.cuh"
+
+namespace wb200 {
+// walnutpy.cpp:36-62: the builders validate exactly like the reference
+static void validate_tuning(const WalnutTuning& t) {
+  using namespace walnuts_b200;
+  if (t.min_warmup_iter < 0 || t.max_warmup_iter < 0 || t.min_sampling_iter < 0 ||
+      t.max_sampling_iter < 0) {
+    throw std::invalid_argument("iteration counts must be non-negative");
+  }
+  WarmupConfigBuilder()
+      .min_max_iter(t.min_warmup_iter, t.max_warmup_iter)
+      .step_size_converge_tol(t.step_size_converge_tol)
+      .mass_converge_tol(t.mass_converge_tol)
+      .mass_init_count(t.mass_init_count)
+      .mass_additive_smoothing(t.mass_additive_smoothing)
+      .max_macro_steps_target(t.max_macro_steps_target)
+      .step_accept_rate_target(t.step_accept_rate_target)
+      .step_learning_rate(t.step_learning_rate)
+      .step_gradient_decay(t.step_gradient_decay)
+      .step_sq_gradient_decay(t.step_sq_gradient_decay)
+      .step_stabilization(t.step_stabilization)
+      .step_learn_rate_decay(t.step_learn_rate_decay)
+      .build();
+  SamplingConfigBuilder()
+      .min_max_iter(t.min_sampling_iter, t.max_sampling_iter)
+      .rhat_converge_tol(t.rhat_converge_tol)
+      .max_trajectory_doublings(t.max_trajectory_doublings)
+      .max_step_halvings(t.max_step_halvings)
+      .max_hamiltonian_error(t.max_hamiltonian_error)
+      .min_micro_steps(static_cast<std::size_t>(std::max(t.min_micro_steps, 0)))
+      .build();
+  // WalnutsSampler's own checks (walnuts.hpp:654-659)
+  validate::positive(static_cast<std::size_t>(std::max(t.max_trajectory_doublings, 0)),
+                     "max_nuts_depth");
+  validate::positive(static_cast<std::size_t>(std::max(t.max_step_halvings, 0)),
+                     "max_step_halvings");
+  if (t.max_trajectory_doublings > kMaxDepth) {
+    throw std::invalid_argument("max_trajectory_doublings above " +
+                                std::to_string(kMaxDepth) +
+                                " is not supported on the device");
+  }
+  validate::finite_positive(t.step_size_init, "step size");
+}
+
+}  // namespace wb200
+
+using namespace wb200;
+
+extern "C" {
+
+const char* walnuts_b200_version(void) { return "walnuts_b200 0.1.0 (sm_100a)"; }
+
+const char* walnutpie_get_error_message(const WalnutpyError* err) {
+  if (err == nullptr) return "Something went wrong: No error found";
+  return err->msg.c_str();
+}
+int walnutpie_get_error_type(const WalnutpyError* err) {
+  if (err == nullptr) return wb200_generic;
+  return err->type;
+}
+void walnutpie_destroy_error(WalnutpyError* err) { delete err; }
+char walnutpie_separator_char(void) { return '\x1C'; }
+
+void walnuts_b200_default_tuning(WalnutTuning* t) {
+  t->min_warmup_iter = 50; t->max_warmup_iter = 1000;
+  t->min_sampling_iter = 50; t->max_sampling_iter = 1000;
+  t->max_trajectory_doublings = 5; t->max_step_halvings = 5; t->min_micro_steps = 1;
+  t->max_hamiltonian_error = 0.5;
+  t->step_size_converge_tol = 0.1; t->mass_converge_tol = 1.0;
+  t->rhat_converge_tol = 1.01;
+  t->mass_init_count = 4.0; t->mass_additive_smoothing = 1e-5;
+  t->max_macro_steps_target = 15.0;
+  t->step_size_init = 1.0;
+  t->step_accept_rate_target = 0.8; t->step_learning_rate = 0.05;
+  t->step_gradient_decay = 0.8; t->step_sq_gradient_decay = 0.9;
+  t->step_stabilization = 1e-4; t->step_learn_rate_decay = 0.5;
+  t->publish_stride = 5;
+}
+
+// ------------------------------------------------------------- session ----
+int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
+                         unsigned int seed, unsigned int chain_offset,
+                         const WalnutTuning* tuning, int device,
+                         wb200_session** out, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    if (!model || !tuning || !out) throw std::invalid_argument("null argument");
+    if (num_chains < 1) throw std::invalid_argument("num_chains must be at least 1");
+    if (model->D < 1) throw std::invalid_argument("num_params must be at least 1");
+    validate_tuning(*tuning);
+    require_gpu();
+    WB200_CUDA(cudaSetDevice(device));
+    auto s = std::make_unique<wb200_session>();
+    s->device = device;
+    s->kind = model->kind;
+    s->D = model->D;
+    s->N = model->N;
+    s->ld = (model->D + 1) & ~1;  // even row stride: 16-byte aligned double2
+    s->C = static_cast<int>(num_chains);
+    s->seed = seed;
+    s->chain_offset = chain_offset;
+    s->tuning = *tuning;
+    if (s->tuning.publish_stride <= 0) s->tuning.publish_stride = 5;
+    s->shape = shape_for_dim(s->D);
+    WB200_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    WB200_CUDA(cudaEventCreate(&s->ev0));
+    WB200_CUDA(cudaEventCreate(&s->ev1));
+    const size_t CL = static_cast<size_t>(s->C) * s->ld;
+    s->theta.alloc(CL);
+    s->inv_mass.alloc(CL);
+    s->est.alloc(4 * CL);
+    s->sc.alloc(s->C);
+    s->ticket.alloc(1);
+    s->red.alloc(std::max<size_t>(s->C, s->D + 8));
+    WB200_CUDA(cudaMemsetAsync(s->theta.ptr, 0, CL * 8, s->stream));
+    WB200_CUDA(cudaMemsetAsync(s->inv_mass.ptr, 0, CL * 8, s->stream));
+    WB200_CUDA(cudaMemsetAsync(s->sc.ptr, 0, s->C * sizeof(ChainScalars), s->stream));
+    // target parameters
+    if (s->kind == kDiagGaussian) {
+      if (!model->data0) throw std::invalid_argument("diag_gaussian needs data0 = precision[D]");
+      const double* prec = static_cast<const double*>(model->data0);
+      for (int d = 0; d < s->D; ++d) {
+        if (!(std::isfinite(prec[d]) && prec[d] > 0)) {
+          throw std::invalid_argument("precision must be finite and > 0");
+        }
+      }
+      s->tparam.alloc(s->ld);
+      WB200_CUDA(cudaMemsetAsync(s->tparam.ptr, 0, s->ld * 8, s->stream));
+      WB200_CUDA(cudaMemcpyAsync(s->tparam.ptr, prec, s->D * 8,
+                                 cudaMemcpyHostToDevice, s->stream));
+    } else if (s->kind != kStdNormal && s->kind != kFunnel) {
+      throw std::invalid_argument("unsupported model kind for the device sampler");
+    }
+    if (s->kind == kFunnel && s->D < 2) {
+      throw std::invalid_argument("funnel needs num_params >= 2");
+    }
+    // slots: resident groups of the chain kernel
+    const int occ = occupancy_for(s->kind, s->shape);
+    int sms = 0;
+    WB200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int max_grid = occ * sms;
+    const int need = (s->C + s->shape.chains_per_cta - 1) / s->shape.chains_per_cta;
+    s->grid = std::min(max_grid, need);
+    s->slots = s->grid * s->shape.chains_per_cta;
+    const size_t stride =
+        static_cast<size_t>(scratch_vectors(s->tuning.max_trajectory_doublings)) * s->ld;
+    s->scratch.alloc(stride * s->slots);
+    WB200_CUDA(cudaMemsetAsync(s->scratch.ptr, 0, stride * s->slots * 8, s->stream));
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+    *out = s.release();
+  });
+}
+
+void wb200_session_destroy(wb200_session* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int wb200_session_init(wb200_session* s, const double* positions,
+                       double init_radius, const double* mass,
+                       const double* steps, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    const size_t C = s->C;
+    const int D = s->D;
+    if (positions) {
+      for (size_t i = 0; i < C * D; ++i) {
+        if (!std::isfinite(positions[i])) throw std::invalid_argument("positions must be finite");
+      }
+      upload_rows(s->theta.ptr, s->ld, positions, D, C, s->stream);
+    } else {
+      walnuts_b200::validate::finite_positive(init_radius, "init_scale");
+    }
+    if (mass) {
+      for (size_t i = 0; i < C * D; ++i) {
+        walnuts_b200::validate::finite_positive(mass[i], "masses");
+      }
+      upload_rows(s->inv_mass.ptr, s->ld, mass, D, C, s->stream);
+    }
+    if (steps) {
+      for (size_t i = 0; i < C; ++i) {
+        walnuts_b200::validate::finite_positive(steps[i], "step_size");
+      }
+      WB200_CUDA(cudaMemcpyAsync(s->red.ptr, steps, C * 8, cudaMemcpyHostToDevice,
+                                 s->stream));
+    }
+    launch_init(*s, mass != nullptr, steps != nullptr, positions != nullptr,
+                init_radius);
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+    s->initialised = true;
+    s->frozen = false;
+  });
+}
+
+int wb200_session_reserve_draws(wb200_session* s, long long capacity, int trace,
+                                WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    if (capacity < 0) throw std::invalid_argument("capacity must be non-negative");
+    const size_t rows = static_cast<size_t>(s->C) * capacity;
+    s->draws.alloc(rows * s->ld);
+    s->trace = trace != 0;
+    if (s->trace) {
+      s->lp_out.alloc(rows);
+      s->depth_out.alloc(rows);
+      s->step_out.alloc(rows);
+      s->im_out.alloc(rows * s->ld);
+    }
+    s->draw_cap = capacity;
+    s->rows_written = 0;
+  });
+}
+
+static void check_room(wb200_session* s, int n_iter, int store) {
+  if (!s->initialised) throw std::runtime_error("session is not initialised");
+  if (n_iter < 0) throw std::invalid_argument("n_iter must be non-negative");
+  if (store && s->rows_written + n_iter > s->draw_cap) {
+    throw std::runtime_error("draw buffer too small: reserve more capacity");
+  }
+}
+
+int wb200_session_warmup(wb200_session* s, int n_iter, int store, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    check_room(s, n_iter, store);
+    if (s->frozen) throw std::runtime_error("warm-up after freeze");
+    if (n_iter > 0) launch_chains(*s, n_iter, 1, store != 0);
+  });
+}
+
+int wb200_session_freeze(wb200_session* s, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    if (!s->initialised) throw std::runtime_error("session is not initialised");
+    launch_freeze(*s);
+    s->frozen = true;
+  });
+}
+
+int wb200_session_sample(wb200_session* s, int n_iter, int store, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    check_room(s, n_iter, store);
+    if (!s->frozen) throw std::runtime_error("sample before freeze");
+    if (n_iter > 0) launch_chains(*s, n_iter, 0, store != 0);
+  });
+}
+
+int wb200_session_sync(wb200_session* s, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+  });
+}
+
+int wb200_session_get_draws(wb200_session* s, long long first, long long count,
+                            double* out, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    if (first < 0 || count < 0 || first + count > s->rows_written) {
+      throw std::invalid_argument("draw range out of bounds");
+    }
+    for (int c = 0; c < s->C; ++c) {
+      download_rows(out + static_cast<size_t>(c) * count * s->D, s->D,
+                    s->draws.ptr + (static_cast<size_t>(c) * s->draw_cap + first) * s->ld,
+                    s->ld, count, s->stream);
+    }
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+  });
+}
+
+int wb200_session_get_trace(wb200_session* s, long long first, long long count,
+                            double* lp, int* depth, double* step, double* inv_mass,
+                            WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    if (!s->trace) throw std::runtime_error("session was reserved without trace");
+    if (first < 0 || count < 0 || first + count > s->rows_written) {
+      throw std::invalid_argument("trace range out of bounds");
+    }
+    for (int c = 0; c < s->C; ++c) {
+      const size_t src = static_cast<size_t>(c) * s->draw_cap + first;
+      const size_t dst = static_cast<size_t>(c) * count;
+      if (lp) WB200_CUDA(cudaMemcpyAsync(lp + dst, s->lp_out.ptr + src, count * 8,
+                                         cudaMemcpyDeviceToHost, s->stream));
+      if (depth) WB200_CUDA(cudaMemcpyAsync(depth + dst, s->depth_out.ptr + src, count * 4,
+                                            cudaMemcpyDeviceToHost, s->stream));
+      if (step) WB200_CUDA(cudaMemcpyAsync(step + dst, s->step_out.ptr + src, count * 8,
+                                           cudaMemcpyDeviceToHost, s->stream));
+      if (inv_mass) download_rows(inv_mass + dst * s->D, s->D,
+                                  s->im_out.ptr + src * s->ld, s->ld, count, s->stream);
+    }
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+  });
+}
+
+int wb200_session_get_state(wb200_session* s, double* theta, double* inv_mass,
+                            double* step, int* min_micro,
+                            unsigned long long* grad_evals, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    if (theta) download_rows(theta, s->D, s->theta.ptr, s->ld, s->C, s->stream);
+    if (inv_mass) download_rows(inv_mass, s->D, s->inv_mass.ptr, s->ld, s->C, s->stream);
+    std::vector<ChainScalars> h(s->C);
+    WB200_CUDA(cudaMemcpyAsync(h.data(), s->sc.ptr, s->C * sizeof(ChainScalars),
+                               cudaMemcpyDeviceToHost, s->stream));
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+    for (int c = 0; c < s->C; ++c) {
+      if (step) step[c] = s->frozen ? h[c].step : std::exp(h[c].adam_x);
+      if (min_micro) min_micro[c] = h[c].min_micro;
+      if (grad_evals) grad_evals[c] = h[c].grad_evals;
+    }
+  });
+}
+
+int wb200_session_device_draws(wb200_session* s, double** draws, long long* capacity,
+                               int* ld, long long* rows_written) {
+  if (!s) return -1;
+  if (draws) *draws = s->draws.ptr;
+  if (capacity) *capacity = s->draw_cap;
+  if (ld) *ld = s->ld;
+  if (rows_written) *rows_written = s->rows_written;
+  return 0;
+}
+
+int wb200_session_counters(wb200_session* s, unsigned long long* grad_evals,
+                           unsigned long long* macro_steps,
+                           unsigned long long* kernel_launches, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    std::vector<ChainScalars> h(s->C);
+    WB200_CUDA(cudaMemcpyAsync(h.data(), s->sc.ptr, s->C * sizeof(ChainScalars),
+                               cudaMemcpyDeviceToHost, s->stream));
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+    unsigned long long g = 0, m = 0;
+    for (const auto& c : h) { g += c.grad_evals; m += c.macro_steps; }
+    if (grad_evals) *grad_evals = g;
+    if (macro_steps) *macro_steps = m;
+    if (kernel_launches) *kernel_launches = s->launches;
+  });
+}
+
+int wb200_session_last_kernel_ms(wb200_session* s, float* ms) {
+  if (!s || !ms) return -1;
+  cudaSetDevice(s->device);
+  if (cudaEventSynchronize(s->ev1) != cudaSuccess) return -1;
+  return cudaEventElapsedTime(ms, s->ev0, s->ev1) == cudaSuccess ? 0 : -1;
+}
+
+// ---------------------------------------------------------------- orbit ----
+int wb200_orbit(const WalnutModelDesc* model, size_t num_chains,
+                const double* theta, const double* rho, const double* inv_mass,
+                double step, int num_steps, double* theta_out, double* rho_out,
+                double* grad_out, double* logp_out, double* joint_out,
+                WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    require_gpu();
+    const int D = model->D, ld = (D + 1) & ~1;
+    const size_t C = num_chains, CL = C * ld;
+    DeviceBuffer<double> th, rh, im, g, lp, jt, tp;
+    th.alloc(CL); rh.alloc(CL); im.alloc(CL); g.alloc(CL); lp.alloc(C); jt.alloc(C);
+    cudaStream_t st = nullptr;
+    WB200_CUDA(cudaMemset(th.ptr, 0, CL * 8));
+    WB200_CUDA(cudaMemset(rh.ptr, 0, CL * 8));
+    WB200_CUDA(cudaMemset(im.ptr, 0, CL * 8));
+    upload_rows(th.ptr, ld, theta, D, C, st);
+    upload_rows(rh.ptr, ld, rho, D, C, st);
+    upload_rows(im.ptr, ld, inv_mass, D, C, st);
+    if (model->kind == kDiagGaussian) {
+      tp.alloc(ld);
+      WB200_CUDA(cudaMemset(tp.ptr, 0, ld * 8));
+      WB200_CUDA(cudaMemcpy(tp.ptr, model->data0, D * 8, cudaMemcpyHostToDevice));
+    }
+    launch_orbit(model->kind, D, ld, static_cast<int>(C), tp.ptr, th.ptr, rh.ptr,
+                 im.ptr, g.ptr, lp.ptr, jt.ptr, step, num_steps, st);
+    download_rows(theta_out, D, th.ptr, ld, C, st);
+    download_rows(rho_out, D, rh.ptr, ld, C, st);
+    download_rows(grad_out, D, g.ptr, ld, C, st);
+    WB200_CUDA(cudaMemcpy(logp_out, lp.ptr, C * 8, cudaMemcpyDeviceToHost));
+    WB200_CUDA(cudaMemcpy(joint_out, jt.ptr, C * 8, cudaMemcpyDeviceToHost));
+    WB200_CUDA(cudaDeviceSynchronize());
+  });
+}
+
+int walnutpie_sample_cfunc(
+    LOGP_CFUNC, void*, int, const double*, size_t, unsigned int, unsigned int,
+    double, const double*, int, int, int, int, int, int, int, double, double,
+    double, double, double, double, double, double, double, double, double,
+    double, double, double, bool, double*, size_t, int*, double*, double*, int,
+    PRINT_CALLBACK, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    throw std::runtime_error(
+        "walnuts_b200 runs device-resident models only: a host LOGP_CFUNC cannot "
+        "feed a GPU batch. Describe the model with WalnutModelDesc and call "
+        "walnutpie_sample_device (same trailing arguments).");
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,683 @@
+// Chain-resident WALNUTS transition kernel for sm_100a.
+//
+// One group of T threads (a warp for D <= 128, a whole CTA above) owns one
+// Markov chain for a whole launch: the live integrator state (theta, rho,
+// grad), the macro-step start state, the inverse mass and the target's
+// parameters stay in REGISTERS across every leapfrog micro-step, the
+// within-orbit step-halving ladder, the reversibility ladder and the iterative
+// orbit doubling.  Only the per-leaf tree bookkeeping (span ends, sub-tree
+// checkpoints, selected state) goes through a per-slot scratch area that is
+// sized to live in the 126 MB L2.  Chains are handed out by an atomic ticket so
+// long and short orbits balance across the 148 SMs; there is no lane divergence
+// between chains because a chain never shares a warp.
+//
+// Reference semantics (all file:line relative to /root/reference/include/walnutpie):
+//   transition_w walnuts.hpp:520-563 | build_span (recursion -> binary-counter
+//   carry loop) :464-495 | build_leaf :420-442 | macro_step
+//   :307-345 | reversible :254-279 | within_tolerance :218-235 | uturn :192-201
+//   | combine :368-387 | AdaptiveWalnuts::operator() adaptive_walnuts.hpp:234-251
+//   | MassEstimator :25-105 | MinMicroStepsAdaptHandler :119-164 | Adam
+//   adam.hpp:70-93 | OnlineMoments::observe online_moments.hpp:185-191 |
+//   WelfordAccumulator :34-70 (sampler.hpp:87-92).
+//
+// Arithmetic is written with explicit __dmul_rn/__dadd_rn in the order of the
+// reference expressions, so element-wise results equal the CPU oracle's bit for
+// bit; only cross-element sums (logp, kinetic energy, U-turn dots) differ, by
+// summation order.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "philox.cuh"
+
+namespace wb200 {
+
+constexpr int kMaxDepth = 12;  // max_trajectory_doublings supported on device
+
+enum TargetKind : int { kStdNormal = 0, kDiagGaussian = 1, kFunnel = 2,
+                        kLogistic = 3 };
+
+// persistent per-chain scalars (SoA would not help: one group reads one record)
+struct ChainScalars {
+  // Adam on log step (adam.hpp:48-66)
+  double adam_x, adam_m, adam_v, adam_t, adam_b1p, adam_b2p;
+  // min-micro controller (adaptive_walnuts.hpp:127-132)
+  double mm_total, mm_count;
+  // shared weight of the two discounted Welford estimators
+  double est_w;
+  // Welford of lp for the sampling R-hat (online_moments.hpp:34-70)
+  double lp_mean, lp_m2;
+  // frozen tuning used by sampling (adaptive_walnuts.hpp:263-271)
+  double step;
+  double last_lp;
+  unsigned long long lp_n;
+  unsigned long long grad_evals;
+  unsigned long long macro_steps;   // leaves attempted
+  unsigned long long rung_sum;      // sum of accepted rung indices (diagnostic)
+  unsigned int iter;       // global transition index (Philox addressing)
+  unsigned int warm_iter;  // AdaptiveWalnuts::iteration_
+  int min_micro;
+  int last_depth;
+};
+
+struct ChainParams {
+  int C, D, ld;
+  int n_iter;
+  int adapt;
+  int max_depth, max_halvings, min_micro_cfg;
+  double max_error;
+  double mass_init_count, macro_target;
+  double adam_target, adam_lr, adam_b1, adam_b2, adam_eps, adam_decay;
+  uint32_t seed, chain_offset;
+  double* theta;        // [C][ld]
+  double* inv_mass;     // [C][ld]  fixed metric used when adapt == 0
+  double* est;          // [C][4][ld]  mu_draw, S_draw, mu_score, S_score
+  ChainScalars* sc;     // [C]
+  double* draws;        // nullable [C][draw_cap][ld]
+  long long draw_cap;
+  long long draw_base;  // first row written by this launch
+  double* lp_out;       // nullable [C][draw_cap]
+  int* depth_out;       // nullable [C][draw_cap]
+  double* step_out;     // nullable [C][draw_cap]  step AFTER the iteration (on_warmup)
+  double* im_out;       // nullable [C][draw_cap][ld]  metric used (on_warmup)
+  double* scratch;      // [slots][nvec][ld]
+  long long scratch_stride;
+  unsigned int* ticket;
+  const double* tparam; // target parameters (e.g. precision[ld])
+};
+
+// scratch vector indices
+enum : int { A_TH_BK = 0, A_RHO_BK, A_G_BK, A_TH_FW, A_RHO_FW, A_G_FW, A_SEL,
+             E_TH, E_RHO, E_G, ST_BASE };
+enum : int { ST_THF = 0, ST_RHOF = 1, ST_SEL = 2 };
+__host__ __device__ inline int scratch_vectors(int max_depth) {
+  return ST_BASE + 3 * max_depth;
+}
+
+// ---------------------------------------------------------------------------
+// T cooperating threads; sums are bitwise identical in every thread.
+template <int T>
+struct Group {
+  static constexpr int W = T / 32;
+  int tid, lane, warp;
+  double* red;  // shared, [2][W][4] when W > 1
+  int parity;
+
+  template <int N>
+  __device__ __forceinline__ void sum(double (&v)[N]) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        v[n] += __shfl_xor_sync(0xffffffffu, v[n], m);
+      }
+    }
+    if constexpr (W > 1) {
+      double* buf = red + parity * (W * 4);
+      if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) buf[warp * 4 + n] = v[n];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        double s = buf[n];
+#pragma unroll
+        for (int w = 1; w < W; ++w) s += buf[w * 4 + n];
+        v[n] = s;
+      }
+      parity ^= 1;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+template <int T, int K>
+struct Vec {
+  // element pair owned by this thread in chunk k: 2*(tid + k*T), +1
+  __device__ __forceinline__ static void load(const double* row, int ld, int tid,
+                                              double (&x)[K][2]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      int e = 2 * (tid + k * T);
+      if (e < ld) {
+        double2 v = *reinterpret_cast<const double2*>(row + e);
+        x[k][0] = v.x; x[k][1] = v.y;
+      } else {
+        x[k][0] = 0.0; x[k][1] = 0.0;
+      }
+    }
+  }
+  __device__ __forceinline__ static void store(double* row, int ld, int tid,
+                                               const double (&x)[K][2]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      int e = 2 * (tid + k * T);
+      if (e < ld) {
+        *reinterpret_cast<double2*>(row + e) = make_double2(x[k][0], x[k][1]);
+      }
+    }
+  }
+  __device__ __forceinline__ static void copy(double (&dst)[K][2],
+                                              const double (&src)[K][2]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) { dst[k][0] = src[k][0]; dst[k][1] = src[k][1]; }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Targets.  grad() fills g and a per-thread partial `lp_part` whose group sum
+// is logp (so Gaussians need no reduction inside a micro-step).
+template <int T, int K>
+struct StdNormalTarget {  // examples/walnutpie_api.cpp:39-43
+  __device__ __forceinline__ void init(const ChainParams&, int) {}
+  __device__ __forceinline__ void grad(const double (&th)[K][2], double (&g)[K][2],
+                                       double& lp_part, Group<T>&) const {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        s = __dadd_rn(s, __dmul_rn(th[k][v], th[k][v]));
+        g[k][v] = -th[k][v];
+      }
+    }
+    lp_part = -0.5 * s;
+  }
+};
+
+template <int T, int K>
+struct DiagGaussianTarget {  // generalises examples/examples.cpp:20-31
+  double prec[K][2];
+  __device__ __forceinline__ void init(const ChainParams& p, int tid) {
+    Vec<T, K>::load(p.tparam, p.ld, tid, prec);
+  }
+  __device__ __forceinline__ void grad(const double (&th)[K][2], double (&g)[K][2],
+                                       double& lp_part, Group<T>&) const {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        double t = __dmul_rn(th[k][v], prec[k][v]);
+        s = __dadd_rn(s, __dmul_rn(th[k][v], t));
+        g[k][v] = -t;
+      }
+    }
+    lp_part = -0.5 * s;
+  }
+};
+
+template <int T, int K>
+struct FunnelTarget {
+  double half_dm1;
+  bool owner;  // owns element 0 (v)
+  __device__ __forceinline__ void init(const ChainParams& p, int tid) {
+    half_dm1 = 0.5 * static_cast<double>(p.D - 1);
+    owner = (tid == 0);
+  }
+  __device__ __forceinline__ void grad(const double (&th)[K][2], double (&g)[K][2],
+                                       double& lp_part, Group<T>& grp) const {
+    double ss = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        bool is_v = owner && k == 0 && v == 0;
+        ss = __dadd_rn(ss, is_v ? 0.0 : __dmul_rn(th[k][v], th[k][v]));
+      }
+    }
+    double r[2] = {ss, owner ? th[0][0] : 0.0};
+    grp.sum(r);
+    const double v0 = r[1];
+    const double ev = exp(-v0);
+    const double q = __dmul_rn(__dmul_rn(0.5, ev), r[0]);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) g[k][v] = -__dmul_rn(th[k][v], ev);
+    }
+    if (owner) {
+      double lp = __dadd_rn(__dadd_rn(-__dmul_rn(v0, v0) / 18.0,
+                                      -__dmul_rn(half_dm1, v0)), -q);
+      g[0][0] = __dadd_rn(__dadd_rn(-v0 / 9.0, -half_dm1), q);
+      lp_part = lp;
+    } else {
+      lp_part = 0.0;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double log_sum_exp2(double x1, double x2) {
+  // util.hpp:174-183
+  double m = fmax(x1, x2);
+  if (isnan(x1) || isnan(x2)) return nan("");
+  if (isinf(m) || isnan(x1 + x2)) return fmax(x1, x2);
+  return m + log(exp(x1 - m) + exp(x2 - m));
+}
+
+__device__ __forceinline__ void adam_update(ChainScalars& sc, const ChainParams& p,
+                                            double alpha) {
+  // adam.hpp:70-86
+  sc.adam_t += 1.0;
+  sc.adam_b1p *= p.adam_b1;
+  sc.adam_b2p *= p.adam_b2;
+  double grad = p.adam_target - alpha;
+  sc.adam_m = p.adam_b1 * sc.adam_m + (1 - p.adam_b1) * grad;
+  sc.adam_v = p.adam_b2 * sc.adam_v + (1 - p.adam_b2) * grad * grad;
+  double m_hat = sc.adam_m / (1 - sc.adam_b1p);
+  double v_hat = sc.adam_v / (1 - sc.adam_b2p);
+  double decayed = p.adam_lr / pow(sc.adam_t, p.adam_decay);
+  double denom = sqrt(v_hat) + p.adam_eps;
+  sc.adam_x -= decayed * m_hat / denom;
+}
+
+__device__ __forceinline__ int min_micro_steps(const ChainScalars& sc,
+                                               const ChainParams& p) {
+  // adaptive_walnuts.hpp:152-157
+  double mean_micro = sc.mm_total / sc.mm_count;
+  long long r = llround(mean_micro / p.macro_target);
+  long long c = p.min_micro_cfg;
+  return static_cast<int>(r > c ? r : c);
+}
+
+// ---------------------------------------------------------------------------
+template <class Target, int T, int K>
+struct ChainRunner {
+  using V = Vec<T, K>;
+  const ChainParams& p;
+  Group<T>& grp;
+  Target tgt;
+  double* scr;   // this slot's scratch
+  int ld, tid;
+  // registers
+  double th[K][2], rho[K][2], g[K][2];
+  double ths[K][2], rhos[K][2], gs[K][2];
+  double im[K][2];
+  ChainScalars sc;
+  unsigned long long evals;
+
+  __device__ ChainRunner(const ChainParams& p_, Group<T>& grp_, double* scr_)
+      : p(p_), grp(grp_), scr(scr_), ld(p_.ld), tid(grp_.tid) {}
+
+  __device__ __forceinline__ double* sv(int v) const {
+    return scr + static_cast<long long>(v) * ld;
+  }
+
+  // one leapfrog micro-step, walnuts.hpp:329-332
+  __device__ __forceinline__ void leapfrog(double h, double hh, double& lp_part) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        rho[k][v] = __dadd_rn(rho[k][v], __dmul_rn(hh, g[k][v]));
+        th[k][v] = __dadd_rn(th[k][v],
+                             __dmul_rn(__dmul_rn(h, im[k][v]), rho[k][v]));
+      }
+    }
+    tgt.grad(th, g, lp_part, grp);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        rho[k][v] = __dadd_rn(rho[k][v], __dmul_rn(hh, g[k][v]));
+      }
+    }
+  }
+
+  // n micro-steps from the live state; returns logp and joint (util.hpp:220-223)
+  __device__ __forceinline__ void integrate(int n, double h, double& lp, double& H) {
+    const double hh = 0.5 * h;
+    double lp_part = 0.0;
+    for (int j = 0; j < n; ++j) leapfrog(h, hh, lp_part);
+    evals += static_cast<unsigned long long>(n);
+    double kin = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        kin = __dadd_rn(kin, __dmul_rn(im[k][v], __dmul_rn(rho[k][v], rho[k][v])));
+      }
+    }
+    double r[2] = {lp_part, kin};
+    grp.sum(r);
+    lp = r[0];
+    H = r[0] + (-0.5 * r[1]);
+  }
+
+  // macro_step (:307-345) + reversible (:254-279) from (ths, rhos, gs, Hs).
+  // On success the new leaf is in (th, rho, g) with (lpn, Hn).
+  __device__ __forceinline__ bool macro_step(int dir, double step, int min_micro, double Hs,
+                             double& lpn, double& Hn) {
+    double h = dir > 0 ? step : -step;
+    int n = min_micro;
+    for (int rung = 0; rung < p.max_halvings; ++rung, n *= 2, h *= 0.5) {
+      V::copy(th, ths); V::copy(rho, rhos); V::copy(g, gs);
+      integrate(n, h, lpn, Hn);
+      if (rung == 0 && p.adapt) adam_update(sc, p, exp(-fabs(Hs - Hn)));
+      if (fabs(Hs - Hn) <= p.max_error) {
+        sc.rung_sum += rung;
+        if (n == 1 || n < 2 * min_micro) return true;
+        // reversibility ladder: coarser rungs must NOT be acceptable from the end
+        V::store(sv(E_TH), ld, tid, th);
+        V::store(sv(E_RHO), ld, tid, rho);
+        V::store(sv(E_G), ld, tid, g);
+        int rn = n;
+        double rh = h;
+        bool first = true;
+        while (rn >= 2 * min_micro) {
+          rn /= 2;
+          rh *= 2;
+          if (!first) {
+            V::load(sv(E_TH), ld, tid, th);
+            V::load(sv(E_RHO), ld, tid, rho);
+            V::load(sv(E_G), ld, tid, g);
+          }
+          first = false;
+#pragma unroll
+          for (int k = 0; k < K; ++k) { rho[k][0] = -rho[k][0]; rho[k][1] = -rho[k][1]; }
+          double lp2, H2;
+          integrate(rn, rh, lp2, H2);
+          if (fabs(H2 - Hn) <= p.max_error) return false;  // irreversible
+        }
+        V::load(sv(E_TH), ld, tid, th);
+        V::load(sv(E_RHO), ld, tid, rho);
+        V::load(sv(E_G), ld, tid, g);
+        return true;
+      }
+    }
+    return false;
+  }
+
+  // uturn (:192-201) between the far state F (in scratch) and the newest leaf
+  // L = (ths, rhos); dir gives the time order.
+  __device__ __forceinline__ bool uturn(const double* thF_row, const double* rhoF_row,
+                                        int dir) {
+    double thF[K][2], rhoF[K][2];
+    V::load(thF_row, ld, tid, thF);
+    V::load(rhoF_row, ld, tid, rhoF);
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        double sd = __dmul_rn(im[k][v], __dadd_rn(ths[k][v], -thF[k][v]));
+        a = __dadd_rn(a, __dmul_rn(rhos[k][v], sd));
+        b = __dadd_rn(b, __dmul_rn(rhoF[k][v], sd));
+      }
+    }
+    double r[2] = {a, b};
+    grp.sum(r);
+    if (dir < 0) { r[0] = -r[0]; r[1] = -r[1]; }
+    return r[0] < 0 || r[1] < 0;
+  }
+
+  __device__ __forceinline__ void run(int chain) {
+    const uint32_t gchain = p.chain_offset + static_cast<uint32_t>(chain);
+    sc = p.sc[chain];
+    evals = 0;
+    tgt.init(p, tid);
+    double* theta_row = p.theta + static_cast<long long>(chain) * ld;
+    double* est_row = p.est + static_cast<long long>(chain) * 4 * ld;
+    double cur[K][2];  // current position of the chain
+    V::load(theta_row, ld, tid, cur);
+    if (!p.adapt) V::load(p.inv_mass + static_cast<long long>(chain) * ld, ld, tid, im);
+
+    for (int it = 0; it < p.n_iter; ++it) {
+      const uint32_t iter = sc.iter;
+      uint32_t sctr = 0;
+      double step;
+      int min_micro;
+      // ---- metric, step, min-micro for this transition
+      if (p.adapt) {
+        double Sd[K][2], Ss[K][2];
+        V::load(est_row + 1 * ld, ld, tid, Sd);
+        V::load(est_row + 3 * ld, ld, tid, Ss);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            // MassEstimator::inv_mass_estimate, adaptive_walnuts.hpp:89-94
+            im[k][v] = sqrt((Sd[k][v] / sc.est_w) / (Ss[k][v] / sc.est_w));
+          }
+        }
+        step = exp(sc.adam_x);
+        min_micro = min_micro_steps(sc, p);
+      } else {
+        step = sc.step;
+        min_micro = sc.min_micro;
+      }
+      const long long row = p.draw_base + it;
+      if (p.im_out) {
+        V::store(p.im_out + (static_cast<long long>(chain) * p.draw_cap + row) * ld,
+                 ld, tid, im);
+      }
+      // ---- momentum refresh rho = chol_mass * z  (walnuts.hpp:528-529)
+      V::copy(th, cur);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int j = tid + k * T;
+        double z0 = 0.0, z1 = 0.0;
+        if (2 * j < p.D) {
+          philox_normal_pair(p.seed, gchain, iter, kKindNormal, j, z0, z1);
+          if (2 * j + 1 >= p.D) z1 = 0.0;
+        }
+        // adaptive: inverse().sqrt() (adaptive_walnuts.hpp:236);
+        // fixed:    sqrt().inverse() (walnuts.hpp:647)
+        double c0 = p.adapt ? sqrt(1.0 / im[k][0]) : 1.0 / sqrt(im[k][0]);
+        double c1 = p.adapt ? sqrt(1.0 / im[k][1]) : 1.0 / sqrt(im[k][1]);
+        rho[k][0] = __dmul_rn(c0, z0);
+        rho[k][1] = __dmul_rn(c1, z1);
+      }
+      // ---- initial point (walnuts.hpp:532-535)
+      double lp0, H0;
+      {
+        double lp_part;
+        tgt.grad(th, g, lp_part, grp);
+        evals += 1;
+        double kin = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            kin = __dadd_rn(kin, __dmul_rn(im[k][v], __dmul_rn(rho[k][v], rho[k][v])));
+          }
+        }
+        double r[2] = {lp_part, kin};
+        grp.sum(r);
+        lp0 = r[0];
+        H0 = r[0] + (-0.5 * r[1]);
+      }
+      V::store(sv(A_TH_BK), ld, tid, th);  V::store(sv(A_TH_FW), ld, tid, th);
+      V::store(sv(A_RHO_BK), ld, tid, rho); V::store(sv(A_RHO_FW), ld, tid, rho);
+      V::store(sv(A_G_BK), ld, tid, g);    V::store(sv(A_G_FW), ld, tid, g);
+      V::store(sv(A_SEL), ld, tid, th);
+      double H_bk = H0, H_fw = H0, logW = H0, lp_sel = lp0;
+      V::copy(ths, th); V::copy(rhos, rho); V::copy(gs, g);
+      int regs_dir = 0;  // 0: (ths..) equals both ends; +-1: equals that end only
+      bool first_ext = true;
+
+      double st_logW[kMaxDepth], st_lp[kMaxDepth];
+      int depth;
+      for (depth = 1; depth <= p.max_depth; ++depth) {
+        const bool fwd = philox_bit(p.seed, gchain, iter, sctr++);  // :552
+        const int dir = fwd ? 1 : -1;
+        if (!first_ext && regs_dir != dir) {
+          const int b = fwd ? A_TH_FW : A_TH_BK;
+          V::load(sv(b), ld, tid, ths);
+          V::load(sv(b + 1), ld, tid, rhos);
+          V::load(sv(b + 2), ld, tid, gs);
+        }
+        first_ext = false;
+        double Hs = fwd ? H_fw : H_bk;
+        // ---- build_span(depth-1): 2^(depth-1) leaves, binary-counter merges
+        const int nleaf = 1 << (depth - 1);
+        int sp = 0;
+        bool ok = true;
+        for (int i = 0; i < nleaf; ++i) {
+          double lpn, Hn;
+          sc.macro_steps += 1;
+          ok = macro_step(dir, step, min_micro, Hs, lpn, Hn);
+          if (!ok) break;
+          V::copy(ths, th); V::copy(rhos, rho); V::copy(gs, g);
+          Hs = Hn;
+          double cur_logW = Hn, cur_lp = lpn;
+          int cur_sel = -1;  // -1: the selection is the newest leaf (registers)
+          const int nm = __ffs(~i) - 1;  // trailing one bits of i
+          for (int m = 0; m < nm; ++m) {
+            const int s = sp - 1;
+            const int sb = ST_BASE + 3 * s;
+            if (uturn(sv(sb + ST_THF), sv(sb + ST_RHOF), dir)) { ok = false; break; }
+            // combine<Barker> (:368-387)
+            const double lw = log_sum_exp2(st_logW[s], cur_logW);
+            const double u = philox_uniform(p.seed, gchain, iter, sctr++);
+            const bool take_new = log(u) < cur_logW - lw;
+            if (take_new) {
+              if (cur_sel >= 0) {
+                double t[K][2];
+                V::load(sv(ST_BASE + 3 * cur_sel + ST_SEL), ld, tid, t);
+                V::store(sv(sb + ST_SEL), ld, tid, t);
+                cur_sel = s;
+              }
+            } else {
+              cur_sel = s;
+              cur_lp = st_lp[s];
+            }
+            cur_logW = lw;
+            sp = s;
+          }
+          if (!ok) break;
+          const int sb = ST_BASE + 3 * sp;
+          if (nm == 0) {
+            V::store(sv(sb + ST_THF), ld, tid, ths);
+            V::store(sv(sb + ST_RHOF), ld, tid, rhos);
+          }
+          if (cur_sel < 0) V::store(sv(sb + ST_SEL), ld, tid, ths);
+          st_logW[sp] = cur_logW;
+          st_lp[sp] = cur_lp;
+          ++sp;
+        }
+        if (!ok) break;  // extension rejected, span unchanged (:543-545)
+        // ---- top level: U-turn across the whole span, then Metropolis merge
+        const int farb = fwd ? A_TH_BK : A_TH_FW;
+        const bool ut = uturn(sv(farb), sv(farb + 1), dir);  // :546
+        const double sub_logW = st_logW[0];
+        const double lw = log_sum_exp2(logW, sub_logW);
+        const double u = philox_uniform(p.seed, gchain, iter, sctr++);
+        const bool take = log(u) < sub_logW - logW;  // Metropolis (:372-378)
+        if (take) {
+          double t[K][2];
+          V::load(sv(ST_BASE + ST_SEL), ld, tid, t);
+          V::store(sv(A_SEL), ld, tid, t);
+          lp_sel = st_lp[0];
+        }
+        const int nb = fwd ? A_TH_FW : A_TH_BK;
+        V::store(sv(nb), ld, tid, ths);
+        V::store(sv(nb + 1), ld, tid, rhos);
+        V::store(sv(nb + 2), ld, tid, gs);
+        if (fwd) H_fw = Hs; else H_bk = Hs;
+        logW = lw;
+        regs_dir = dir;
+        if (ut) break;  // :556-558
+      }
+      // ---- the draw
+      V::load(sv(A_SEL), ld, tid, cur);
+      if (p.adapt) {
+        // AdaptiveWalnuts::operator() tail, adaptive_walnuts.hpp:247-250
+        double gsel[K][2], lp_dummy;
+        tgt.grad(cur, gsel, lp_dummy, grp);  // grad_select (cached by the reference)
+        const double gamma =
+            1.0 - 1.0 / (p.mass_init_count + static_cast<double>(sc.warm_iter));
+        sc.est_w = gamma * sc.est_w + 1.0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double mu[K][2], S[K][2];
+          V::load(est_row + (2 * e) * ld, ld, tid, mu);
+          V::load(est_row + (2 * e + 1) * ld, ld, tid, S);
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              const double y = e == 0 ? cur[k][v] : gsel[k][v];
+              // online_moments.hpp:185-191 (both factors see the updated mean)
+              mu[k][v] = __dadd_rn(mu[k][v], __dadd_rn(y, -mu[k][v]) / sc.est_w);
+              const double d = __dadd_rn(y, -mu[k][v]);
+              S[k][v] = __dadd_rn(__dmul_rn(gamma, S[k][v]), __dmul_rn(d, d));
+            }
+          }
+          V::store(est_row + (2 * e) * ld, ld, tid, mu);
+          V::store(est_row + (2 * e + 1) * ld, ld, tid, S);
+        }
+        sc.mm_total += static_cast<double>(1ull << depth);
+        sc.mm_count += 1.0;
+        sc.warm_iter += 1;
+      } else {
+        // WelfordAccumulator::observe (sampler.hpp:87-88)
+        sc.lp_n += 1;
+        const double delta = lp_sel - sc.lp_mean;
+        sc.lp_mean += delta / static_cast<double>(sc.lp_n);
+        sc.lp_m2 += delta * (lp_sel - sc.lp_mean);
+      }
+      sc.iter += 1;
+      sc.last_depth = depth;
+      sc.last_lp = lp_sel;
+      if (p.draws) {
+        V::store(p.draws + (static_cast<long long>(chain) * p.draw_cap + row) * ld,
+                 ld, tid, cur);
+      }
+      if (tid == 0) {
+        const long long o = static_cast<long long>(chain) * p.draw_cap + row;
+        if (p.lp_out) p.lp_out[o] = lp_sel;
+        if (p.depth_out) p.depth_out[o] = depth;
+        if (p.step_out) p.step_out[o] = p.adapt ? exp(sc.adam_x) : sc.step;
+      }
+    }
+    V::store(theta_row, ld, tid, cur);
+    sc.grad_evals += evals;
+    if (tid == 0) p.sc[chain] = sc;
+  }
+};
+
+// ---------------------------------------------------------------------------
+template <class Target, int T, int K, int CTA>
+__global__ void __launch_bounds__(CTA)
+walnuts_chain_kernel(const ChainParams p) {
+  constexpr int W = T / 32;
+  __shared__ double red_smem[(W > 1) ? 2 * W * 4 : 1];
+  __shared__ int next_chain;
+  Group<T> grp;
+  grp.lane = threadIdx.x & 31;
+  grp.red = red_smem;
+  grp.parity = 0;
+  int slot;
+  if constexpr (T == 32) {
+    grp.tid = grp.lane;
+    grp.warp = 0;
+    slot = blockIdx.x * (CTA / 32) + (threadIdx.x >> 5);
+  } else {
+    static_assert(T == 32 || CTA == T, "one chain per CTA above one warp");
+    grp.tid = threadIdx.x;
+    grp.warp = threadIdx.x >> 5;
+    slot = blockIdx.x;
+  }
+  double* scr = p.scratch + static_cast<long long>(slot) * p.scratch_stride;
+  ChainRunner<Target, T, K> runner(p, grp, scr);
+  while (true) {
+    int chain;
+    if constexpr (T == 32) {
+      chain = 0;
+      if (grp.lane == 0) chain = static_cast<int>(atomicAdd(p.ticket, 1u));
+      chain = __shfl_sync(0xffffffffu, chain, 0);
+    } else {
+      if (threadIdx.x == 0) next_chain = static_cast<int>(atomicAdd(p.ticket, 1u));
+      __syncthreads();
+      chain = next_chain;
+      __syncthreads();
+    }
+    if (chain >= p.C) break;
+    runner.run(chain);
+  }
+}
+
+}  // namespace wb200

@@ -1,0 +1,354 @@
+// Cross-chain controllers and the one-shot entry point.
+//
+// Reference: the warm-up controller adapt.hpp:173-229 and the sampling
+// controller sampler.hpp:118-158 poll lock-free per-chain snapshots from a host
+// thread.  Here the per-chain statistics are reduced on the device and only a
+// few scalars cross PCIe per check; with several GPUs the per-GPU sums are the
+// payload of one NCCL all-reduce (done by the caller between the two phases).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../host/config.hpp"
+#include "engine.cuh"
+
+namespace wb200 {
+
+// sums[d] = sum_c log M_c[d]; sums[D] = sum_c log eps_c; sums[D+1] = C.
+// One thread per dimension walks the chains in ascending order, so a single-GPU
+// result equals the reference's sequential accumulation (adapt.hpp:195-206).
+__global__ void warmup_sums_kernel(ChainParams p, double* sums) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < p.D) {
+    double acc = 0.0;
+    for (int c = 0; c < p.C; ++c) {
+      const double* est_row = p.est + static_cast<long long>(c) * 4 * p.ld;
+      const double w = p.sc[c].est_w;
+      const double im = sqrt((est_row[1 * p.ld + d] / w) / (est_row[3 * p.ld + d] / w));
+      acc += -log(im);  // AdaptiveWalnuts::log_mass, adaptive_walnuts.hpp:320-323
+    }
+    sums[d] = acc;
+  }
+  if (d == 0) {
+    double acc = 0.0;
+    for (int c = 0; c < p.C; ++c) acc += log(exp(p.sc[c].adam_x));  // :312
+    sums[p.D] = acc;
+    sums[p.D + 1] = static_cast<double>(p.C);
+  }
+}
+
+__device__ __forceinline__ void atomic_fmax_nonneg(double* addr, double v) {
+  // std::fmax against a running maximum that starts at 0.0 (adapt.hpp:209-217):
+  // NaN and negative candidates never win
+  if (v > 0.0) {
+    atomicMax(reinterpret_cast<unsigned long long*>(addr),
+              static_cast<unsigned long long>(__double_as_longlong(v)));
+  }
+}
+
+// out[0] = max_c ||(M_c - gm)/gm||_2, out[1] = max_c (eps_c - gs)/gs
+__global__ void warmup_deviation_kernel(ChainParams p, const double* sums,
+                                        double* out) {
+  __shared__ double red[32];
+  const int c = blockIdx.x;
+  const double count = sums[p.D + 1];
+  const double* est_row = p.est + static_cast<long long>(c) * 4 * p.ld;
+  const double w = p.sc[c].est_w;
+  double acc = 0.0;
+  for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
+    const double gm = exp(sums[d] / count);
+    const double im = sqrt((est_row[1 * p.ld + d] / w) / (est_row[3 * p.ld + d] / w));
+    const double mass = exp(-log(im));  // snap.mass = exp(log_mass), adapt.hpp:137
+    const double r = (mass - gm) / gm;
+    acc += r * r;
+  }
+  for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < (blockDim.x + 31) / 32; ++i) s += red[i];
+    atomic_fmax_nonneg(out + 0, sqrt(s));
+    const double gs = exp(sums[p.D] / count);
+    const double step = exp(log(exp(p.sc[c].adam_x)));
+    atomic_fmax_nonneg(out + 1, (step - gs) / gs);
+  }
+}
+
+// per-chain (mean, unbiased variance, count) of lp -> pinned-size arrays
+__global__ void lp_stats_kernel(ChainParams p, double* mean, double* var, double* cnt) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.C) return;
+  const ChainScalars& sc = p.sc[c];
+  mean[c] = sc.lp_mean;
+  var[c] = sc.lp_n > 1 ? sc.lp_m2 / static_cast<double>(sc.lp_n - 1) : nan("");
+  cnt[c] = static_cast<double>(sc.lp_n);
+}
+
+__global__ void philox_kernel(const uint32_t* in6, size_t n, uint32_t* out4) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* q = in6 + 6 * i;
+  Philox4 r = philox4x32_10(q[0], q[1], q[2], q[3], q[4], q[5]);
+  out4[4 * i + 0] = r.x; out4[4 * i + 1] = r.y; out4[4 * i + 2] = r.z; out4[4 * i + 3] = r.w;
+}
+
+__global__ void philox_normals_kernel(uint32_t seed, uint32_t chain, uint32_t iter,
+                                      uint32_t kind, size_t n, double* out) {
+  const size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (2 * j >= n) return;
+  double z0, z1;
+  philox_normal_pair(seed, chain, iter, kind, static_cast<uint32_t>(j), z0, z1);
+  out[2 * j] = z0;
+  if (2 * j + 1 < n) out[2 * j + 1] = z1;
+}
+
+}  // namespace wb200
+
+using namespace wb200;
+
+extern "C" {
+
+int wb200_session_warmup_sums(wb200_session* s, double* sums_device,
+                              WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    ChainParams p = s->params(0, 1, false);
+    warmup_sums_kernel<<<(s->D + 127) / 128, 128, 0, s->stream>>>(p, sums_device);
+    WB200_CUDA(cudaGetLastError());
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+    s->launches += 1;
+  });
+}
+
+int wb200_session_warmup_deviation(wb200_session* s, const double* sums_device,
+                                   double* out_host2, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    ChainParams p = s->params(0, 1, false);
+    double* out = s->red.ptr;  // 2 doubles of scratch
+    WB200_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(double), s->stream));
+    warmup_deviation_kernel<<<s->C, 256, 0, s->stream>>>(p, sums_device, out);
+    WB200_CUDA(cudaGetLastError());
+    WB200_CUDA(cudaMemcpyAsync(out_host2, out, 2 * sizeof(double),
+                               cudaMemcpyDeviceToHost, s->stream));
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+    s->launches += 1;
+  });
+}
+
+// {sum mu, sum mu^2, sum var, count of chains, min lp count} over local chains:
+// the payload of the sampling R-hat (sampler.hpp:132-151)
+int wb200_session_lp_moments(wb200_session* s, double* moments_host4,
+                             WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    ChainParams p = s->params(0, 0, false);
+    DeviceBuffer<double> buf;
+    buf.alloc(3 * static_cast<size_t>(s->C));
+    lp_stats_kernel<<<(s->C + 255) / 256, 256, 0, s->stream>>>(
+        p, buf.ptr, buf.ptr + s->C, buf.ptr + 2 * s->C);
+    WB200_CUDA(cudaGetLastError());
+    std::vector<double> h(3 * static_cast<size_t>(s->C));
+    WB200_CUDA(cudaMemcpyAsync(h.data(), buf.ptr, h.size() * 8, cudaMemcpyDeviceToHost,
+                               s->stream));
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+    s->launches += 1;
+    double sm = 0, sm2 = 0, sv = 0;
+    for (int c = 0; c < s->C; ++c) {
+      sm += h[c];
+      sm2 += h[c] * h[c];
+      sv += h[s->C + c];
+    }
+    moments_host4[0] = sm; moments_host4[1] = sm2; moments_host4[2] = sv;
+    moments_host4[3] = static_cast<double>(s->C);
+  });
+}
+
+int wb200_philox(const uint32_t* ctr_key6, size_t n, uint32_t* out4, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    DeviceBuffer<uint32_t> in, out;
+    in.alloc(6 * n); out.alloc(4 * n);
+    WB200_CUDA(cudaMemcpy(in.ptr, ctr_key6, 6 * n * 4, cudaMemcpyHostToDevice));
+    philox_kernel<<<static_cast<unsigned>((n + 127) / 128), 128>>>(in.ptr, n, out.ptr);
+    WB200_CUDA(cudaGetLastError());
+    WB200_CUDA(cudaMemcpy(out4, out.ptr, 4 * n * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+int wb200_philox_normals(unsigned int seed, unsigned int chain, unsigned int iter,
+                         unsigned int kind, size_t n, double* out, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    DeviceBuffer<double> buf;
+    buf.alloc(n);
+    const size_t pairs = (n + 1) / 2;
+    philox_normals_kernel<<<static_cast<unsigned>((pairs + 127) / 128), 128>>>(
+        seed, chain, iter, kind, n, buf.ptr);
+    WB200_CUDA(cudaGetLastError());
+    WB200_CUDA(cudaMemcpy(out, buf.ptr, n * 8, cudaMemcpyDeviceToHost));
+  });
+}
+
+// ---------------------------------------------------------------------------
+// walnutpie_sample_device: the whole of walnutpy.cpp:134-222 + run_sampler
+// (:20-84) + walnutpie::walnuts (api.hpp:33-69) for a device model.
+int walnutpie_sample_device(
+    const WalnutModelDesc* model, int num_params, const double* inits,
+    size_t num_chains, unsigned int seed, unsigned int id, double init_radius,
+    const double* init_inv_metric, int min_warmup_iter, int max_warmup_iter,
+    int min_sampling_iter, int max_sampling_iter, int max_trajectory_doublings,
+    int max_step_halvings, int min_micro_steps, double max_hamiltonian_error,
+    double step_size_converge_tol, double mass_converge_tol,
+    double rhat_converge_tol, double mass_init_count,
+    double mass_additive_smoothing, double max_macro_steps_target,
+    double step_size_init, double step_accept_rate_target,
+    double step_learning_rate, double step_gradient_decay,
+    double step_sq_gradient_decay, double step_stabilization,
+    double step_learn_rate_decay, bool save_warmup, double* out,
+    size_t out_size, int* final_lengths, double* stepsize_out,
+    double* inv_metric_out, int refresh, PRINT_CALLBACK print,
+    WalnutpyError** err) {
+  wb200_session* s = nullptr;
+  int rc = catch_exceptions(err, [&] {
+    if (refresh < 0) {  // errors.hpp:74-81
+      std::stringstream msg;
+      msg << "refresh must be non-negative, was " << refresh;
+      throw std::invalid_argument(msg.str());
+    }
+    if (!model) throw std::invalid_argument("model descriptor is null");
+    if (model->D != num_params) {
+      throw std::invalid_argument("model dimension and num_params differ");
+    }
+    const size_t C = num_chains;
+    const size_t rows_per_chain =
+        static_cast<size_t>(max_sampling_iter) +
+        (save_warmup ? static_cast<size_t>(max_warmup_iter) : 0);
+    const size_t draws_offset = static_cast<size_t>(num_params) * rows_per_chain;
+    if (out_size < C * draws_offset) {  // walnutpy.cpp:153-160
+      std::stringstream ss;
+      ss << "Output buffer too small. Expected at least " << C << " chains of "
+         << draws_offset << " doubles, got " << out_size;
+      throw std::runtime_error(ss.str());
+    }
+    WalnutTuning t;
+    walnuts_b200_default_tuning(&t);
+    t.min_warmup_iter = min_warmup_iter; t.max_warmup_iter = max_warmup_iter;
+    t.min_sampling_iter = min_sampling_iter; t.max_sampling_iter = max_sampling_iter;
+    t.max_trajectory_doublings = max_trajectory_doublings;
+    t.max_step_halvings = max_step_halvings;
+    t.min_micro_steps = min_micro_steps;
+    t.max_hamiltonian_error = max_hamiltonian_error;
+    t.step_size_converge_tol = step_size_converge_tol;
+    t.mass_converge_tol = mass_converge_tol;
+    t.rhat_converge_tol = rhat_converge_tol;
+    t.mass_init_count = mass_init_count;
+    t.mass_additive_smoothing = mass_additive_smoothing;
+    t.max_macro_steps_target = max_macro_steps_target;
+    t.step_size_init = step_size_init;
+    t.step_accept_rate_target = step_accept_rate_target;
+    t.step_learning_rate = step_learning_rate;
+    t.step_gradient_decay = step_gradient_decay;
+    t.step_sq_gradient_decay = step_sq_gradient_decay;
+    t.step_stabilization = step_stabilization;
+    t.step_learn_rate_decay = step_learn_rate_decay;
+
+    auto check = [&](int r, WalnutpyError*& e) {
+      if (r != 0) {
+        std::string msg = e ? e->msg : "unknown failure";
+        WalnutpyErrorType ty = e ? e->type : wb200_generic;
+        delete e;
+        e = nullptr;
+        if (ty == wb200_config) throw std::invalid_argument(msg);
+        throw std::runtime_error(msg);
+      }
+    };
+    WalnutpyError* e = nullptr;
+    // per-chain streams are keyed by (seed + id + num_chains, chain): the same
+    // mixing of seed and id as walnutpy.cpp:82
+    const unsigned int run_seed = seed + id + static_cast<unsigned int>(num_chains);
+    check(wb200_session_create(model, C, run_seed, 0, &t, 0, &s, &e), e);
+    check(wb200_session_init(s, inits, init_radius, init_inv_metric, nullptr, &e), e);
+    check(wb200_session_reserve_draws(s, static_cast<long long>(rows_per_chain), 0, &e), e);
+
+    auto say = [&](const std::string& m) {
+      if (print) print(m.c_str(), m.size(), false);
+    };
+    auto progress = [&](int from, int to, bool warm) {  // handlers.hpp:38-48
+      if (refresh == 0 || !print) return;
+      for (int it = from + 1; it <= to; ++it) {
+        if (it % refresh != 0) continue;
+        for (size_t c = 0; c < C; ++c) {
+          std::stringstream ss;
+          ss << "Chain [" << (c + 1) << "]: Iteration " << it << "\t"
+             << (warm ? "(Warmup)" : "(Sampling)") << std::endl;
+          say(ss.str());
+        }
+      }
+    };
+
+    // ---- warm-up: blocks of publish_stride iterations, controller between
+    const int stride = t.publish_stride > 0 ? t.publish_stride : 5;
+    int warm_done = 0;
+    DeviceBuffer<double> sums;
+    sums.alloc(static_cast<size_t>(num_params) + 2);
+    while (warm_done < max_warmup_iter) {
+      const int n = std::min(stride, max_warmup_iter - warm_done);
+      check(wb200_session_warmup(s, n, save_warmup ? 1 : 0, &e), e);
+      progress(warm_done, warm_done + n, true);
+      warm_done += n;
+      if (warm_done >= min_warmup_iter && warm_done < max_warmup_iter) {
+        double dev[2];
+        check(wb200_session_warmup_sums(s, sums.ptr, &e), e);
+        check(wb200_session_warmup_deviation(s, sums.ptr, dev, &e), e);
+        if (dev[0] <= mass_converge_tol && dev[1] <= step_size_converge_tol) break;
+      }
+    }
+    check(wb200_session_freeze(s, &e), e);
+    // ---- sampling: R-hat of lp between blocks (sampler.hpp:132-151)
+    int samp_done = 0;
+    while (samp_done < max_sampling_iter) {
+      const int n = std::min(stride, max_sampling_iter - samp_done);
+      check(wb200_session_sample(s, n, 1, &e), e);
+      progress(warm_done + samp_done, warm_done + samp_done + n, false);
+      samp_done += n;
+      if (samp_done >= min_sampling_iter && samp_done < max_sampling_iter) {
+        double m[4];
+        check(wb200_session_lp_moments(s, m, &e), e);
+        const double M = m[3];
+        const double var_of_means = (m[1] - m[0] * m[0] / M) / (M - 1.0);
+        const double mean_of_vars = m[2] / M;
+        const double r_hat = std::sqrt(1 + var_of_means / mean_of_vars);
+        if (refresh != 0 && print) {  // handlers.hpp:164-172
+          std::stringstream ss;
+          ss.precision(10);
+          ss << "Controller: R-hat at " << r_hat << std::endl;
+          say(ss.str());
+        }
+        if (r_hat <= rhat_converge_tol) break;
+      }
+    }
+    check(wb200_session_sync(s, &e), e);
+    // ---- outputs (walnutpy.cpp:196-221; handlers.hpp:73-100)
+    const int saved_warm = save_warmup ? warm_done : 0;
+    const long long rows = saved_warm + samp_done;
+    WB200_CUDA(cudaSetDevice(s->device));
+    for (size_t c = 0; c < C; ++c) {
+      WB200_CUDA(cudaMemcpy2DAsync(
+          out + draws_offset * c, num_params * sizeof(double),
+          s->draws.ptr + c * s->draw_cap * s->ld, s->ld * sizeof(double),
+          num_params * sizeof(double), rows, cudaMemcpyDeviceToHost, s->stream));
+      final_lengths[c] = saved_warm;
+      final_lengths[c + C] = samp_done;
+    }
+    check(wb200_session_get_state(s, nullptr, inv_metric_out, stepsize_out, nullptr,
+                                  nullptr, &e), e);
+  });
+  wb200_session_destroy(s);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// Host-side session object of the device sampler (declarations shared by
+// engine.cu, summary.cu and capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/walnuts_b200.h"
+#include "chain_kernel.cuh"
+
+// errors.hpp:26-36
+struct WalnutpyError {
+  std::string msg;
+  WalnutpyErrorType type;
+};
+
+namespace wb200 {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define WB200_CUDA(expr)                                                        \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      throw ::wb200::CudaError(std::string("CUDA error: ") +                    \
+                               cudaGetErrorString(_e) + " at " + __FILE__ +     \
+                               ":" + std::to_string(__LINE__));                 \
+    }                                                                           \
+  } while (0)
+
+template <class T>
+struct DeviceBuffer {
+  T* ptr = nullptr;
+  size_t count = 0;
+  DeviceBuffer() = default;
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  ~DeviceBuffer() { release(); }
+  void alloc(size_t n) {
+    release();
+    if (n) WB200_CUDA(cudaMalloc(&ptr, n * sizeof(T)));
+    count = n;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+};
+
+struct LaunchShape {
+  int T, K, cta, chains_per_cta;
+};
+LaunchShape shape_for_dim(int D);
+int occupancy_for(int kind, const LaunchShape& shape);
+
+// python/src/walnutpie/errors.hpp:42-72: exceptions -> error object + rc
+template <class F>
+int catch_exceptions(WalnutpyError** err, F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::invalid_argument& e) {
+    if (err) *err = new WalnutpyError{e.what(), wb200_config};
+  } catch (const std::exception& e) {
+    if (err) *err = new WalnutpyError{e.what(), wb200_generic};
+  } catch (...) {
+    if (err) *err = new WalnutpyError{"Unknown error", wb200_generic};
+  }
+  return -1;
+}
+
+inline void require_gpu() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    throw std::runtime_error(
+        "walnuts_b200: no CUDA device is visible; this library has no CPU path");
+  }
+}
+
+// host [rows][D] <-> device [rows][ld]
+inline void upload_rows(double* dst, int ld, const double* src, int D, size_t rows,
+                        cudaStream_t st) {
+  WB200_CUDA(cudaMemcpy2DAsync(dst, ld * sizeof(double), src, D * sizeof(double),
+                               D * sizeof(double), rows, cudaMemcpyHostToDevice, st));
+}
+inline void download_rows(double* dst, int D, const double* src, int ld, size_t rows,
+                          cudaStream_t st) {
+  WB200_CUDA(cudaMemcpy2DAsync(dst, D * sizeof(double), src, ld * sizeof(double),
+                               D * sizeof(double), rows, cudaMemcpyDeviceToHost, st));
+}
+
+}  // namespace wb200
+
+struct wb200_session {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int kind = 0, D = 0, ld = 0;
+  size_t N = 0;
+  int C = 0;
+  uint32_t seed = 0, chain_offset = 0;
+  WalnutTuning tuning{};
+  wb200::LaunchShape shape{};
+  int slots = 0, grid = 0;
+  bool frozen = false, initialised = false;
+  long long draw_cap = 0, rows_written = 0;
+  bool trace = false;
+  unsigned long long launches = 0;
+
+  wb200::DeviceBuffer<double> theta, inv_mass, est, tparam, scratch, draws,
+      lp_out, step_out, im_out, red;
+  wb200::DeviceBuffer<int> depth_out;
+  wb200::DeviceBuffer<wb200::ChainScalars> sc;
+  wb200::DeviceBuffer<unsigned int> ticket;
+
+  wb200::ChainParams params(int n_iter, int adapt, bool store);
+};
+
+namespace wb200 {
+void launch_chains(wb200_session& s, int n_iter, int adapt, bool store);
+void launch_init(wb200_session& s, bool have_mass, bool have_steps,
+                 bool have_positions, double init_radius);
+void launch_freeze(wb200_session& s);
+void launch_orbit(int kind, int D, int ld, int C, const double* tparam,
+                  double* theta, double* rho, const double* inv_mass, double* grad,
+                  double* logp, double* joint, double step, int num_steps,
+                  cudaStream_t stream);
+// summaries over ragged chains: chain c = rows start[c] .. start[c]+len[c] of a
+// device matrix with row stride ld; outputs are HOST arrays of D (nullable)
+void device_summary(const double* draws, int ld, int D,
+                    const std::vector<long long>& start,
+                    const std::vector<long long>& len, double* rhat, double* ess,
+                    double* mcse, double* mean, double* var, cudaStream_t stream);
+}  // namespace wb200

@@ -1,0 +1,299 @@
+"""Python entry points of the device sampler.
+
+``walnuts_device`` keeps the keyword signature and return type of the
+reference's ``walnuts_pyfunc`` (python/src/walnutpie/pyfunc.py:45-83, :270-286);
+the only change is that ``logp`` is a :class:`DeviceModel` instead of a host
+callback.  :class:`Session` exposes the device-resident batch (thousands of
+chains kept in HBM) for callers that do not want the draws copied back.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _ffi
+from .models import DeviceModel
+from .util import (WarmupInfo, prepare_inv_metric, prepare_output_buffer,
+                   prepare_seed)
+
+
+class WalnutsOutputArray(np.ndarray):
+    """ndarray of draws with a ``warmup`` attribute (pyfunc.py:10-29)."""
+
+    warmup: WarmupInfo
+
+    def __new__(cls, input_array, warmup: WarmupInfo):
+        obj = np.asarray(input_array).view(cls)
+        obj.warmup = warmup
+        return obj
+
+    def __array_finalize__(self, obj):
+        if obj is None:
+            return
+        self.warmup = getattr(obj, "warmup", None)
+
+
+def make_tuning(**kw) -> _ffi.WalnutTuning:
+    t = _ffi.WalnutTuning()
+    _ffi._lib.walnuts_b200_default_tuning(ctypes.byref(t))
+    for k, v in kw.items():
+        if not hasattr(t, k):
+            raise TypeError(f"unknown tuning argument {k!r}")
+        setattr(t, k, v)
+    return t
+
+
+def walnuts_device(
+    logp: DeviceModel,
+    *,
+    num_params: Optional[int] = None,
+    inits: Optional[np.ndarray] = None,
+    num_chains: int = 4,
+    seed: Optional[int] = None,
+    id: int = 1,
+    init_radius: float = 2.0,
+    init_inv_metric: Optional[np.ndarray] = None,
+    save_inv_metric: bool = False,
+    min_warmup_iter: int = 50,
+    max_warmup_iter: int = 1000,
+    min_sampling_iter: int = 50,
+    max_sampling_iter: int = 1000,
+    max_trajectory_doublings: int = 5,
+    max_step_halvings: int = 5,
+    min_micro_steps: int = 1,
+    max_hamiltonian_error: float = 0.5,
+    step_size_converge_tol: float = 0.1,
+    mass_converge_tol: float = 1.0,
+    rhat_converge_tol: float = 1.01,
+    mass_init_count: float = 4.0,
+    mass_additive_smoothing: float = 1e-5,
+    max_macro_steps_target: float = 15.0,
+    step_size_init: float = 1.0,
+    step_accept_rate_target: float = 0.8,
+    step_learning_rate: float = 0.05,
+    step_gradient_decay: float = 0.8,
+    step_sq_gradient_decay: float = 0.9,
+    step_stabilization: float = 1e-4,
+    step_learn_rate_decay: float = 0.5,
+    save_warmup: bool = False,
+    refresh: int = 0,
+) -> list[WalnutsOutputArray]:
+    """Sample ``logp`` (a device model) with ``num_chains`` chains on the GPU.
+
+    Arguments, defaults, validation errors and the returned list of
+    :class:`WalnutsOutputArray` follow ``walnuts_pyfunc`` (pyfunc.py:45-286).
+    Differences: (i) ``logp`` is a :class:`DeviceModel`; (ii) early stopping is
+    evaluated every ``publish_stride`` (5) iterations for all chains at once, so
+    every chain stops at the same iteration (the reference's chain lengths are
+    thread-schedule dependent, docs/py.rst:13-20); (iii) random numbers come
+    from a counter-based Philox stream keyed by ``(seed + id + num_chains,
+    chain)``, not from ``std::mt19937_64``.
+    """
+    if not isinstance(logp, DeviceModel):
+        raise TypeError(
+            "walnuts_b200 samples device models only; pass a walnuts_b200.models."
+            "DeviceModel (a host callback cannot feed a GPU batch)")
+    if num_params is None:
+        num_params = logp.num_params
+    if num_params != logp.num_params:
+        raise ValueError("num_params does not match the model")
+
+    seed = prepare_seed(seed)
+    out = prepare_output_buffer(num_chains=num_chains, num_params=num_params,
+                                max_sampling_iter=max_sampling_iter,
+                                max_warmup_iter=max_warmup_iter,
+                                save_warmup=save_warmup)
+    if inits is not None:
+        inits = np.ascontiguousarray(inits, dtype=np.float64)
+        if inits.shape == (num_params,):
+            inits = np.ascontiguousarray(
+                np.repeat(inits[np.newaxis], num_chains, axis=0))
+        elif inits.shape == (num_chains, num_params):
+            pass
+        else:
+            raise ValueError(
+                f"Invalid inits size. Expected a {(num_params,)} "
+                f"or {(num_chains, num_params)} matrix.")
+    init_inv_metric = prepare_inv_metric(init_inv_metric, (num_params,), num_chains)
+
+    lengths_out = np.zeros((num_chains * 2,), dtype=np.int32)
+    stepsize_out = np.zeros(num_chains, dtype=np.float64)
+    inv_metric_out = None
+    if save_inv_metric:
+        inv_metric_out = np.zeros((num_chains, num_params), dtype=np.float64)
+
+    desc = logp.desc()
+    _ffi._ffi_sample_device(
+        ctypes.byref(desc), num_params, inits, num_chains, seed, id, init_radius,
+        init_inv_metric, min_warmup_iter, max_warmup_iter, min_sampling_iter,
+        max_sampling_iter, max_trajectory_doublings, max_step_halvings,
+        min_micro_steps, max_hamiltonian_error, step_size_converge_tol,
+        mass_converge_tol, rhat_converge_tol, mass_init_count,
+        mass_additive_smoothing, max_macro_steps_target, step_size_init,
+        step_accept_rate_target, step_learning_rate, step_gradient_decay,
+        step_sq_gradient_decay, step_stabilization, step_learn_rate_decay,
+        save_warmup, out, out.size, lengths_out, stepsize_out, inv_metric_out,
+        refresh, _ffi.print_callback)
+
+    outputs = []
+    for i in range(num_chains):
+        warmup_written = lengths_out[i]
+        samples_written = lengths_out[i + num_chains]
+        warmup_info = WarmupInfo(
+            stepsize=stepsize_out[i],
+            inv_metric=inv_metric_out[i] if inv_metric_out is not None else None,
+            warmup_draws=(out[i, 0:warmup_written, :] if save_warmup else None))
+        outputs.append(WalnutsOutputArray(
+            out[i, warmup_written:warmup_written + samples_written, :], warmup_info))
+    return outputs
+
+
+class Session:
+    """A device-resident batch of chains (include/walnuts_b200.h, session API).
+
+    The stages of ``walnutpie::walnuts`` (api.hpp:33-69), batched:
+    ``init`` -> ``warmup(n)`` ... -> ``freeze()`` -> ``sample(n)`` ...
+    """
+
+    def __init__(self, model: DeviceModel, num_chains: int, seed: int = 0,
+                 chain_offset: int = 0, device: int = 0, **tuning):
+        self.model = model
+        self.num_chains = int(num_chains)
+        self.num_params = int(model.num_params)
+        self._desc = model.desc()
+        self.tuning = make_tuning(**tuning)
+        self._h = _ffi.session_p()
+        _ffi.session_create(ctypes.byref(self._desc), self.num_chains, seed,
+                            chain_offset, ctypes.byref(self.tuning), device,
+                            ctypes.byref(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _ffi.session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @staticmethod
+    def _c(a):
+        return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+    def init(self, positions=None, init_radius: float = 2.0, mass=None, steps=None):
+        _ffi.session_init(self._h, self._c(positions), float(init_radius),
+                          self._c(mass), self._c(steps))
+        return self
+
+    def reserve(self, capacity: int, trace: bool = False):
+        _ffi.session_reserve(self._h, int(capacity), int(trace))
+        return self
+
+    def warmup(self, n_iter: int, store: bool = False):
+        _ffi.session_warmup(self._h, int(n_iter), int(store))
+        return self
+
+    def freeze(self):
+        _ffi.session_freeze(self._h)
+        return self
+
+    def sample(self, n_iter: int, store: bool = True):
+        _ffi.session_sample(self._h, int(n_iter), int(store))
+        return self
+
+    def sync(self):
+        _ffi.session_sync(self._h)
+        return self
+
+    def draws(self, first: int, count: int) -> np.ndarray:
+        out = np.zeros((self.num_chains, count, self.num_params))
+        _ffi.session_get_draws(self._h, first, count, out)
+        return out
+
+    def trace(self, first: int, count: int):
+        C, D = self.num_chains, self.num_params
+        lp = np.zeros((C, count))
+        depth = np.zeros((C, count), np.int32)
+        step = np.zeros((C, count))
+        im = np.zeros((C, count, D))
+        _ffi.session_get_trace(self._h, first, count, lp, depth, step, im)
+        return dict(lp=lp, depth=depth, step=step, inv_mass=im)
+
+    def state(self):
+        C, D = self.num_chains, self.num_params
+        theta = np.zeros((C, D))
+        im = np.zeros((C, D))
+        step = np.zeros(C)
+        mm = np.zeros(C, np.int32)
+        ge = np.zeros(C, np.uint64)
+        _ffi.session_get_state(self._h, theta, im, step, mm, ge.ctypes.data)
+        return dict(theta=theta, inv_mass=im, step=step, min_micro=mm, grad_evals=ge)
+
+    def counters(self):
+        g, m, l = (ctypes.c_ulonglong(0) for _ in range(3))
+        _ffi.session_counters(self._h, ctypes.byref(g), ctypes.byref(m), ctypes.byref(l))
+        return dict(grad_evals=g.value, macro_steps=m.value, kernel_launches=l.value)
+
+    def last_kernel_ms(self) -> float:
+        ms = ctypes.c_float(0)
+        if _ffi.session_last_kernel_ms(self._h, ctypes.byref(ms)) != 0:
+            raise RuntimeError("no kernel has been timed on this session")
+        return ms.value
+
+    def device_draws(self):
+        """(device pointer, capacity, ld, rows_written) of the draw buffer."""
+        p = ctypes.c_void_p()
+        cap, rows = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        ld = ctypes.c_int(0)
+        _ffi.session_device_draws(self._h, ctypes.byref(p), ctypes.byref(cap),
+                                  ctypes.byref(ld), ctypes.byref(rows))
+        return p.value, cap.value, ld.value, rows.value
+
+    def summary(self, first: int, count: int):
+        """Per-dimension R-hat, ESS, MCSE, mean, variance of stored draws,
+        computed on the device (summary.hpp:594-769)."""
+        ptr, cap, ld, _ = self.device_draws()
+        D = self.num_params
+        out = {k: np.zeros(D) for k in ("r_hat", "ess", "mcse", "mean", "variance")}
+        self.sync()
+        _ffi.device_summary(ptr, self.num_chains, cap, first, count, D, ld,
+                            out["r_hat"] if self.num_chains > 1 else None,
+                            out["ess"], out["mcse"], out["mean"], out["variance"])
+        return out
+
+    def warmup_deviation(self, sums_device_ptr: int):
+        out = np.zeros(2)
+        _ffi.session_warmup_deviation(self._h, sums_device_ptr, out)
+        return out
+
+    def warmup_sums(self, sums_device_ptr: int):
+        _ffi.session_warmup_sums(self._h, sums_device_ptr)
+
+    def lp_moments(self):
+        out = np.zeros(4)
+        _ffi.session_lp_moments(self._h, out)
+        return out
+
+
+def orbit(model: DeviceModel, theta, rho, inv_mass, step: float, num_steps: int):
+    """``num_steps`` leapfrog micro-steps (walnuts.hpp:329-332) for a batch."""
+    theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+    rho = np.ascontiguousarray(np.atleast_2d(rho), dtype=np.float64)
+    im = np.ascontiguousarray(np.atleast_2d(inv_mass), dtype=np.float64)
+    C, D = theta.shape
+    desc = model.desc()
+    th, rh, g = np.zeros((C, D)), np.zeros((C, D)), np.zeros((C, D))
+    lp, jt = np.zeros(C), np.zeros(C)
+    _ffi.orbit(ctypes.byref(desc), C, theta, rho, im, float(step), int(num_steps),
+               th, rh, g, lp, jt)
+    return th, rh, g, lp, jt
