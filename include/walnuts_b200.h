@@ -203,6 +203,16 @@ int wb200_session_counters(wb200_session* s, unsigned long long* grad_evals,
                            WalnutpyError** err);
 /* last kernel's device time in ms (CUDA events on the session stream) */
 int wb200_session_last_kernel_ms(wb200_session* s, float* ms);
+/* user timer on the session stream: record event `which` (0 = start, 1 = stop)
+ * where the stream currently is; elapsed waits for the stop event */
+int wb200_session_timer_record(wb200_session* s, int which, WalnutpyError** err);
+int wb200_session_timer_elapsed_ms(wb200_session* s, float* ms, WalnutpyError** err);
+/* Statistics of the most recent walnutpie_sample_device call of this process:
+ * gradient evaluations, macro steps, kernels launched, warm-up and sampling
+ * iterations actually run. */
+int wb200_last_run_stats(unsigned long long* grad_evals, unsigned long long* macro_steps,
+                         unsigned long long* kernel_launches, int* warmup_iters,
+                         int* sampling_iters);
 
 /* Fixed-step leapfrog orbit (walnuts.hpp:329-332) for parity checks:
  * theta/rho/inv_mass HOST [C][D]; advances `num_steps` micro-steps. */

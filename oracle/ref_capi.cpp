@@ -53,11 +53,8 @@ struct EigenTarget {
   std::atomic<uint64_t>* counter = nullptr;
   void operator()(const VectorXd& x, double& lp, VectorXd& grad) const {
     if (counter) counter->fetch_add(1, std::memory_order_relaxed);
-    thread_local oracle::Vec xv, gv;
-    xv.assign(x.data(), x.data() + x.size());
-    base(xv, lp, gv);
     grad.resize(x.size());
-    std::memcpy(grad.data(), gv.data(), gv.size() * 8);
+    base.eval(x.data(), static_cast<std::size_t>(x.size()), lp, grad.data());
   }
 };
 

@@ -23,29 +23,35 @@ enum TargetKind : int { kStdNormal = 0, kDiagGaussian = 1, kFunnel = 2,
                         kLogistic = 3 };
 
 struct StdNormal {
-  void operator()(const Vec& x, double& lp, Vec& g) const {
-    g.resize(x.size());
+  void eval(const double* x, std::size_t n, double& lp, double* g) const {
     double s = 0.0;
-    for (std::size_t i = 0; i < x.size(); ++i) {
+    for (std::size_t i = 0; i < n; ++i) {
       s += x[i] * x[i];
       g[i] = -x[i];
     }
     lp = -0.5 * s;
+  }
+  void operator()(const Vec& x, double& lp, Vec& g) const {
+    g.resize(x.size());
+    eval(x.data(), x.size(), lp, g.data());
   }
 };
 
 // logp = -1/2 sum_d x_d^2 * prec_d ; grad_d = -(x_d * prec_d)
 struct DiagGaussian {
   Vec prec;  // 1 / sigma_d^2
-  void operator()(const Vec& x, double& lp, Vec& g) const {
-    g.resize(x.size());
+  void eval(const double* x, std::size_t n, double& lp, double* g) const {
     double s = 0.0;
-    for (std::size_t i = 0; i < x.size(); ++i) {
+    for (std::size_t i = 0; i < n; ++i) {
       double t = x[i] * prec[i];
       s += x[i] * t;
       g[i] = -t;
     }
     lp = -0.5 * s;
+  }
+  void operator()(const Vec& x, double& lp, Vec& g) const {
+    g.resize(x.size());
+    eval(x.data(), x.size(), lp, g.data());
   }
 };
 
@@ -53,8 +59,10 @@ struct DiagGaussian {
 // logp = -v^2/18 - (D-1)/2 v - 1/2 e^{-v} sum_i x_i^2
 struct Funnel {
   void operator()(const Vec& x, double& lp, Vec& g) const {
-    const std::size_t D = x.size();
-    g.resize(D);
+    g.resize(x.size());
+    eval(x.data(), x.size(), lp, g.data());
+  }
+  void eval(const double* x, std::size_t D, double& lp, double* g) const {
     const double v = x[0];
     const double ev = std::exp(-v);
     double ss = 0.0;
@@ -77,7 +85,11 @@ struct Logistic {
   const double* X = nullptr;
   const double* y = nullptr;
   void operator()(const Vec& x, double& lp, Vec& g) const {
-    g.assign(D, 0.0);
+    g.resize(D);
+    eval(x.data(), D, lp, g.data());
+  }
+  void eval(const double* x, std::size_t, double& lp, double* g) const {
+    for (std::size_t d = 0; d < D; ++d) g[d] = 0.0;
     double ll = 0.0;
     for (std::size_t n = 0; n < N; ++n) {
       const double* row = X + n * D;
@@ -109,7 +121,10 @@ struct CFuncTarget {
   void* data = nullptr;
   void operator()(const Vec& x, double& lp, Vec& g) const {
     g.resize(x.size());
-    int rc = fn(x.size(), x.data(), g.data(), &lp, data);
+    eval(x.data(), x.size(), lp, g.data());
+  }
+  void eval(const double* x, std::size_t n, double& lp, double* g) const {
+    int rc = fn(n, x, g, &lp, data);
     if (rc != 0) {
       throw std::runtime_error("logp failed with code " + std::to_string(rc));
     }

@@ -1,0 +1,58 @@
+"""TEST INFRASTRUCTURE: g++ build of the device transition state machine (T = 1)."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+SO = HERE / "libemu.so"
+SRC = HERE / "emu.cpp"
+CSRC = HERE.parents[1] / "walnuts_b200" / "csrc"
+KIND = {"std_normal": 0, "diag_gaussian": 1, "funnel": 2}
+
+
+class EmuTuning(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("max_depth", "max_halvings", "min_micro")] + [
+        (n, C.c_double) for n in ("max_error", "mass_init_count", "macro_target",
+                                  "adam_target", "adam_lr", "adam_b1", "adam_b2",
+                                  "adam_eps", "adam_decay")]
+
+
+def build():
+    deps = [SRC, CSRC / "chain_kernel.cuh", CSRC / "philox.cuh", CSRC / "host_shims.hpp"]
+    if not SO.exists() or any(d.stat().st_mtime > SO.stat().st_mtime for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared",
+                        "-I/usr/local/cuda/include", "-o", str(SO), str(SRC)], check=True)
+    return C.CDLL(str(SO))
+
+
+def run_chain(lib, kind, D, tparam, cfg, seed, chain, th0, m0, step0, nw, ns):
+    """cfg is an oracle.binding.OracleConfig; returns the device-code results."""
+    t = EmuTuning(cfg.max_trajectory_doublings, cfg.max_step_halvings, cfg.min_micro_steps,
+                  cfg.max_hamiltonian_error, cfg.mass_init_count,
+                  cfg.max_macro_steps_target, cfg.step_accept_rate_target,
+                  cfg.step_learning_rate, cfg.step_gradient_decay,
+                  cfg.step_sq_gradient_decay, cfg.step_stabilization,
+                  cfg.step_learn_rate_decay)
+    n = nw + ns
+    draws, lp = np.zeros((n, D)), np.zeros(n)
+    depth, st = np.zeros(n, np.int32), np.zeros(n)
+    im, imo = np.zeros((max(nw, 1), D)), np.zeros(D)
+    so, mm, ev = C.c_double(0), C.c_int(0), C.c_ulonglong(0)
+
+    def dp(a):
+        return a.ctypes.data_as(C.POINTER(C.c_double))
+
+    tp = None if tparam is None else np.ascontiguousarray(tparam, np.float64)
+    th0 = np.ascontiguousarray(th0, np.float64)
+    m0 = np.ascontiguousarray(m0, np.float64)
+    rc = lib.emu_run_chain(KIND[kind], D, None if tp is None else dp(tp), C.byref(t),
+                           C.c_uint32(seed), C.c_uint32(chain), dp(th0), dp(m0),
+                           C.c_double(step0), nw, ns, dp(draws), dp(lp),
+                           depth.ctypes.data_as(C.POINTER(C.c_int)), dp(st), dp(im),
+                           dp(imo), C.byref(so), C.byref(mm), C.byref(ev))
+    if rc != 0:
+        raise RuntimeError(f"emu_run_chain rc={rc}")
+    return dict(draws=draws, lp=lp, depth=depth, step_trace=st, warmup_inv_mass=im[:nw],
+                inv_mass=imo, step=so.value, min_micro=mm.value, grad_evals=ev.value)

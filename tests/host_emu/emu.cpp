@@ -1,0 +1,115 @@
+// TEST INFRASTRUCTURE: the device transition state machine
+// (walnuts_b200/csrc/chain_kernel.cuh) compiled for the host with one emulated
+// thread per chain (T = 1, K = kEmuK register chunks).  Same source, same
+// -ffp-contract=off arithmetic; sums run in element order, i.e. exactly the
+// oracle's order, so tests can demand bit equality of whole warm-up + sampling
+// runs against the oracle's Philox policy on CPU.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../walnuts_b200/csrc/chain_kernel.cuh"
+
+using namespace wb200;
+
+constexpr int kEmuK = 64;  // up to 128 dimensions
+
+struct EmuTuning {
+  int max_depth, max_halvings, min_micro;
+  double max_error, mass_init_count, macro_target;
+  double adam_target, adam_lr, adam_b1, adam_b2, adam_eps, adam_decay;
+};
+
+template <template <int, int> class TargetT>
+static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
+                uint32_t chain, const double* theta0, const double* mass0, double step0,
+                int n_warmup, int n_sampling, double* draws, double* lp, int* depth,
+                double* step_trace, double* im_trace, double* inv_mass_out,
+                double* step_out, int* min_micro_out, unsigned long long* evals) {
+  const int ld = (D + 1) & ~1;
+  const int total = n_warmup + n_sampling;
+  std::vector<double> theta(ld, 0.0), inv_mass(ld, 0.0), est(4 * ld, 0.0), tp(ld, 0.0);
+  std::vector<double> scratch(static_cast<size_t>(scratch_vectors(t.max_depth)) * ld, 0.0);
+  std::vector<double> d_draws(static_cast<size_t>(total) * ld), d_im(static_cast<size_t>(total) * ld);
+  std::memcpy(theta.data(), theta0, D * 8);
+  if (tparam) std::memcpy(tp.data(), tparam, D * 8);
+  // what init_kernel does for given positions / masses / steps
+  for (int i = 0; i < ld; ++i) {
+    double m = i < D ? mass0[i] : 1.0;
+    est[1 * ld + i] = t.mass_init_count * (1.0 / m);
+    est[3 * ld + i] = t.mass_init_count * m;
+  }
+  ChainScalars sc{};
+  sc.adam_x = std::log(step0);
+  sc.adam_b1p = 1.0; sc.adam_b2p = 1.0;
+  sc.mm_total = 2.0; sc.mm_count = 1.0;
+  sc.est_w = t.mass_init_count;
+  sc.step = step0;
+  sc.min_micro = t.min_micro;
+  unsigned int ticket = 0;
+  ChainParams p{};
+  p.C = 1; p.D = D; p.ld = ld;
+  p.max_depth = t.max_depth; p.max_halvings = t.max_halvings; p.min_micro_cfg = t.min_micro;
+  p.max_error = t.max_error; p.mass_init_count = t.mass_init_count;
+  p.macro_target = t.macro_target;
+  p.adam_target = t.adam_target; p.adam_lr = t.adam_lr; p.adam_b1 = t.adam_b1;
+  p.adam_b2 = t.adam_b2; p.adam_eps = t.adam_eps; p.adam_decay = t.adam_decay;
+  p.seed = seed; p.chain_offset = chain;
+  p.theta = theta.data(); p.inv_mass = inv_mass.data(); p.est = est.data(); p.sc = &sc;
+  p.draws = d_draws.data(); p.draw_cap = total;
+  p.lp_out = lp; p.depth_out = depth; p.step_out = step_trace; p.im_out = d_im.data();
+  p.scratch = scratch.data(); p.scratch_stride = scratch.size();
+  p.ticket = &ticket; p.tparam = tp.data();
+  Group<1> grp{};
+  using Target = TargetT<1, kEmuK>;
+  // warm-up launch
+  p.n_iter = n_warmup; p.adapt = 1; p.draw_base = 0;
+  {
+    ChainRunner<Target, 1, kEmuK> r(p, grp, scratch.data());
+    if (n_warmup > 0) r.run(0);
+  }
+  // freeze_kernel
+  for (int i = 0; i < ld; ++i) {
+    inv_mass[i] = std::sqrt((est[1 * ld + i] / sc.est_w) / (est[3 * ld + i] / sc.est_w));
+  }
+  sc.step = std::exp(sc.adam_x);
+  sc.min_micro = min_micro_steps(sc, p);
+  *step_out = sc.step;
+  *min_micro_out = sc.min_micro;
+  std::memcpy(inv_mass_out, inv_mass.data(), D * 8);
+  p.n_iter = n_sampling; p.adapt = 0; p.draw_base = n_warmup; p.im_out = nullptr;
+  {
+    ChainRunner<Target, 1, kEmuK> r(p, grp, scratch.data());
+    if (n_sampling > 0) r.run(0);
+  }
+  for (int i = 0; i < total; ++i) {
+    std::memcpy(draws + static_cast<size_t>(i) * D, d_draws.data() + static_cast<size_t>(i) * ld, D * 8);
+    if (i < n_warmup && im_trace) {
+      std::memcpy(im_trace + static_cast<size_t>(i) * D, d_im.data() + static_cast<size_t>(i) * ld, D * 8);
+    }
+  }
+  *evals = sc.grad_evals;
+}
+
+extern "C" int emu_run_chain(int kind, int D, const double* tparam, const EmuTuning* t,
+                             uint32_t seed, uint32_t chain, const double* theta0,
+                             const double* mass0, double step0, int n_warmup,
+                             int n_sampling, double* draws, double* lp, int* depth,
+                             double* step_trace, double* im_trace, double* inv_mass_out,
+                             double* step_out, int* min_micro_out,
+                             unsigned long long* evals) {
+  if (D > 2 * kEmuK || t->max_depth > kMaxDepth) return -1;
+  switch (kind) {
+    case 0: run<StdNormalTarget>(*t, D, tparam, seed, chain, theta0, mass0, step0, n_warmup,
+                                 n_sampling, draws, lp, depth, step_trace, im_trace,
+                                 inv_mass_out, step_out, min_micro_out, evals); break;
+    case 1: run<DiagGaussianTarget>(*t, D, tparam, seed, chain, theta0, mass0, step0,
+                                    n_warmup, n_sampling, draws, lp, depth, step_trace,
+                                    im_trace, inv_mass_out, step_out, min_micro_out, evals); break;
+    case 2: run<FunnelTarget>(*t, D, tparam, seed, chain, theta0, mass0, step0, n_warmup,
+                              n_sampling, draws, lp, depth, step_trace, im_trace,
+                              inv_mass_out, step_out, min_micro_out, evals); break;
+    default: return -2;
+  }
+  return 0;
+}

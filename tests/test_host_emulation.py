@@ -1,0 +1,66 @@
+"""The DEVICE transition state machine (walnuts_b200/csrc/chain_kernel.cuh) compiled
+with g++ for one emulated thread per chain, against the oracle's Philox policy.
+
+Same source as the CUDA build, same non-contracted fp64 arithmetic, sums in
+element order — so whole warm-up + sampling runs must equal the oracle's bit
+for bit: iterative doubling vs the reference's recursion (walnuts.hpp:464-495),
+the halving and reversibility ladders (:254-345), Barker / Metropolis selection
+(:368-387), Adam, the discounted Welford estimators and the min-micro controller
+(adaptive_walnuts.hpp:234-251).  Runs without a GPU.
+"""
+import numpy as np
+import pytest
+
+from oracle.binding import Target, default_config
+from tests import host_emu
+
+CASES = [
+    ("std_normal", 10, dict(), 0.4, 60, 60),
+    ("std_normal", 100, dict(), 0.5, 30, 30),
+    ("diag_gaussian", 12, dict(max_trajectory_doublings=8), 0.7, 80, 80),
+    ("funnel", 11, dict(max_step_halvings=8, max_trajectory_doublings=7), 0.5, 120, 120),
+    ("std_normal", 5, dict(min_micro_steps=2, max_macro_steps_target=3.0), 1.5, 80, 80),
+    ("diag_gaussian", 7, dict(max_step_halvings=1, max_trajectory_doublings=3), 0.3, 40, 40),
+    ("funnel", 2, dict(max_step_halvings=10, max_trajectory_doublings=10), 1.0, 60, 60),
+    ("std_normal", 1, dict(max_trajectory_doublings=12), 0.2, 30, 30),
+    ("std_normal", 37, dict(max_macro_steps_target=1.0), 0.05, 25, 25),  # min_micro grows
+]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return host_emu.build()
+
+
+@pytest.mark.parametrize("kind,D,over,step0,nw,ns", CASES)
+def test_device_state_machine_equals_oracle_bitwise(emu, oracle, kind, D, over, step0, nw, ns):
+    rng = np.random.default_rng(100 * D + nw)
+    prec = rng.uniform(0.05, 20.0, D) if kind == "diag_gaussian" else None
+    target = Target(kind, D, prec=prec)
+    cfg = default_config(**over)
+    for chain in (0, 5):
+        th0 = rng.normal(size=D)
+        m0 = rng.uniform(0.3, 3.0, D)
+        e = host_emu.run_chain(emu, kind, D, prec, cfg, 4242, chain, th0, m0, step0, nw, ns)
+        o = oracle.run_chain(target, cfg, 4242, chain, th0, m0, step0, nw, ns, rng_policy=1)
+        np.testing.assert_array_equal(e["draws"], np.concatenate([o["warmup_draws"], o["draws"]]))
+        np.testing.assert_array_equal(e["lp"], np.concatenate([o["warmup_lp"], o["lp"]]))
+        np.testing.assert_array_equal(e["depth"], np.concatenate([o["warmup_depth"], o["depth"]]))
+        np.testing.assert_array_equal(e["step_trace"][:nw], o["warmup_step"])
+        np.testing.assert_array_equal(e["warmup_inv_mass"], o["warmup_inv_mass"])
+        np.testing.assert_array_equal(e["inv_mass"], o["inv_mass"])
+        assert e["step"] == o["step"]
+        assert e["min_micro"] == o["min_micro"]
+        assert e["grad_evals"] == o["grad_evals"]
+
+
+def test_trajectories_exercise_every_branch(emu, oracle):
+    """the cases above must actually reach halvings, reversibility ladders, deep
+    trees and rejected extensions, or the bitwise agreement proves little"""
+    cfg = default_config(max_step_halvings=8, max_trajectory_doublings=7)
+    rng = np.random.default_rng(5)
+    th0, m0 = rng.normal(size=11), np.ones(11)
+    e = host_emu.run_chain(emu, "funnel", 11, None, cfg, 1, 0, th0, m0, 0.5, 200, 200)
+    depths = np.bincount(e["depth"], minlength=9)
+    assert (depths > 0).sum() >= 5          # many different tree depths
+    assert e["grad_evals"] > 3 * 400 * 2    # ladders well beyond one step per leaf

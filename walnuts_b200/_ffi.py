@@ -259,6 +259,25 @@ _lib.wb200_session_last_kernel_ms.restype = ctypes.c_int
 _lib.wb200_session_last_kernel_ms.argtypes = [session_p, ctypes.POINTER(ctypes.c_float)]
 session_last_kernel_ms = _lib.wb200_session_last_kernel_ms
 
+session_timer_record = _sess("wb200_session_timer_record", [session_p, ctypes.c_int])
+session_timer_elapsed_ms = _sess("wb200_session_timer_elapsed_ms",
+                                 [session_p, ctypes.POINTER(ctypes.c_float)])
+_lib.wb200_last_run_stats.restype = ctypes.c_int
+_lib.wb200_last_run_stats.argtypes = [
+    ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong),
+    ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_int),
+    ctypes.POINTER(ctypes.c_int)]
+
+
+def last_run_stats():
+    g, m, l = (ctypes.c_ulonglong(0) for _ in range(3))
+    w, s_ = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.wb200_last_run_stats(ctypes.byref(g), ctypes.byref(m), ctypes.byref(l),
+                              ctypes.byref(w), ctypes.byref(s_))
+    return dict(grad_evals=g.value, macro_steps=m.value, kernel_launches=l.value,
+                warmup_iters=w.value, sampling_iters=s_.value)
+
+
 orbit = _sess("wb200_orbit", [
     ctypes.POINTER(WalnutModelDesc), ctypes.c_size_t, double_array, double_array,
     double_array, ctypes.c_double, ctypes.c_int, double_array, double_array,
@@ -286,6 +305,7 @@ EXPORTED_SYMBOLS = [
     "wb200_session_warmup_deviation", "wb200_session_lp_moments",
     "wb200_session_get_draws", "wb200_session_get_trace", "wb200_session_get_state",
     "wb200_session_device_draws", "wb200_session_counters",
-    "wb200_session_last_kernel_ms", "wb200_orbit", "wb200_philox",
+    "wb200_session_last_kernel_ms", "wb200_session_timer_record",
+    "wb200_session_timer_elapsed_ms", "wb200_last_run_stats", "wb200_orbit", "wb200_philox",
     "wb200_philox_normals", "wb200_device_summary",
 ]

@@ -116,6 +116,8 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
     WB200_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     WB200_CUDA(cudaEventCreate(&s->ev0));
     WB200_CUDA(cudaEventCreate(&s->ev1));
+    WB200_CUDA(cudaEventCreate(&s->tm0));
+    WB200_CUDA(cudaEventCreate(&s->tm1));
     const size_t CL = static_cast<size_t>(s->C) * s->ld;
     s->theta.alloc(CL);
     s->inv_mass.alloc(CL);
@@ -168,6 +170,8 @@ void wb200_session_destroy(wb200_session* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->tm0) cudaEventDestroy(s->tm0);
+  if (s->tm1) cudaEventDestroy(s->tm1);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -361,6 +365,21 @@ int wb200_session_last_kernel_ms(wb200_session* s, float* ms) {
   cudaSetDevice(s->device);
   if (cudaEventSynchronize(s->ev1) != cudaSuccess) return -1;
   return cudaEventElapsedTime(ms, s->ev0, s->ev1) == cudaSuccess ? 0 : -1;
+}
+
+int wb200_session_timer_record(wb200_session* s, int which, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    WB200_CUDA(cudaEventRecord(which == 0 ? s->tm0 : s->tm1, s->stream));
+  });
+}
+
+int wb200_session_timer_elapsed_ms(wb200_session* s, float* ms, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    WB200_CUDA(cudaEventSynchronize(s->tm1));
+    WB200_CUDA(cudaEventElapsedTime(ms, s->tm0, s->tm1));
+  });
 }
 
 // ---------------------------------------------------------------- orbit ----

@@ -28,6 +28,12 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#if !defined(__CUDACC__)
+// g++ build of the very same state machine for tests/host_emu (one emulated
+// thread owns the whole vector: T = 1); never part of the shipped library
+#include "host_shims.hpp"
+#endif
+
 #include "philox.cuh"
 
 namespace wb200 {
@@ -105,11 +111,13 @@ struct Group {
 
   template <int N>
   __device__ __forceinline__ void sum(double (&v)[N]) {
+    if constexpr (T >= 32) {
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
+      for (int n = 0; n < N; ++n) {
 #pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) {
-        v[n] += __shfl_xor_sync(0xffffffffu, v[n], m);
+        for (int m = 16; m >= 1; m >>= 1) {
+          v[n] += __shfl_xor_sync(0xffffffffu, v[n], m);
+        }
       }
     }
     if constexpr (W > 1) {
@@ -448,6 +456,15 @@ struct ChainRunner {
         step = sc.step;
         min_micro = sc.min_micro;
       }
+      // lanes beyond D (padding of the 2*T*K register slots) carry a unit metric so
+      // that every quotient below stays finite; their theta / rho / grad stay 0
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          if (2 * (tid + k * T) + v >= p.D) im[k][v] = 1.0;
+        }
+      }
       const long long row = p.draw_base + it;
       if (p.im_out) {
         V::store(p.im_out + (static_cast<long long>(chain) * p.draw_cap + row) * ld,
@@ -639,6 +656,7 @@ struct ChainRunner {
   }
 };
 
+#if defined(__CUDACC__)
 // ---------------------------------------------------------------------------
 template <class Target, int T, int K, int CTA>
 __global__ void __launch_bounds__(CTA)
@@ -679,5 +697,6 @@ walnuts_chain_kernel(const ChainParams p) {
     runner.run(chain);
   }
 }
+#endif  // __CUDACC__
 
 }  // namespace wb200

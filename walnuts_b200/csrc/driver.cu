@@ -111,7 +111,25 @@ __global__ void philox_normals_kernel(uint32_t seed, uint32_t chain, uint32_t it
 
 using namespace wb200;
 
+namespace {
+struct LastRun {
+  unsigned long long grad_evals = 0, macro_steps = 0, launches = 0;
+  int warmup_iters = 0, sampling_iters = 0;
+} g_last_run;
+}  // namespace
+
 extern "C" {
+
+int wb200_last_run_stats(unsigned long long* grad_evals, unsigned long long* macro_steps,
+                         unsigned long long* kernel_launches, int* warmup_iters,
+                         int* sampling_iters) {
+  if (grad_evals) *grad_evals = g_last_run.grad_evals;
+  if (macro_steps) *macro_steps = g_last_run.macro_steps;
+  if (kernel_launches) *kernel_launches = g_last_run.launches;
+  if (warmup_iters) *warmup_iters = g_last_run.warmup_iters;
+  if (sampling_iters) *sampling_iters = g_last_run.sampling_iters;
+  return 0;
+}
 
 int wb200_session_warmup_sums(wb200_session* s, double* sums_device,
                               WalnutpyError** err) {
@@ -346,6 +364,10 @@ int walnutpie_sample_device(
     }
     check(wb200_session_get_state(s, nullptr, inv_metric_out, stepsize_out, nullptr,
                                   nullptr, &e), e);
+    check(wb200_session_counters(s, &g_last_run.grad_evals, &g_last_run.macro_steps,
+                                 &g_last_run.launches, &e), e);
+    g_last_run.warmup_iters = warm_done;
+    g_last_run.sampling_iters = samp_done;
   });
   wb200_session_destroy(s);
   return rc;

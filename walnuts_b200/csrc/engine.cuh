@@ -101,7 +101,7 @@ inline void download_rows(double* dst, int D, const double* src, int ld, size_t 
 struct wb200_session {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
   int kind = 0, D = 0, ld = 0;
   size_t N = 0;
   int C = 0;

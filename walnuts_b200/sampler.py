@@ -250,6 +250,15 @@ class Session:
             raise RuntimeError("no kernel has been timed on this session")
         return ms.value
 
+    def timer_start(self):
+        _ffi.session_timer_record(self._h, 0)
+
+    def timer_stop_ms(self) -> float:
+        _ffi.session_timer_record(self._h, 1)
+        ms = ctypes.c_float(0)
+        _ffi.session_timer_elapsed_ms(self._h, ctypes.byref(ms))
+        return ms.value
+
     def device_draws(self):
         """(device pointer, capacity, ld, rows_written) of the draw buffer."""
         p = ctypes.c_void_p()
