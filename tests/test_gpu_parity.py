@@ -176,9 +176,12 @@ def test_seeded_trajectories_match_oracle(wb, oracle, kind, D, C, over, nw, ns):
     assert full >= (C + 1) // 2
 
 
-def test_fixed_parameter_sampler_is_bit_exact_for_gaussians(wb, oracle):
-    """With frozen tuning, Gaussian dynamics are purely element-wise, so the draws
-    equal the oracle's bit for bit as long as no accept/U-turn decision flips."""
+def test_fixed_parameter_sampler_matches_oracle_to_rounding(wb, oracle):
+    """With frozen tuning, Gaussian dynamics are purely element-wise; the only
+    differences from the oracle are the last bits of the Box-Muller normals (CUDA
+    vs glibc log / sincos) and of the reduced energies, so whole chains agree to
+    ~1e-12 as long as no accept / U-turn decision flips.  (Bit equality of the
+    same source is asserted on CPU by tests/test_host_emulation.py.)"""
     D, C, n = 50, 6, 40
     rng = np.random.default_rng(8)
     var = rng.uniform(0.5, 4.0, D)
@@ -190,12 +193,14 @@ def test_fixed_parameter_sampler_is_bit_exact_for_gaussians(wb, oracle):
         s.reserve(n, trace=True)
         s.freeze().sample(n, store=True).sync()
         draws = s.draws(0, n)
-        im_used = s.state()["inv_mass"]
+        st = s.state()
     exact = 0
     for c in range(C):
-        o = oracle.run_sampler(target, 5, c, positions[c], im_used[c], 0.45, 6, 5, 1, 0.5, n,
-                               rng_policy=1)
-        exact += int(np.array_equal(draws[c], o["draws"]))
+        # the frozen step is exp(log(0.45)), one ulp away from 0.45: take the device's
+        o = oracle.run_sampler(target, 5, c, positions[c], st["inv_mass"][c], st["step"][c],
+                               6, 5, 1, 0.5, n, rng_policy=1)
+        scale = np.max(np.abs(o["draws"]), axis=1, keepdims=True)
+        exact += int(np.max(np.abs(draws[c] - o["draws"]) / scale) < 1e-11)
     assert exact >= C - 1
 
 
