@@ -10,7 +10,8 @@ for line in txt.splitlines():
         cur = dict(name=m.group(1), regs=0, spill_st=0, spill_ld=0, stack=0, smem=0); rows.append(cur); continue
     if cur is None: continue
     m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", line)
-    if m: cur["stack"], cur["spill_st"], cur["spill_ld"] = map(int, m.groups())
+    if m and not cur.get("seen_stack"):
+        cur["stack"], cur["spill_st"], cur["spill_ld"] = map(int, m.groups()); cur["seen_stack"] = True
     m = re.search(r"Used (\d+) registers", line)
     if m:
         cur["regs"] = int(m.group(1))

@@ -5,11 +5,16 @@
 // grad), the macro-step start state, the inverse mass and the target's
 // parameters stay in REGISTERS across every leapfrog micro-step, the
 // within-orbit step-halving ladder, the reversibility ladder and the iterative
-// orbit doubling.  Only the per-leaf tree bookkeeping (span ends, sub-tree
-// checkpoints, selected state) goes through a per-slot scratch area that is
-// sized to live in the 126 MB L2.  Chains are handed out by an atomic ticket so
-// long and short orbits balance across the 148 SMs; there is no lane divergence
-// between chains because a chain never shares a warp.
+// orbit doubling.  Only the tree bookkeeping of sub-trees with two or more
+// leaves (span ends, sub-tree first state, selected state) goes through a
+// per-slot scratch area that is sized to live in the 126 MB L2; single leaves
+// are merged straight from registers.  Chains are handed out by an atomic
+// ticket so long and short orbits balance across the 148 SMs; there is no lane
+// divergence between chains because a chain never shares a warp.
+//
+// Scalar decision arithmetic (Philox draws, log, log-sum-exp, Adam) runs on the
+// group's first warp only and is broadcast through shared memory, so the other
+// warps' issue slots go to the chains that share the SM.
 //
 // Reference semantics (all file:line relative to /root/reference/include/walnutpie):
 //   transition_w walnuts.hpp:520-563 | build_span (recursion -> binary-counter
@@ -101,16 +106,22 @@ __host__ __device__ inline int scratch_vectors(int max_depth) {
 }
 
 // ---------------------------------------------------------------------------
-// T cooperating threads; sums are bitwise identical in every thread.
+// T cooperating threads.  sum(): all-reduce, bitwise identical in every thread.
+// bcast(): values computed by the control warp reach every thread.
+constexpr int kRedStride = 4;  // doubles per warp row / broadcast row
+
 template <int T>
 struct Group {
   static constexpr int W = T / 32;
   int tid, lane, warp;
-  double* red;  // shared, [2][W][4] when W > 1
+  double* red;  // shared, [2][W + 1][kRedStride] when W > 1
   int parity;
+
+  __device__ __forceinline__ bool ctl() const { return W <= 1 || warp == 0; }
 
   template <int N>
   __device__ __forceinline__ void sum(double (&v)[N]) {
+    static_assert(N <= kRedStride, "too many values");
     if constexpr (T >= 32) {
 #pragma unroll
       for (int n = 0; n < N; ++n) {
@@ -121,23 +132,45 @@ struct Group {
       }
     }
     if constexpr (W > 1) {
-      double* buf = red + parity * (W * 4);
+      double* buf = red + parity * ((W + 1) * kRedStride);
       if (lane == 0) {
 #pragma unroll
-        for (int n = 0; n < N; ++n) buf[warp * 4 + n] = v[n];
+        for (int n = 0; n < N; ++n) buf[warp * kRedStride + n] = v[n];
       }
       __syncthreads();
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         double s = buf[n];
 #pragma unroll
-        for (int w = 1; w < W; ++w) s += buf[w * 4 + n];
+        for (int w = 1; w < W; ++w) s += buf[w * kRedStride + n];
         v[n] = s;
       }
       parity ^= 1;
     }
   }
+
+  // v[] as computed by the control warp becomes visible to every thread
+  template <int N>
+  __device__ __forceinline__ void bcast(double (&v)[N]) {
+    static_assert(N <= kRedStride, "too many values");
+    if constexpr (W > 1) {
+      double* buf = red + parity * ((W + 1) * kRedStride) + W * kRedStride;
+      if (warp == 0 && lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) buf[n] = v[n];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int n = 0; n < N; ++n) v[n] = buf[n];
+      parity ^= 1;
+    }
+  }
 };
+
+template <int T>
+constexpr int group_smem_doubles() {
+  return (T / 32 > 1) ? 2 * (T / 32 + 1) * kRedStride : 1;
+}
 
 // ---------------------------------------------------------------------------
 template <int T, int K>
@@ -258,11 +291,12 @@ struct FunnelTarget {
 
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double log_sum_exp2(double x1, double x2) {
-  // util.hpp:174-183
+  // util.hpp:174-183.  exp(max - max) is exactly 1, so the reference's
+  // exp(x1-m) + exp(x2-m) equals 1 + exp(min - max) bit for bit: one exp fewer.
   double m = fmax(x1, x2);
   if (isnan(x1) || isnan(x2)) return nan("");
   if (isinf(m) || isnan(x1 + x2)) return fmax(x1, x2);
-  return m + log(exp(x1 - m) + exp(x2 - m));
+  return m + log(1.0 + exp(fmin(x1, x2) - m));
 }
 
 __device__ __forceinline__ void adam_update(ChainScalars& sc, const ChainParams& p,
@@ -300,10 +334,10 @@ struct ChainRunner {
   double* scr;   // this slot's scratch
   int ld, tid;
   // registers
-  double th[K][2], rho[K][2], g[K][2];
-  double ths[K][2], rhos[K][2], gs[K][2];
+  double th[K][2], rho[K][2], g[K][2];       // live integrator state / newest leaf
+  double ths[K][2], rhos[K][2], gs[K][2];    // macro-step start = previous leaf
   double im[K][2];
-  ChainScalars sc;
+  ChainScalars sc;  // Adam fields are only current on the control warp
   unsigned long long evals;
 
   __device__ ChainRunner(const ChainParams& p_, Group<T>& grp_, double* scr_)
@@ -334,8 +368,12 @@ struct ChainRunner {
     }
   }
 
-  // n micro-steps from the live state; returns logp and joint (util.hpp:220-223)
-  __device__ __forceinline__ void integrate(int n, double h, double& lp, double& H) {
+  // n micro-steps from the live state; logp and joint (util.hpp:220-223).  With
+  // `with_dots` the U-turn dots (:192-201) of the end state against the start
+  // state (ths, rhos) ride in the same reduction.
+  __device__ __forceinline__ void integrate(int n, double h, double& lp, double& H,
+                                            bool with_dots, double& dot_new,
+                                            double& dot_old) {
     const double hh = 0.5 * h;
     double lp_part = 0.0;
     for (int j = 0; j < n; ++j) leapfrog(h, hh, lp_part);
@@ -348,22 +386,46 @@ struct ChainRunner {
         kin = __dadd_rn(kin, __dmul_rn(im[k][v], __dmul_rn(rho[k][v], rho[k][v])));
       }
     }
-    double r[2] = {lp_part, kin};
-    grp.sum(r);
-    lp = r[0];
-    H = r[0] + (-0.5 * r[1]);
+    if (with_dots) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          double sd = __dmul_rn(im[k][v], __dadd_rn(th[k][v], -ths[k][v]));
+          a = __dadd_rn(a, __dmul_rn(rho[k][v], sd));
+          b = __dadd_rn(b, __dmul_rn(rhos[k][v], sd));
+        }
+      }
+      double r[4] = {lp_part, kin, a, b};
+      grp.sum(r);
+      lp = r[0];
+      H = r[0] + (-0.5 * r[1]);
+      dot_new = r[2];
+      dot_old = r[3];
+    } else {
+      double r[2] = {lp_part, kin};
+      grp.sum(r);
+      lp = r[0];
+      H = r[0] + (-0.5 * r[1]);
+    }
   }
 
   // macro_step (:307-345) + reversible (:254-279) from (ths, rhos, gs, Hs).
-  // On success the new leaf is in (th, rho, g) with (lpn, Hn).
-  __device__ __forceinline__ bool macro_step(int dir, double step, int min_micro, double Hs,
-                             double& lpn, double& Hn) {
+  // On success the new leaf is in (th, rho, g) with (lpn, Hn); (ths, rhos, gs)
+  // still hold the start state.
+  __device__ __forceinline__ bool macro_step(int dir, double step, int min_micro,
+                                             double Hs, double& lpn, double& Hn,
+                                             bool with_dots, double& dot_new,
+                                             double& dot_old) {
     double h = dir > 0 ? step : -step;
     int n = min_micro;
     for (int rung = 0; rung < p.max_halvings; ++rung, n *= 2, h *= 0.5) {
       V::copy(th, ths); V::copy(rho, rhos); V::copy(g, gs);
-      integrate(n, h, lpn, Hn);
-      if (rung == 0 && p.adapt) adam_update(sc, p, exp(-fabs(Hs - Hn)));
+      integrate(n, h, lpn, Hn, with_dots, dot_new, dot_old);
+      if (rung == 0 && p.adapt && grp.ctl()) {
+        adam_update(sc, p, exp(-fabs(Hs - Hn)));  // only the coarsest attempt (:335-338)
+      }
       if (fabs(Hs - Hn) <= p.max_error) {
         sc.rung_sum += rung;
         if (n == 1 || n < 2 * min_micro) return true;
@@ -385,8 +447,8 @@ struct ChainRunner {
           first = false;
 #pragma unroll
           for (int k = 0; k < K; ++k) { rho[k][0] = -rho[k][0]; rho[k][1] = -rho[k][1]; }
-          double lp2, H2;
-          integrate(rn, rh, lp2, H2);
+          double lp2, H2, d0, d1;
+          integrate(rn, rh, lp2, H2, false, d0, d1);
           if (fabs(H2 - Hn) <= p.max_error) return false;  // irreversible
         }
         V::load(sv(E_TH), ld, tid, th);
@@ -398,8 +460,8 @@ struct ChainRunner {
     return false;
   }
 
-  // uturn (:192-201) between the far state F (in scratch) and the newest leaf
-  // L = (ths, rhos); dir gives the time order.
+  // uturn (:192-201) between a far state F (in scratch) and the newest leaf
+  // L = (th, rho); dir gives the time order.
   __device__ __forceinline__ bool uturn(const double* thF_row, const double* rhoF_row,
                                         int dir) {
     double thF[K][2], rhoF[K][2];
@@ -410,8 +472,8 @@ struct ChainRunner {
     for (int k = 0; k < K; ++k) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        double sd = __dmul_rn(im[k][v], __dadd_rn(ths[k][v], -thF[k][v]));
-        a = __dadd_rn(a, __dmul_rn(rhos[k][v], sd));
+        double sd = __dmul_rn(im[k][v], __dadd_rn(th[k][v], -thF[k][v]));
+        a = __dadd_rn(a, __dmul_rn(rho[k][v], sd));
         b = __dadd_rn(b, __dmul_rn(rhoF[k][v], sd));
       }
     }
@@ -419,6 +481,24 @@ struct ChainRunner {
     grp.sum(r);
     if (dir < 0) { r[0] = -r[0]; r[1] = -r[1]; }
     return r[0] < 0 || r[1] < 0;
+  }
+
+  // combine<U> (:368-387) on the control warp: {take_new, logW of the union}
+  __device__ __forceinline__ void merge_decision(bool metropolis, double logW_old,
+                                                 double logW_new, uint32_t gchain,
+                                                 uint32_t iter, uint32_t index,
+                                                 bool& take_new, double& logW) {
+    double r[2] = {0.0, 0.0};
+    if (grp.ctl()) {
+      const double lw = log_sum_exp2(logW_old, logW_new);
+      const double u = philox_uniform(p.seed, gchain, iter, index);
+      const double denom = metropolis ? logW_old : lw;
+      r[0] = (log(u) < logW_new - denom) ? 1.0 : 0.0;
+      r[1] = lw;
+    }
+    grp.bcast(r);
+    take_new = r[0] != 0.0;
+    logW = r[1];
   }
 
   __device__ __forceinline__ void run(int chain) {
@@ -450,7 +530,10 @@ struct ChainRunner {
             im[k][v] = sqrt((Sd[k][v] / sc.est_w) / (Ss[k][v] / sc.est_w));
           }
         }
-        step = exp(sc.adam_x);
+        double r[1] = {0.0};
+        if (grp.ctl()) r[0] = exp(sc.adam_x);  // Adam state lives on the control warp
+        grp.bcast(r);
+        step = r[0];
         min_micro = min_micro_steps(sc, p);
       } else {
         step = sc.step;
@@ -512,9 +595,10 @@ struct ChainRunner {
       V::store(sv(A_SEL), ld, tid, th);
       double H_bk = H0, H_fw = H0, logW = H0, lp_sel = lp0;
       V::copy(ths, th); V::copy(rhos, rho); V::copy(gs, g);
-      int regs_dir = 0;  // 0: (ths..) equals both ends; +-1: equals that end only
+      int regs_dir = 0;  // +-1: (ths, rhos, gs) equal that end of the span
       bool first_ext = true;
 
+      // stack of finished sub-trees with >= 2 leaves
       double st_logW[kMaxDepth], st_lp[kMaxDepth];
       int depth;
       for (depth = 1; depth <= p.max_depth; ++depth) {
@@ -528,66 +612,89 @@ struct ChainRunner {
         }
         first_ext = false;
         double Hs = fwd ? H_fw : H_bk;
-        // ---- build_span(depth-1): 2^(depth-1) leaves, binary-counter merges
+        double lps = 0.0;  // logp of the previous leaf (the level-0 entry)
+        // ---- build_span(depth-1): 2^(depth-1) leaves, binary-counter merges.
+        // The level-0 entry (a single leaf) is never written out: it is the
+        // macro-step start state, still in (ths, rhos) when leaf i+1 arrives.
         const int nleaf = 1 << (depth - 1);
         int sp = 0;
         bool ok = true;
+        double sub_logW = 0.0, sub_lp = 0.0;
         for (int i = 0; i < nleaf; ++i) {
-          double lpn, Hn;
+          double lpn, Hn, dot_new = 0.0, dot_old = 0.0;
+          const bool odd = (i & 1) != 0;
           sc.macro_steps += 1;
-          ok = macro_step(dir, step, min_micro, Hs, lpn, Hn);
+          ok = macro_step(dir, step, min_micro, Hs, lpn, Hn, odd, dot_new, dot_old);
           if (!ok) break;
+          double cur_logW = Hn, cur_lp = lpn;
+          // selection of the span being assembled: -1 newest leaf (th),
+          // -2 previous leaf (ths), >= 0 already in that stack slot
+          int cur_sel = -1;
+          const int nm = __ffs(~i) - 1;  // trailing one bits of i = merges
+          if (odd) {
+            // merge with the previous leaf: uturn (:490) from the fused dots
+            if (dir < 0) { dot_new = -dot_new; dot_old = -dot_old; }
+            if (dot_new < 0 || dot_old < 0) { ok = false; break; }
+            bool take_new;
+            double lw;
+            merge_decision(false, Hs, cur_logW, gchain, iter, sctr++, take_new, lw);
+            if (!take_new) { cur_sel = -2; cur_lp = lps; }
+            cur_logW = lw;
+            for (int m = 1; m < nm; ++m) {
+              const int s = sp - 1;
+              const int sb = ST_BASE + 3 * s;
+              if (uturn(sv(sb + ST_THF), sv(sb + ST_RHOF), dir)) { ok = false; break; }
+              merge_decision(false, st_logW[s], cur_logW, gchain, iter, sctr++,
+                             take_new, lw);
+              if (take_new) {
+                if (cur_sel >= 0) {
+                  double t[K][2];
+                  V::load(sv(ST_BASE + 3 * cur_sel + ST_SEL), ld, tid, t);
+                  V::store(sv(sb + ST_SEL), ld, tid, t);
+                  cur_sel = s;
+                }
+              } else {
+                cur_sel = s;
+                cur_lp = st_lp[s];
+              }
+              cur_logW = lw;
+              sp = s;
+            }
+            if (!ok) break;
+            const int sb = ST_BASE + 3 * sp;
+            if (nm == 1) {  // new two-leaf entry: its first state is the previous leaf
+              V::store(sv(sb + ST_THF), ld, tid, ths);
+              V::store(sv(sb + ST_RHOF), ld, tid, rhos);
+            }
+            if (cur_sel == -1) V::store(sv(sb + ST_SEL), ld, tid, th);
+            if (cur_sel == -2) V::store(sv(sb + ST_SEL), ld, tid, ths);
+            st_logW[sp] = cur_logW;
+            st_lp[sp] = cur_lp;
+            ++sp;
+          }
+          sub_logW = cur_logW;
+          sub_lp = cur_lp;
+          // the newest leaf becomes the start of the next macro step
           V::copy(ths, th); V::copy(rhos, rho); V::copy(gs, g);
           Hs = Hn;
-          double cur_logW = Hn, cur_lp = lpn;
-          int cur_sel = -1;  // -1: the selection is the newest leaf (registers)
-          const int nm = __ffs(~i) - 1;  // trailing one bits of i
-          for (int m = 0; m < nm; ++m) {
-            const int s = sp - 1;
-            const int sb = ST_BASE + 3 * s;
-            if (uturn(sv(sb + ST_THF), sv(sb + ST_RHOF), dir)) { ok = false; break; }
-            // combine<Barker> (:368-387)
-            const double lw = log_sum_exp2(st_logW[s], cur_logW);
-            const double u = philox_uniform(p.seed, gchain, iter, sctr++);
-            const bool take_new = log(u) < cur_logW - lw;
-            if (take_new) {
-              if (cur_sel >= 0) {
-                double t[K][2];
-                V::load(sv(ST_BASE + 3 * cur_sel + ST_SEL), ld, tid, t);
-                V::store(sv(sb + ST_SEL), ld, tid, t);
-                cur_sel = s;
-              }
-            } else {
-              cur_sel = s;
-              cur_lp = st_lp[s];
-            }
-            cur_logW = lw;
-            sp = s;
-          }
-          if (!ok) break;
-          const int sb = ST_BASE + 3 * sp;
-          if (nm == 0) {
-            V::store(sv(sb + ST_THF), ld, tid, ths);
-            V::store(sv(sb + ST_RHOF), ld, tid, rhos);
-          }
-          if (cur_sel < 0) V::store(sv(sb + ST_SEL), ld, tid, ths);
-          st_logW[sp] = cur_logW;
-          st_lp[sp] = cur_lp;
-          ++sp;
+          lps = lpn;
         }
         if (!ok) break;  // extension rejected, span unchanged (:543-545)
         // ---- top level: U-turn across the whole span, then Metropolis merge
         const int farb = fwd ? A_TH_BK : A_TH_FW;
-        const bool ut = uturn(sv(farb), sv(farb + 1), dir);  // :546
-        const double sub_logW = st_logW[0];
-        const double lw = log_sum_exp2(logW, sub_logW);
-        const double u = philox_uniform(p.seed, gchain, iter, sctr++);
-        const bool take = log(u) < sub_logW - logW;  // Metropolis (:372-378)
+        const bool ut = uturn(sv(farb), sv(farb + 1), dir);  // :546 (th == ths here)
+        bool take;
+        double lw;
+        merge_decision(true, logW, sub_logW, gchain, iter, sctr++, take, lw);
         if (take) {
-          double t[K][2];
-          V::load(sv(ST_BASE + ST_SEL), ld, tid, t);
-          V::store(sv(A_SEL), ld, tid, t);
-          lp_sel = st_lp[0];
+          if (nleaf == 1) {
+            V::store(sv(A_SEL), ld, tid, ths);
+          } else {
+            double t[K][2];
+            V::load(sv(ST_BASE + ST_SEL), ld, tid, t);
+            V::store(sv(A_SEL), ld, tid, t);
+          }
+          lp_sel = sub_lp;
         }
         const int nb = fwd ? A_TH_FW : A_TH_BK;
         V::store(sv(nb), ld, tid, ths);
@@ -658,11 +765,10 @@ struct ChainRunner {
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------
-template <class Target, int T, int K, int CTA>
-__global__ void __launch_bounds__(CTA)
+template <class Target, int T, int K, int CTA, int MINB>
+__global__ void __launch_bounds__(CTA, MINB)
 walnuts_chain_kernel(const ChainParams p) {
-  constexpr int W = T / 32;
-  __shared__ double red_smem[(W > 1) ? 2 * W * 4 : 1];
+  __shared__ double red_smem[group_smem_doubles<T>()];
   __shared__ int next_chain;
   Group<T> grp;
   grp.lane = threadIdx.x & 31;

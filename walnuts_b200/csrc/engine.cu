@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <string>
 
 namespace wb200 {
 
@@ -13,22 +15,29 @@ LaunchShape shape_for_dim(int D) {
   if (D <= 128) return {32, 2, 128, 4};
   if (D <= 256) return {64, 2, 64, 1};
   if (D <= 512) return {128, 2, 128, 1};
-  if (D <= 1024) return {256, 2, 256, 1};
+  if (D <= 1024) {
+    // WB200_SHAPE_1024=256x2 selects the 8-warp variant (experiments)
+    const char* e = std::getenv("WB200_SHAPE_1024");
+    if (e && std::string(e) == "256x2") return {256, 2, 256, 1};
+    return {128, 4, 128, 1};
+  }
   if (D <= 2048) return {256, 4, 256, 1};
   if (D <= 4096) return {512, 4, 512, 1};
   throw std::invalid_argument("num_params above 4096 is not supported by the "
                               "chain-resident kernel");
 }
 
+// (TARGET, T, K, CTA, min resident CTAs per SM -> register cap)
 #define WB200_FOR_SHAPE(S, MACRO, TARGET)                                      \
   do {                                                                         \
-    if ((S).T == 32 && (S).K == 1) { MACRO(TARGET, 32, 1, 128); }              \
-    else if ((S).T == 32 && (S).K == 2) { MACRO(TARGET, 32, 2, 128); }         \
-    else if ((S).T == 64) { MACRO(TARGET, 64, 2, 64); }                        \
-    else if ((S).T == 128) { MACRO(TARGET, 128, 2, 128); }                     \
-    else if ((S).T == 256 && (S).K == 2) { MACRO(TARGET, 256, 2, 256); }       \
-    else if ((S).T == 256 && (S).K == 4) { MACRO(TARGET, 256, 4, 256); }       \
-    else { MACRO(TARGET, 512, 4, 512); }                                       \
+    if ((S).T == 32 && (S).K == 1) { MACRO(TARGET, 32, 1, 128, 4); }           \
+    else if ((S).T == 32 && (S).K == 2) { MACRO(TARGET, 32, 2, 128, 3); }      \
+    else if ((S).T == 64) { MACRO(TARGET, 64, 2, 64, 6); }                     \
+    else if ((S).T == 128 && (S).K == 2) { MACRO(TARGET, 128, 2, 128, 3); }    \
+    else if ((S).T == 128 && (S).K == 4) { MACRO(TARGET, 128, 4, 128, 3); }    \
+    else if ((S).T == 256 && (S).K == 2) { MACRO(TARGET, 256, 2, 256, 2); }    \
+    else if ((S).T == 256 && (S).K == 4) { MACRO(TARGET, 256, 4, 256, 1); }    \
+    else { MACRO(TARGET, 512, 4, 512, 1); }                                    \
   } while (0)
 
 #define WB200_FOR_TARGET(KIND, S, MACRO)                                       \
@@ -59,8 +68,7 @@ template <template <int, int> class TargetT, int T, int K, int CTA>
 __global__ void __launch_bounds__(CTA) init_kernel(const InitParams ip) {
   using Target = TargetT<T, K>;
   using V = Vec<T, K>;
-  constexpr int W = T / 32;
-  __shared__ double red_smem[(W > 1) ? 2 * W * 4 : 1];
+  __shared__ double red_smem[group_smem_doubles<T>()];
   const ChainParams& p = ip.cp;
   Group<T> grp;
   grp.lane = threadIdx.x & 31;
@@ -230,8 +238,7 @@ template <template <int, int> class TargetT, int T, int K, int CTA>
 __global__ void __launch_bounds__(CTA) orbit_kernel(const OrbitParams op) {
   using Target = TargetT<T, K>;
   using V = Vec<T, K>;
-  constexpr int W = T / 32;
-  __shared__ double red_smem[(W > 1) ? 2 * W * 4 : 1];
+  __shared__ double red_smem[group_smem_doubles<T>()];
   const ChainParams& p = op.cp;
   Group<T> grp;
   grp.lane = threadIdx.x & 31; grp.red = red_smem; grp.parity = 0;
@@ -255,7 +262,8 @@ __global__ void __launch_bounds__(CTA) orbit_kernel(const OrbitParams op) {
   r.evals = 0;
   double lp, H;
   if (op.num_steps > 0) {
-    r.integrate(op.num_steps, op.step, lp, H);
+    double d0, d1;
+    r.integrate(op.num_steps, op.step, lp, H, false, d0, d1);
   } else {
     double kin = 0.0;
     for (int k = 0; k < K; ++k)
@@ -284,14 +292,14 @@ static int sm_count(int device) {
   return n;
 }
 
-#define WB200_OCC(TARGET, T_, K_, CTA_)                                        \
-  occ = blocks_per_sm(walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_>, CTA_)
-#define WB200_LAUNCH_CHAIN(TARGET, T_, K_, CTA_)                               \
-  walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_>                           \
+#define WB200_OCC(TARGET, T_, K_, CTA_, MINB_)                                 \
+  occ = blocks_per_sm(walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_>, CTA_)
+#define WB200_LAUNCH_CHAIN(TARGET, T_, K_, CTA_, MINB_)                        \
+  walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_>                    \
       <<<s.grid, CTA_, 0, s.stream>>>(p)
-#define WB200_LAUNCH_INIT(TARGET, T_, K_, CTA_)                                \
+#define WB200_LAUNCH_INIT(TARGET, T_, K_, CTA_, MINB_)                         \
   init_kernel<TARGET, T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(ip)
-#define WB200_LAUNCH_ORBIT(TARGET, T_, K_, CTA_)                               \
+#define WB200_LAUNCH_ORBIT(TARGET, T_, K_, CTA_, MINB_)                        \
   orbit_kernel<TARGET, T_, K_, CTA_><<<grid, CTA_, 0, stream>>>(op)
 
 int occupancy_for(int kind, const LaunchShape& shape) {
