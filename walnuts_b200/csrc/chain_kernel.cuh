@@ -119,6 +119,14 @@ struct Group {
 
   __device__ __forceinline__ bool ctl() const { return W <= 1 || warp == 0; }
 
+  __device__ __forceinline__ void sync() const {
+    if constexpr (W > 1) {
+      __syncthreads();
+    } else {
+      __syncwarp();
+    }
+  }
+
   template <int N>
   __device__ __forceinline__ void sum(double (&v)[N]) {
     static_assert(N <= kRedStride, "too many values");
@@ -299,8 +307,10 @@ __device__ __forceinline__ double log_sum_exp2(double x1, double x2) {
   return m + log(1.0 + exp(fmin(x1, x2) - m));
 }
 
-__device__ __forceinline__ void adam_update(ChainScalars& sc, const ChainParams& p,
-                                            double alpha) {
+// Scalar helpers are kept out of line: the transition kernel is large and the
+// instruction cache is what its hot loop competes for.
+__device__ __noinline__ inline void adam_update(ChainScalars& sc, const ChainParams& p,
+                                         double alpha) {
   // adam.hpp:70-86
   sc.adam_t += 1.0;
   sc.adam_b1p *= p.adam_b1;
@@ -315,14 +325,45 @@ __device__ __forceinline__ void adam_update(ChainScalars& sc, const ChainParams&
   sc.adam_x -= decayed * m_hat / denom;
 }
 
-__device__ __forceinline__ int min_micro_steps(const ChainScalars& sc,
+__device__ __forceinline__ int min_micro_steps(double mm_total, double mm_count,
                                                const ChainParams& p) {
   // adaptive_walnuts.hpp:152-157
-  double mean_micro = sc.mm_total / sc.mm_count;
+  double mean_micro = mm_total / mm_count;
   long long r = llround(mean_micro / p.macro_target);
   long long c = p.min_micro_cfg;
   return static_cast<int>(r > c ? r : c);
 }
+__device__ __forceinline__ int min_micro_steps(const ChainScalars& sc,
+                                               const ChainParams& p) {
+  return min_micro_steps(sc.mm_total, sc.mm_count, p);
+}
+
+// combine<U> (walnuts.hpp:368-387): logW of the union and whether the new span's
+// selection wins; one uniform from the chain's scalar stream
+struct MergeResult { double logW; bool take_new; };
+__device__ __noinline__ inline MergeResult merge_scalar(bool metropolis, double logW_old,
+                                                 double logW_new, uint32_t seed,
+                                                 uint32_t gchain, uint32_t iter,
+                                                 uint32_t index) {
+  const double lw = log_sum_exp2(logW_old, logW_new);
+  const double u = philox_uniform(seed, gchain, iter, index);
+  const double denom = metropolis ? logW_old : lw;
+  return MergeResult{lw, log(u) < logW_new - denom};
+}
+
+__device__ __noinline__ inline bool direction_bit(uint32_t seed, uint32_t gchain, uint32_t iter,
+                                           uint32_t index) {
+  return philox_bit(seed, gchain, iter, index);
+}
+
+__device__ __noinline__ inline double2 momentum_normals(uint32_t seed, uint32_t gchain,
+                                                 uint32_t iter, uint32_t j) {
+  double z0, z1;
+  philox_normal_pair(seed, gchain, iter, kKindNormal, j, z0, z1);
+  return make_double2(z0, z1);
+}
+
+__device__ __noinline__ inline double exp_noinline(double x) { return exp(x); }
 
 // ---------------------------------------------------------------------------
 template <class Target, int T, int K>
@@ -337,11 +378,17 @@ struct ChainRunner {
   double th[K][2], rho[K][2], g[K][2];       // live integrator state / newest leaf
   double ths[K][2], rhos[K][2], gs[K][2];    // macro-step start = previous leaf
   double im[K][2];
-  ChainScalars sc;  // Adam fields are only current on the control warp
+  // per-chain scalars live in shared memory; read-modify-write only by thread 0,
+  // read by others only after a barrier.  The few values every thread needs for
+  // its own vector work are mirrored in registers (u_*), updated redundantly.
+  ChainScalars& sc;
+  uint32_t u_iter, u_warm_iter;
+  double u_est_w, u_mm_total, u_mm_count;
   unsigned long long evals;
 
-  __device__ ChainRunner(const ChainParams& p_, Group<T>& grp_, double* scr_)
-      : p(p_), grp(grp_), scr(scr_), ld(p_.ld), tid(grp_.tid) {}
+  __device__ ChainRunner(const ChainParams& p_, Group<T>& grp_, double* scr_,
+                         ChainScalars& sc_)
+      : p(p_), grp(grp_), scr(scr_), ld(p_.ld), tid(grp_.tid), sc(sc_) {}
 
   __device__ __forceinline__ double* sv(int v) const {
     return scr + static_cast<long long>(v) * ld;
@@ -418,46 +465,58 @@ struct ChainRunner {
                                              double Hs, double& lpn, double& Hn,
                                              bool with_dots, double& dot_new,
                                              double& dot_old) {
+    // One loop, one integrate() site (code size): forward rungs of the halving
+    // ladder, then -- once a rung conserves the Hamiltonian -- the reversibility
+    // ladder, which re-integrates from the accepted end state with the momentum
+    // flipped at every coarser rung and must find none acceptable.
     double h = dir > 0 ? step : -step;
-    int n = min_micro;
-    for (int rung = 0; rung < p.max_halvings; ++rung, n *= 2, h *= 0.5) {
-      V::copy(th, ths); V::copy(rho, rhos); V::copy(g, gs);
-      integrate(n, h, lpn, Hn, with_dots, dot_new, dot_old);
-      if (rung == 0 && p.adapt && grp.ctl()) {
-        adam_update(sc, p, exp(-fabs(Hs - Hn)));  // only the coarsest attempt (:335-338)
-      }
-      if (fabs(Hs - Hn) <= p.max_error) {
-        sc.rung_sum += rung;
+    int n = min_micro, rung = 0;
+    bool reversing = false, first_rev = true;
+    int cur_n = n;
+    double cur_h = h;
+    V::copy(th, ths); V::copy(rho, rhos); V::copy(g, gs);
+    while (true) {
+      double lp2, H2, d_new = 0.0, d_old = 0.0;
+      integrate(cur_n, cur_h, lp2, H2, with_dots && !reversing, d_new, d_old);
+      if (!reversing) {
+        lpn = lp2; Hn = H2; dot_new = d_new; dot_old = d_old;
+        if (rung == 0 && p.adapt && tid == 0) {
+          adam_update(sc, p, exp_noinline(-fabs(Hs - Hn)));  // coarsest attempt only (:335-338)
+        }
+        if (!(fabs(Hs - Hn) <= p.max_error)) {
+          ++rung;
+          if (rung >= p.max_halvings) return false;
+          n *= 2; h *= 0.5;
+          cur_n = n; cur_h = h;
+          V::copy(th, ths); V::copy(rho, rhos); V::copy(g, gs);
+          continue;
+        }
+        if (tid == 0) sc.rung_sum += rung;
         if (n == 1 || n < 2 * min_micro) return true;
-        // reversibility ladder: coarser rungs must NOT be acceptable from the end
         V::store(sv(E_TH), ld, tid, th);
         V::store(sv(E_RHO), ld, tid, rho);
         V::store(sv(E_G), ld, tid, g);
-        int rn = n;
-        double rh = h;
-        bool first = true;
-        while (rn >= 2 * min_micro) {
-          rn /= 2;
-          rh *= 2;
-          if (!first) {
-            V::load(sv(E_TH), ld, tid, th);
-            V::load(sv(E_RHO), ld, tid, rho);
-            V::load(sv(E_G), ld, tid, g);
-          }
-          first = false;
-#pragma unroll
-          for (int k = 0; k < K; ++k) { rho[k][0] = -rho[k][0]; rho[k][1] = -rho[k][1]; }
-          double lp2, H2, d0, d1;
-          integrate(rn, rh, lp2, H2, false, d0, d1);
-          if (fabs(H2 - Hn) <= p.max_error) return false;  // irreversible
-        }
+        reversing = true;
+      } else if (fabs(H2 - Hn) <= p.max_error) {
+        return false;  // a coarser rung is acceptable from the end: irreversible
+      }
+      if (cur_n < 2 * min_micro) {  // ladder exhausted: restore the accepted leaf
         V::load(sv(E_TH), ld, tid, th);
         V::load(sv(E_RHO), ld, tid, rho);
         V::load(sv(E_G), ld, tid, g);
         return true;
       }
+      cur_n /= 2;
+      cur_h *= 2;
+      if (!first_rev) {
+        V::load(sv(E_TH), ld, tid, th);
+        V::load(sv(E_RHO), ld, tid, rho);
+        V::load(sv(E_G), ld, tid, g);
+      }
+      first_rev = false;
+#pragma unroll
+      for (int k = 0; k < K; ++k) { rho[k][0] = -rho[k][0]; rho[k][1] = -rho[k][1]; }
     }
-    return false;
   }
 
   // uturn (:192-201) between a far state F (in scratch) and the newest leaf
@@ -490,11 +549,10 @@ struct ChainRunner {
                                                  bool& take_new, double& logW) {
     double r[2] = {0.0, 0.0};
     if (grp.ctl()) {
-      const double lw = log_sum_exp2(logW_old, logW_new);
-      const double u = philox_uniform(p.seed, gchain, iter, index);
-      const double denom = metropolis ? logW_old : lw;
-      r[0] = (log(u) < logW_new - denom) ? 1.0 : 0.0;
-      r[1] = lw;
+      const MergeResult m =
+          merge_scalar(metropolis, logW_old, logW_new, p.seed, gchain, iter, index);
+      r[0] = m.take_new ? 1.0 : 0.0;
+      r[1] = m.logW;
     }
     grp.bcast(r);
     take_new = r[0] != 0.0;
@@ -503,7 +561,10 @@ struct ChainRunner {
 
   __device__ __forceinline__ void run(int chain) {
     const uint32_t gchain = p.chain_offset + static_cast<uint32_t>(chain);
-    sc = p.sc[chain];
+    if (tid == 0) sc = p.sc[chain];
+    grp.sync();
+    u_iter = sc.iter; u_warm_iter = sc.warm_iter;
+    u_est_w = sc.est_w; u_mm_total = sc.mm_total; u_mm_count = sc.mm_count;
     evals = 0;
     tgt.init(p, tid);
     double* theta_row = p.theta + static_cast<long long>(chain) * ld;
@@ -513,7 +574,7 @@ struct ChainRunner {
     if (!p.adapt) V::load(p.inv_mass + static_cast<long long>(chain) * ld, ld, tid, im);
 
     for (int it = 0; it < p.n_iter; ++it) {
-      const uint32_t iter = sc.iter;
+      const uint32_t iter = u_iter;
       uint32_t sctr = 0;
       double step;
       int min_micro;
@@ -527,14 +588,14 @@ struct ChainRunner {
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
             // MassEstimator::inv_mass_estimate, adaptive_walnuts.hpp:89-94
-            im[k][v] = sqrt((Sd[k][v] / sc.est_w) / (Ss[k][v] / sc.est_w));
+            im[k][v] = sqrt((Sd[k][v] / u_est_w) / (Ss[k][v] / u_est_w));
           }
         }
         double r[1] = {0.0};
-        if (grp.ctl()) r[0] = exp(sc.adam_x);  // Adam state lives on the control warp
+        if (grp.ctl()) r[0] = exp_noinline(sc.adam_x);  // Adam state: thread 0 writes it
         grp.bcast(r);
         step = r[0];
-        min_micro = min_micro_steps(sc, p);
+        min_micro = min_micro_steps(u_mm_total, u_mm_count, p);
       } else {
         step = sc.step;
         min_micro = sc.min_micro;
@@ -560,8 +621,9 @@ struct ChainRunner {
         const int j = tid + k * T;
         double z0 = 0.0, z1 = 0.0;
         if (2 * j < p.D) {
-          philox_normal_pair(p.seed, gchain, iter, kKindNormal, j, z0, z1);
-          if (2 * j + 1 >= p.D) z1 = 0.0;
+          const double2 z = momentum_normals(p.seed, gchain, iter, j);
+          z0 = z.x;
+          z1 = (2 * j + 1 >= p.D) ? 0.0 : z.y;
         }
         // adaptive: inverse().sqrt() (adaptive_walnuts.hpp:236);
         // fixed:    sqrt().inverse() (walnuts.hpp:647)
@@ -602,7 +664,7 @@ struct ChainRunner {
       double st_logW[kMaxDepth], st_lp[kMaxDepth];
       int depth;
       for (depth = 1; depth <= p.max_depth; ++depth) {
-        const bool fwd = philox_bit(p.seed, gchain, iter, sctr++);  // :552
+        const bool fwd = direction_bit(p.seed, gchain, iter, sctr++);  // :552
         const int dir = fwd ? 1 : -1;
         if (!first_ext && regs_dir != dir) {
           const int b = fwd ? A_TH_FW : A_TH_BK;
@@ -623,7 +685,7 @@ struct ChainRunner {
         for (int i = 0; i < nleaf; ++i) {
           double lpn, Hn, dot_new = 0.0, dot_old = 0.0;
           const bool odd = (i & 1) != 0;
-          sc.macro_steps += 1;
+          if (tid == 0) sc.macro_steps += 1;
           ok = macro_step(dir, step, min_micro, Hs, lpn, Hn, odd, dot_new, dot_old);
           if (!ok) break;
           double cur_logW = Hn, cur_lp = lpn;
@@ -712,8 +774,8 @@ struct ChainRunner {
         double gsel[K][2], lp_dummy;
         tgt.grad(cur, gsel, lp_dummy, grp);  // grad_select (cached by the reference)
         const double gamma =
-            1.0 - 1.0 / (p.mass_init_count + static_cast<double>(sc.warm_iter));
-        sc.est_w = gamma * sc.est_w + 1.0;
+            1.0 - 1.0 / (p.mass_init_count + static_cast<double>(u_warm_iter));
+        u_est_w = gamma * u_est_w + 1.0;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           double mu[K][2], S[K][2];
@@ -725,7 +787,7 @@ struct ChainRunner {
             for (int v = 0; v < 2; ++v) {
               const double y = e == 0 ? cur[k][v] : gsel[k][v];
               // online_moments.hpp:185-191 (both factors see the updated mean)
-              mu[k][v] = __dadd_rn(mu[k][v], __dadd_rn(y, -mu[k][v]) / sc.est_w);
+              mu[k][v] = __dadd_rn(mu[k][v], __dadd_rn(y, -mu[k][v]) / u_est_w);
               const double d = __dadd_rn(y, -mu[k][v]);
               S[k][v] = __dadd_rn(__dmul_rn(gamma, S[k][v]), __dmul_rn(d, d));
             }
@@ -733,19 +795,21 @@ struct ChainRunner {
           V::store(est_row + (2 * e) * ld, ld, tid, mu);
           V::store(est_row + (2 * e + 1) * ld, ld, tid, S);
         }
-        sc.mm_total += static_cast<double>(1ull << depth);
-        sc.mm_count += 1.0;
-        sc.warm_iter += 1;
-      } else {
+        u_mm_total += static_cast<double>(1ull << depth);
+        u_mm_count += 1.0;
+        u_warm_iter += 1;
+      } else if (tid == 0) {
         // WelfordAccumulator::observe (sampler.hpp:87-88)
         sc.lp_n += 1;
         const double delta = lp_sel - sc.lp_mean;
         sc.lp_mean += delta / static_cast<double>(sc.lp_n);
         sc.lp_m2 += delta * (lp_sel - sc.lp_mean);
       }
-      sc.iter += 1;
-      sc.last_depth = depth;
-      sc.last_lp = lp_sel;
+      u_iter += 1;
+      if (tid == 0) {
+        sc.last_depth = depth;
+        sc.last_lp = lp_sel;
+      }
       if (p.draws) {
         V::store(p.draws + (static_cast<long long>(chain) * p.draw_cap + row) * ld,
                  ld, tid, cur);
@@ -754,12 +818,17 @@ struct ChainRunner {
         const long long o = static_cast<long long>(chain) * p.draw_cap + row;
         if (p.lp_out) p.lp_out[o] = lp_sel;
         if (p.depth_out) p.depth_out[o] = depth;
-        if (p.step_out) p.step_out[o] = p.adapt ? exp(sc.adam_x) : sc.step;
+        if (p.step_out) p.step_out[o] = p.adapt ? exp_noinline(sc.adam_x) : sc.step;
       }
     }
     V::store(theta_row, ld, tid, cur);
-    sc.grad_evals += evals;
-    if (tid == 0) p.sc[chain] = sc;
+    if (tid == 0) {
+      sc.grad_evals += evals;
+      sc.iter = u_iter; sc.warm_iter = u_warm_iter;
+      sc.est_w = u_est_w; sc.mm_total = u_mm_total; sc.mm_count = u_mm_count;
+      p.sc[chain] = sc;
+    }
+    grp.sync();
   }
 };
 
@@ -769,6 +838,7 @@ template <class Target, int T, int K, int CTA, int MINB>
 __global__ void __launch_bounds__(CTA, MINB)
 walnuts_chain_kernel(const ChainParams p) {
   __shared__ double red_smem[group_smem_doubles<T>()];
+  __shared__ ChainScalars sc_smem[CTA / T];
   __shared__ int next_chain;
   Group<T> grp;
   grp.lane = threadIdx.x & 31;
@@ -786,7 +856,7 @@ walnuts_chain_kernel(const ChainParams p) {
     slot = blockIdx.x;
   }
   double* scr = p.scratch + static_cast<long long>(slot) * p.scratch_stride;
-  ChainRunner<Target, T, K> runner(p, grp, scr);
+  ChainRunner<Target, T, K> runner(p, grp, scr, sc_smem[threadIdx.x / T]);
   while (true) {
     int chain;
     if constexpr (T == 32) {

@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(CTA) orbit_kernel(const OrbitParams op) {
     chain = blockIdx.x;
   }
   if (chain >= p.C) return;
-  ChainRunner<Target, T, K> r(p, grp, nullptr);
+  ChainScalars unused_sc{};
+  ChainRunner<Target, T, K> r(p, grp, nullptr, unused_sc);
   r.tgt.init(p, grp.tid);
   const long long off = static_cast<long long>(chain) * p.ld;
   V::load(p.theta + off, p.ld, grp.tid, r.th);

@@ -16,3 +16,7 @@ inline int __ffs(int x) { return __builtin_ffs(x); }
 inline void __syncthreads() {}
 using std::isinf;
 using std::isnan;
+inline void __syncwarp() {}
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
