@@ -20,15 +20,17 @@ class EmuTuning(C.Structure):
 
 
 def build():
-    deps = [SRC, CSRC / "chain_kernel.cuh", CSRC / "philox.cuh", CSRC / "host_shims.hpp"]
+    deps = [SRC, CSRC / "chain_kernel.cuh", CSRC / "tick_kernel.cuh", CSRC / "philox.cuh",
+            CSRC / "host_shims.hpp"]
     if not SO.exists() or any(d.stat().st_mtime > SO.stat().st_mtime for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared",
                         "-I/usr/local/cuda/include", "-o", str(SO), str(SRC)], check=True)
     return C.CDLL(str(SO))
 
 
-def run_chain(lib, kind, D, tparam, cfg, seed, chain, th0, m0, step0, nw, ns):
-    """cfg is an oracle.binding.OracleConfig; returns the device-code results."""
+def run_chain(lib, kind, D, tparam, cfg, seed, chain, th0, m0, step0, nw, ns, engine="chain"):
+    """cfg is an oracle.binding.OracleConfig; returns the device-code results.
+    engine: "chain" (chain_kernel.cuh) or "tick" (tick_kernel.cuh)."""
     t = EmuTuning(cfg.max_trajectory_doublings, cfg.max_step_halvings, cfg.min_micro_steps,
                   cfg.max_hamiltonian_error, cfg.mass_init_count,
                   cfg.max_macro_steps_target, cfg.step_accept_rate_target,
@@ -47,7 +49,8 @@ def run_chain(lib, kind, D, tparam, cfg, seed, chain, th0, m0, step0, nw, ns):
     tp = None if tparam is None else np.ascontiguousarray(tparam, np.float64)
     th0 = np.ascontiguousarray(th0, np.float64)
     m0 = np.ascontiguousarray(m0, np.float64)
-    rc = lib.emu_run_chain(KIND[kind], D, None if tp is None else dp(tp), C.byref(t),
+    fn = lib.emu_run_chain if engine == "chain" else lib.emu_run_chain_tick
+    rc = fn(KIND[kind], D, None if tp is None else dp(tp), C.byref(t),
                            C.c_uint32(seed), C.c_uint32(chain), dp(th0), dp(m0),
                            C.c_double(step0), nw, ns, dp(draws), dp(lp),
                            depth.ctypes.data_as(C.POINTER(C.c_int)), dp(st), dp(im),

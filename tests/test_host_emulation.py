@@ -32,8 +32,10 @@ def emu():
     return host_emu.build()
 
 
+@pytest.mark.parametrize("engine", ["chain", "tick"])
 @pytest.mark.parametrize("kind,D,over,step0,nw,ns", CASES)
-def test_device_state_machine_equals_oracle_bitwise(emu, oracle, kind, D, over, step0, nw, ns):
+def test_device_state_machine_equals_oracle_bitwise(emu, oracle, engine, kind, D, over, step0,
+                                                    nw, ns):
     rng = np.random.default_rng(100 * D + nw)
     prec = rng.uniform(0.05, 20.0, D) if kind == "diag_gaussian" else None
     target = Target(kind, D, prec=prec)
@@ -41,7 +43,8 @@ def test_device_state_machine_equals_oracle_bitwise(emu, oracle, kind, D, over, 
     for chain in (0, 5):
         th0 = rng.normal(size=D)
         m0 = rng.uniform(0.3, 3.0, D)
-        e = host_emu.run_chain(emu, kind, D, prec, cfg, 4242, chain, th0, m0, step0, nw, ns)
+        e = host_emu.run_chain(emu, kind, D, prec, cfg, 4242, chain, th0, m0, step0, nw, ns,
+                               engine=engine)
         o = oracle.run_chain(target, cfg, 4242, chain, th0, m0, step0, nw, ns, rng_policy=1)
         np.testing.assert_array_equal(e["draws"], np.concatenate([o["warmup_draws"], o["draws"]]))
         np.testing.assert_array_equal(e["lp"], np.concatenate([o["warmup_lp"], o["lp"]]))

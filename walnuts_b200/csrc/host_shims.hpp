@@ -20,3 +20,5 @@ inline void __syncwarp() {}
 #ifndef __noinline__
 #define __noinline__ __attribute__((noinline))
 #endif
+inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { unsigned int o = *p; *p += v; return o; }
