@@ -236,6 +236,14 @@ int wb200_device_summary(const double* draws_device, size_t num_chains,
                          int D, int ld, double* rhat, double* ess, double* mcse,
                          double* mean, double* var, WalnutpyError** err);
 
+/* Batched logistic-regression log density and gradient on the tensor cores
+ * (tcgen05): X host fp64 [N][D] row-major (rounded to bf16), y host fp64 [N],
+ * theta host fp64 [C][D]; outputs logp [C], grad [C][D].  repeats > 0 also times
+ * `repeats` further evaluations with CUDA events (ms per batched evaluation). */
+int wb200_logistic_logp_grad(const double* X, const double* y, size_t N, int D,
+                             const double* theta, size_t C, double* logp, double* grad,
+                             int repeats, float* ms_per_eval, WalnutpyError** err);
+
 const char* walnuts_b200_version(void);
 
 #ifdef __cplusplus

@@ -294,6 +294,11 @@ device_summary = _sess("wb200_device_summary", [
     nullable_double_array, nullable_double_array, nullable_double_array,
     nullable_double_array])
 
+logistic_logp_grad = _sess("wb200_logistic_logp_grad", [
+    double_array, double_array, ctypes.c_size_t, ctypes.c_int, double_array,
+    ctypes.c_size_t, double_array, double_array, ctypes.c_int,
+    ctypes.POINTER(ctypes.c_float)])
+
 EXPORTED_SYMBOLS = [
     "walnutpie_sample_device", "walnutpie_sample_cfunc", "walnutpie_separator_char",
     "walnutpie_ess", "walnutpie_r_hat", "walnutpie_mcse",
@@ -307,5 +312,5 @@ EXPORTED_SYMBOLS = [
     "wb200_session_device_draws", "wb200_session_counters",
     "wb200_session_last_kernel_ms", "wb200_session_timer_record",
     "wb200_session_timer_elapsed_ms", "wb200_last_run_stats", "wb200_orbit", "wb200_philox",
-    "wb200_philox_normals", "wb200_device_summary",
+    "wb200_philox_normals", "wb200_device_summary", "wb200_logistic_logp_grad",
 ]

@@ -306,3 +306,17 @@ def orbit(model: DeviceModel, theta, rho, inv_mass, step: float, num_steps: int)
     _ffi.orbit(ctypes.byref(desc), C, theta, rho, im, float(step), int(num_steps),
                th, rh, g, lp, jt)
     return th, rh, g, lp, jt
+
+
+def logistic_logp_grad(X, y, theta, repeats: int = 0):
+    """Batched logistic-regression log density and gradient for C parameter vectors
+    on the tensor cores; returns (logp [C], grad [C][D], ms per evaluation or None)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    theta = np.ascontiguousarray(np.atleast_2d(theta), dtype=np.float64)
+    N, D = X.shape
+    C = theta.shape[0]
+    lp, g = np.zeros(C), np.zeros((C, D))
+    ms = ctypes.c_float(0)
+    _ffi.logistic_logp_grad(X, y, N, D, theta, C, lp, g, int(repeats), ctypes.byref(ms))
+    return lp, g, (ms.value if repeats > 0 else None)
