@@ -331,3 +331,107 @@ def test_results_do_not_depend_on_sharding(wb):
     whole = run(8, 0)
     np.testing.assert_array_equal(whole[:4], run(4, 0))
     np.testing.assert_array_equal(whole[4:], run(4, 4))
+
+
+# ---- lock-step tick engine and the tensor-core logistic gradient --------------
+@pytest.fixture
+def tick_engine_env(monkeypatch):
+    monkeypatch.setenv("WB200_ENGINE", "tick")
+
+
+@pytest.mark.parametrize("kind,D,C,over,nw,ns", [
+    ("std_normal", 100, 4, dict(), 40, 40),
+    ("diag_gaussian", 10, 6, dict(max_trajectory_doublings=8), 60, 60),
+    ("funnel", 11, 6, dict(max_step_halvings=8, max_trajectory_doublings=7), 50, 50),
+    ("diag_gaussian", 300, 3, dict(), 25, 25),
+])
+def test_tick_engine_trajectories_match_oracle(wb, oracle, tick_engine_env, kind, D, C, over,
+                                               nw, ns):
+    """The lock-step engine (one gradient request per tick per chain) through the same
+    session API, element-wise targets: identical-seed trajectories vs the oracle."""
+    rng = np.random.default_rng(2000 + D)
+    model, target = make_model(wb, kind, D, rng)
+    positions = rng.normal(size=(C, D))
+    mass = rng.uniform(0.5, 2.0, (C, D))
+    steps = rng.uniform(0.2, 0.6, C)
+    cfg = default_config(**over)
+    with wb.Session(model, C, seed=99, **over) as s:
+        s.init(positions=positions, mass=mass, steps=steps)
+        s.reserve(nw + ns, trace=True)
+        s.warmup(nw, store=True).freeze().sample(ns, store=True).sync()
+        draws = s.draws(0, nw + ns)
+        tr = s.trace(0, nw + ns)
+        st = s.state()
+    full = 0
+    for c in range(C):
+        o = oracle.run_chain(target, cfg, 99, c, positions[c], mass[c], steps[c], nw, ns,
+                             rng_policy=1)
+        ref_draws = np.concatenate([o["warmup_draws"], o["draws"]])
+        k = first_divergence(draws[c], ref_draws, 1e-9)
+        assert k >= 5
+        if k == nw + ns:
+            full += 1
+            np.testing.assert_array_equal(tr["depth"][c],
+                                          np.concatenate([o["warmup_depth"], o["depth"]]))
+            assert st["step"][c] == pytest.approx(o["step"], rel=1e-10)
+            # the carried gradient saves the reference's re-evaluation per transition
+            assert int(st["grad_evals"][c]) == o["grad_evals"] - (nw + ns)
+    assert full >= (C + 1) // 2
+
+
+def bf16_round(a):
+    import torch
+    return torch.tensor(a, dtype=torch.float64).to(torch.bfloat16).to(torch.float64).numpy()
+
+
+def make_logistic(N, D, seed):
+    rng = np.random.default_rng(seed)
+    X = bf16_round(rng.normal(size=(N, D)))
+    tstar = rng.normal(size=D) / np.sqrt(D)
+    y = (rng.uniform(size=N) < 1 / (1 + np.exp(-X @ tstar))).astype(np.float64)
+    return X, y
+
+
+@pytest.mark.parametrize("N,D,C", [(256, 64, 128), (300, 16, 5), (1000, 200, 130),
+                                   (4096, 512, 256), (1, 1, 1)])
+def test_logistic_gradient_operator_matches_oracle(wb, oracle, N, D, C):
+    """tcgen05 GEMM path vs the fp64 CPU density.  Tolerances: logp is accumulated in
+    fp32 tiles / fp64 totals from a bf16 hi+lo split of theta (1e-5 relative); the
+    residual r = y - sigmoid(z) enters the second GEMM in bf16, i.e. 2^-9 relative per
+    element (3e-3 of the largest gradient component)."""
+    from walnuts_b200.sampler import logistic_logp_grad
+    X, y = make_logistic(N, D, N + D)
+    theta = np.random.default_rng(C).normal(size=(C, D)) * 0.3
+    lp, g, _ = logistic_logp_grad(X, y, theta)
+    t = Target("logistic", D, X=X, y=y)
+    for c in range(min(C, 8)):
+        olp, og = oracle.logp_grad(t, theta[c])
+        assert abs(lp[c] - olp) <= 1e-5 * max(1.0, abs(olp))
+        assert np.max(np.abs(g[c] - og)) <= 3e-3 * max(np.max(np.abs(og)), 1.0)
+
+
+def test_logistic_sampler_moments_match_oracle_within_mcse(wb, oracle):
+    N, D, C, nw, ns = 500, 8, 256, 150, 100
+    X, y = make_logistic(N, D, 77)
+    over = dict(max_trajectory_doublings=8)
+    with wb.Session(wb.models.logistic(X, y), C, seed=5, **over) as s:
+        s.init(init_radius=1.0)
+        s.reserve(ns)
+        s.warmup(nw).freeze().sample(ns).sync()
+        summ = s.summary(0, ns)
+        evals = s.counters()["grad_evals"]
+    assert evals > C * (nw + ns)
+    assert np.max(summ["r_hat"]) < 1.05
+    target = Target("logistic", D, X=X, y=y)
+    cfg = default_config(min_warmup_iter=nw, max_warmup_iter=nw, min_sampling_iter=4 * ns,
+                         max_sampling_iter=4 * ns, **over)
+    pos = oracle.init_positions(8, D, 4, 1.0)
+    mass, steps = oracle.init_mass_step(target, pos, 4, 1.0)
+    cpu = oracle.walnuts(target, cfg, 4, pos, mass, steps)
+    chains = [cpu["out"][c, :4 * ns] for c in range(8)]
+    cpu_mean = np.mean(np.concatenate(chains), axis=0)
+    cpu_var = np.var(np.concatenate(chains), axis=0, ddof=1)
+    cpu_mcse = oracle.mcse(chains)
+    z = np.abs(summ["mean"] - cpu_mean) / np.sqrt(summ["mcse"] ** 2 + cpu_mcse ** 2)
+    assert np.max(z) < 5.0, z
+    assert np.max(np.abs(summ["variance"] / cpu_var - 1)) < 0.25

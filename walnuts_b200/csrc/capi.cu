@@ -141,11 +141,21 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
       WB200_CUDA(cudaMemsetAsync(s->tparam.ptr, 0, s->ld * 8, s->stream));
       WB200_CUDA(cudaMemcpyAsync(s->tparam.ptr, prec, s->D * 8,
                                  cudaMemcpyHostToDevice, s->stream));
-    } else if (s->kind != kStdNormal && s->kind != kFunnel) {
+    } else if (s->kind != kStdNormal && s->kind != kFunnel && s->kind != kLogistic) {
       throw std::invalid_argument("unsupported model kind for the device sampler");
     }
     if (s->kind == kFunnel && s->D < 2) {
       throw std::invalid_argument("funnel needs num_params >= 2");
+    }
+    // engine: chain-resident kernel for element-wise targets, lock-step ticks where the
+    // gradient is a cross-chain batched contraction (or when forced, for testing)
+    const char* eng = std::getenv("WB200_ENGINE");
+    const bool use_tick = s->kind == kLogistic || (eng && std::string(eng) == "tick");
+    if (use_tick) {
+      tick_create(*s, *model);
+      WB200_CUDA(cudaStreamSynchronize(s->stream));
+      *out = s.release();
+      return;
     }
     // slots: resident groups of the chain kernel
     const int occ = occupancy_for(s->kind, s->shape);
@@ -168,6 +178,7 @@ void wb200_session_destroy(wb200_session* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->tick) tick_destroy(*s);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->tm0) cudaEventDestroy(s->tm0);
@@ -204,8 +215,12 @@ int wb200_session_init(wb200_session* s, const double* positions,
       WB200_CUDA(cudaMemcpyAsync(s->red.ptr, steps, C * 8, cudaMemcpyHostToDevice,
                                  s->stream));
     }
-    launch_init(*s, mass != nullptr, steps != nullptr, positions != nullptr,
-                init_radius);
+    if (s->tick) {
+      tick_init(*s, mass != nullptr, steps != nullptr, positions != nullptr, init_radius);
+    } else {
+      launch_init(*s, mass != nullptr, steps != nullptr, positions != nullptr,
+                  init_radius);
+    }
     WB200_CUDA(cudaStreamSynchronize(s->stream));
     s->initialised = true;
     s->frozen = false;
@@ -244,7 +259,10 @@ int wb200_session_warmup(wb200_session* s, int n_iter, int store, WalnutpyError*
     WB200_CUDA(cudaSetDevice(s->device));
     check_room(s, n_iter, store);
     if (s->frozen) throw std::runtime_error("warm-up after freeze");
-    if (n_iter > 0) launch_chains(*s, n_iter, 1, store != 0);
+    if (n_iter > 0) {
+      if (s->tick) tick_run(*s, n_iter, 1, store != 0);
+      else launch_chains(*s, n_iter, 1, store != 0);
+    }
   });
 }
 
@@ -262,7 +280,10 @@ int wb200_session_sample(wb200_session* s, int n_iter, int store, WalnutpyError*
     WB200_CUDA(cudaSetDevice(s->device));
     check_room(s, n_iter, store);
     if (!s->frozen) throw std::runtime_error("sample before freeze");
-    if (n_iter > 0) launch_chains(*s, n_iter, 0, store != 0);
+    if (n_iter > 0) {
+      if (s->tick) tick_run(*s, n_iter, 0, store != 0);
+      else launch_chains(*s, n_iter, 0, store != 0);
+    }
   });
 }
 

@@ -98,6 +98,8 @@ inline void download_rows(double* dst, int D, const double* src, int ld, size_t 
 
 }  // namespace wb200
 
+namespace wb200 { struct TickEngine; }
+
 struct wb200_session {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -119,6 +121,7 @@ struct wb200_session {
   wb200::DeviceBuffer<int> depth_out;
   wb200::DeviceBuffer<wb200::ChainScalars> sc;
   wb200::DeviceBuffer<unsigned int> ticket;
+  wb200::TickEngine* tick = nullptr;  // lock-step engine (logistic; WB200_ENGINE=tick)
 
   wb200::ChainParams params(int n_iter, int adapt, bool store);
 };
@@ -128,6 +131,13 @@ void launch_chains(wb200_session& s, int n_iter, int adapt, bool store);
 void launch_init(wb200_session& s, bool have_mass, bool have_steps,
                  bool have_positions, double init_radius);
 void launch_freeze(wb200_session& s);
+// lock-step tick engine (tick_engine.cu)
+void tick_create(wb200_session& s, const WalnutModelDesc& model);
+void tick_destroy(wb200_session& s);
+void tick_init(wb200_session& s, bool have_mass, bool have_steps, bool have_positions,
+               double init_radius);
+void tick_run(wb200_session& s, int n_iter, int adapt, bool store);
+unsigned long long tick_count(const wb200_session& s);
 void launch_orbit(int kind, int D, int ld, int C, const double* tparam,
                   double* theta, double* rho, const double* inv_mass, double* grad,
                   double* logp, double* joint, double step, int num_steps,

@@ -1,0 +1,447 @@
+// Host side of the lock-step tick engine (tick_kernel.cuh): buffers, batched
+// initialisation, the tick / gradient loop.  Used for targets whose gradient is a
+// cross-chain batched contraction (logistic regression, logistic.cu); element-wise
+// targets can be routed through it too (WB200_ENGINE=tick) to test the plumbing.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <string>
+
+#include "engine.cuh"
+#include "logistic.cuh"
+#include "tick_kernel.cuh"
+
+namespace wb200 {
+
+struct TickEngine {
+  DeviceBuffer<double> TH, G, LP, vecs;
+  DeviceBuffer<TickState> ts;
+  DeviceBuffer<int> active;
+  int* active_host = nullptr;  // pinned
+  long long vec_stride = 0;
+  LogisticGrad* logistic = nullptr;
+  unsigned long long ticks = 0, grad_batches = 0;
+  ~TickEngine() {
+    delete logistic;
+    if (active_host) cudaFreeHost(active_host);
+  }
+};
+
+// (T, K, CTA) dispatch shared with the chain kernel's shapes
+#define WB200_TICK_SHAPE(S, MACRO)                                             \
+  do {                                                                         \
+    if ((S).T == 32 && (S).K == 1) { MACRO(32, 1, 128); }                      \
+    else if ((S).T == 32 && (S).K == 2) { MACRO(32, 2, 128); }                 \
+    else if ((S).T == 64) { MACRO(64, 2, 64); }                                \
+    else if ((S).T == 128 && (S).K == 2) { MACRO(128, 2, 128); }               \
+    else if ((S).T == 128 && (S).K == 4) { MACRO(128, 4, 128); }               \
+    else if ((S).T == 256 && (S).K == 2) { MACRO(256, 2, 256); }               \
+    else if ((S).T == 256 && (S).K == 4) { MACRO(256, 4, 256); }               \
+    else { MACRO(512, 4, 512); }                                               \
+  } while (0)
+
+template <int T, int CTA>
+__device__ __forceinline__ int group_setup(Group<T>& grp, double* red_smem) {
+  grp.lane = threadIdx.x & 31;
+  grp.red = red_smem;
+  grp.parity = 0;
+  if constexpr (T == 32) {
+    grp.tid = grp.lane;
+    grp.warp = 0;
+    return blockIdx.x * (CTA / 32) + (threadIdx.x >> 5);
+  } else {
+    grp.tid = threadIdx.x;
+    grp.warp = threadIdx.x >> 5;
+    return blockIdx.x;
+  }
+}
+
+// gradient stage for element-wise targets: G, LP at the posted positions TH
+template <template <int, int> class TargetT, int T, int K, int CTA>
+__global__ void __launch_bounds__(CTA) elementwise_grad_kernel(const TickParams tp) {
+  __shared__ double red_smem[group_smem_doubles<T>()];
+  Group<T> grp;
+  const int chain = group_setup<T, CTA>(grp, red_smem);
+  if (chain >= tp.cp.C) return;
+  using V = Vec<T, K>;
+  TargetT<T, K> tgt;
+  tgt.init(tp.cp, grp.tid);
+  double x[K][2], g[K][2], part;
+  const long long off = static_cast<long long>(chain) * tp.cp.ld;
+  V::load(tp.TH + off, tp.cp.ld, grp.tid, x);
+  tgt.grad(x, g, part, grp);
+  double r[1] = {part};
+  grp.sum(r);
+  V::store(tp.G + off, tp.cp.ld, grp.tid, g);
+  if (grp.tid == 0) tp.LP[chain] = r[0];
+}
+
+__global__ void tick_begin_kernel(TickState* ts, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    ts[c].pc = PC_START_TRANSITION;
+    ts[c].done_iters = 0;
+  }
+}
+
+// ---- batched initialisation (config.hpp:259-268, :360-370; util.hpp:285-303) ----
+struct TickInitParams {
+  TickParams tp;
+  int have_positions, have_mass, have_steps;
+  double init_radius, smoothing, step_init;
+  double* mass;   // [C][ld] staged masses (in/out)
+  double* steps;  // [C] staged steps (in/out)
+};
+
+// positions -> TH (request) and TV_CUR
+template <int T, int K, int CTA>
+__global__ void __launch_bounds__(CTA) tick_init_positions_kernel(const TickInitParams ip) {
+  __shared__ double red_smem[group_smem_doubles<T>()];
+  Group<T> grp;
+  const int chain = group_setup<T, CTA>(grp, red_smem);
+  const ChainParams& p = ip.tp.cp;
+  if (chain >= p.C) return;
+  using V = Vec<T, K>;
+  const int tid = grp.tid, ld = p.ld;
+  const uint32_t gchain = p.chain_offset + chain;
+  double th[K][2];
+  double* theta_row = p.theta + static_cast<long long>(chain) * ld;
+  if (ip.have_positions) {
+    V::load(theta_row, ld, tid, th);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int j = tid + k * T;
+      double z0 = 0.0, z1 = 0.0;
+      if (2 * j < p.D) {
+        philox_normal_pair(p.seed, gchain, 0u, kKindInit, j, z0, z1);
+        if (2 * j + 1 >= p.D) z1 = 0.0;
+      }
+      th[k][0] = z0 * ip.init_radius;
+      th[k][1] = z1 * ip.init_radius;
+    }
+    V::store(theta_row, ld, tid, th);
+  }
+  V::store(ip.tp.TH + static_cast<long long>(chain) * ld, ld, tid, th);
+  double* vb = ip.tp.vecs + static_cast<long long>(chain) * ip.tp.vec_stride;
+  V::store(vb + static_cast<long long>(TV_CUR) * ld, ld, tid, th);
+}
+
+// after the first gradient: mass, estimators, scalars, search momentum
+template <int T, int K, int CTA>
+__global__ void __launch_bounds__(CTA) tick_init_state_kernel(const TickInitParams ip) {
+  __shared__ double red_smem[group_smem_doubles<T>()];
+  Group<T> grp;
+  const int chain = group_setup<T, CTA>(grp, red_smem);
+  const ChainParams& p = ip.tp.cp;
+  if (chain >= p.C) return;
+  using V = Vec<T, K>;
+  const int tid = grp.tid, ld = p.ld;
+  const uint32_t gchain = p.chain_offset + chain;
+  const long long off = static_cast<long long>(chain) * ld;
+  double* vb = ip.tp.vecs + static_cast<long long>(chain) * ip.tp.vec_stride;
+  double g[K][2], mass[K][2];
+  V::load(ip.tp.G + off, ld, tid, g);
+  V::store(vb + static_cast<long long>(TV_CUR_G) * ld, ld, tid, g);
+  double* mass_row = ip.mass + off;
+  if (ip.have_mass) {
+    V::load(mass_row, ld, tid, mass);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        mass[k][v] = (1 - ip.smoothing) * fabs(g[k][v]) + ip.smoothing;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      if (2 * (tid + k * T) + v >= p.D) mass[k][v] = 1.0;
+    }
+  }
+  V::store(mass_row, ld, tid, mass);
+  double* est_row = p.est + static_cast<long long>(chain) * 4 * ld;
+  double zero[K][2], sd[K][2], ss[K][2], rho[K][2];
+  double kin = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int j = tid + k * T;
+    double z0 = 0.0, z1 = 0.0;
+    if (2 * j < p.D) {
+      philox_normal_pair(p.seed, gchain, 0u, kKindStepInit, j, z0, z1);
+      if (2 * j + 1 >= p.D) z1 = 0.0;
+    }
+    const double z[2] = {z0, z1};
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      zero[k][v] = 0.0;
+      sd[k][v] = p.mass_init_count * (1.0 / mass[k][v]);
+      ss[k][v] = p.mass_init_count * mass[k][v];
+      rho[k][v] = z[v] * sqrt(mass[k][v]);
+      kin += (1.0 / mass[k][v]) * (rho[k][v] * rho[k][v]);
+    }
+  }
+  V::store(est_row + 0 * ld, ld, tid, zero);
+  V::store(est_row + 1 * ld, ld, tid, sd);
+  V::store(est_row + 2 * ld, ld, tid, zero);
+  V::store(est_row + 3 * ld, ld, tid, ss);
+  V::store(vb + static_cast<long long>(TV_RHO) * ld, ld, tid, rho);
+  double r[1] = {kin};
+  grp.sum(r);
+  if (tid == 0) {
+    const double step = ip.have_steps ? ip.steps[chain] : ip.step_init;
+    ChainScalars sc{};
+    sc.adam_x = log(step);
+    sc.adam_b1p = 1.0; sc.adam_b2p = 1.0;
+    sc.mm_total = 2.0; sc.mm_count = 1.0;
+    sc.est_w = p.mass_init_count;
+    sc.step = step;
+    sc.min_micro = p.min_micro_cfg;
+    p.sc[chain] = sc;
+    TickState st{};
+    st.pc = PC_START_TRANSITION;
+    st.lp_cur = ip.tp.LP[chain];
+    st.Hs = st.lp_cur + (-0.5 * r[0]);   // joint at the start of the step search
+    st.step = step;
+    st.rung = 0;                          // search phase: 0 doubling, 1 shrinking
+    st.reversing = ip.have_steps ? 1 : 0; // search finished?
+    ip.tp.ts[chain] = st;
+  }
+}
+
+// step search, post: theta* = theta + s (M^-1 (rho + s/2 g))  (util.hpp:250-252)
+template <int T, int K, int CTA>
+__global__ void __launch_bounds__(CTA) tick_search_post_kernel(const TickInitParams ip) {
+  __shared__ double red_smem[group_smem_doubles<T>()];
+  Group<T> grp;
+  const int chain = group_setup<T, CTA>(grp, red_smem);
+  const ChainParams& p = ip.tp.cp;
+  if (chain >= p.C) return;
+  using V = Vec<T, K>;
+  const int tid = grp.tid, ld = p.ld;
+  const TickState& st = ip.tp.ts[chain];
+  if (st.reversing) return;
+  const long long off = static_cast<long long>(chain) * ld;
+  double* vb = ip.tp.vecs + static_cast<long long>(chain) * ip.tp.vec_stride;
+  double th[K][2], g[K][2], rho[K][2], mass[K][2];
+  V::load(vb + static_cast<long long>(TV_CUR) * ld, ld, tid, th);
+  V::load(vb + static_cast<long long>(TV_CUR_G) * ld, ld, tid, g);
+  V::load(vb + static_cast<long long>(TV_RHO) * ld, ld, tid, rho);
+  V::load(ip.mass + off, ld, tid, mass);
+  const double s = st.step, hs = 0.5 * s;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const double rs = rho[k][v] + hs * g[k][v];
+      th[k][v] = th[k][v] + s * ((1.0 / mass[k][v]) * rs);
+    }
+  }
+  V::store(ip.tp.TH + off, ld, tid, th);
+}
+
+// step search, update: leapfrog_error and the two while loops of util.hpp:294-301
+template <int T, int K, int CTA>
+__global__ void __launch_bounds__(CTA) tick_search_update_kernel(const TickInitParams ip) {
+  __shared__ double red_smem[group_smem_doubles<T>()];
+  Group<T> grp;
+  const int chain = group_setup<T, CTA>(grp, red_smem);
+  const ChainParams& p = ip.tp.cp;
+  if (chain >= p.C) return;
+  using V = Vec<T, K>;
+  const int tid = grp.tid, ld = p.ld;
+  TickState st = ip.tp.ts[chain];
+  if (st.reversing) return;
+  const long long off = static_cast<long long>(chain) * ld;
+  double* vb = ip.tp.vecs + static_cast<long long>(chain) * ip.tp.vec_stride;
+  double g0[K][2], g1[K][2], rho[K][2], mass[K][2];
+  V::load(vb + static_cast<long long>(TV_CUR_G) * ld, ld, tid, g0);
+  V::load(ip.tp.G + off, ld, tid, g1);
+  V::load(vb + static_cast<long long>(TV_RHO) * ld, ld, tid, rho);
+  V::load(ip.mass + off, ld, tid, mass);
+  const double hs = 0.5 * st.step;
+  double kin = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const double rs = (rho[k][v] + hs * g0[k][v]) + hs * g1[k][v];
+      kin += (1.0 / mass[k][v]) * (rs * rs);
+    }
+  }
+  double r[1] = {kin};
+  grp.sum(r);
+  const double err = (ip.tp.LP[chain] + (-0.5 * r[0])) - st.Hs;
+  const double log09 = log(0.9), log06 = log(0.6);
+  if (st.rung == 0) {
+    if (err > log09 && st.sctr < 200) {
+      st.step *= 2;
+      st.sctr += 1;
+    } else {
+      st.rung = 1;
+      st.sctr = 0;
+    }
+  }
+  if (st.rung == 1) {
+    if (err < log06 && st.sctr < 400) {
+      st.step *= sqrt(0.5);
+      st.sctr += 1;
+    } else {
+      st.reversing = 1;
+    }
+  }
+  if (tid == 0) {
+    ip.tp.ts[chain] = st;
+    if (st.reversing) {
+      ChainScalars& sc = p.sc[chain];
+      sc.adam_x = log(st.step);
+      sc.step = st.step;
+      ip.steps[chain] = st.step;
+    } else {
+      atomicAdd(ip.tp.active_count, 1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+static TickParams tick_params(wb200_session& s, int n_iter, int adapt, bool store) {
+  TickEngine& e = *s.tick;
+  TickParams tp{};
+  tp.cp = s.params(n_iter, adapt, store);
+  tp.TH = e.TH.ptr; tp.G = e.G.ptr; tp.LP = e.LP.ptr;
+  tp.vecs = e.vecs.ptr; tp.vec_stride = e.vec_stride;
+  tp.ts = e.ts.ptr; tp.active_count = e.active.ptr;
+  return tp;
+}
+
+#define WB200_EW_GRAD(T_, K_, CTA_)                                                     \
+  do {                                                                                  \
+    if (s.kind == kStdNormal)                                                           \
+      elementwise_grad_kernel<StdNormalTarget, T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(tp); \
+    else if (s.kind == kDiagGaussian)                                                   \
+      elementwise_grad_kernel<DiagGaussianTarget, T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(tp); \
+    else                                                                                \
+      elementwise_grad_kernel<FunnelTarget, T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(tp); \
+  } while (0)
+
+static void tick_gradient(wb200_session& s, const TickParams& tp) {
+  TickEngine& e = *s.tick;
+  if (s.kind == kLogistic) {
+    e.logistic->evaluate(e.TH.ptr, e.G.ptr, e.LP.ptr, s.stream);
+    s.launches += e.logistic->kernels_per_eval();
+  } else {
+    const int grid = (s.C + s.shape.chains_per_cta - 1) / s.shape.chains_per_cta;
+    WB200_TICK_SHAPE(s.shape, WB200_EW_GRAD);
+    WB200_CUDA(cudaGetLastError());
+    s.launches += 1;
+  }
+  e.grad_batches += 1;
+}
+
+static int read_active(wb200_session& s) {
+  TickEngine& e = *s.tick;
+  WB200_CUDA(cudaMemcpyAsync(e.active_host, e.active.ptr, sizeof(int), cudaMemcpyDeviceToHost,
+                             s.stream));
+  WB200_CUDA(cudaStreamSynchronize(s.stream));
+  return *e.active_host;
+}
+
+void tick_create(wb200_session& s, const WalnutModelDesc& model) {
+  s.tick = new TickEngine();
+  TickEngine& e = *s.tick;
+  const size_t CL = static_cast<size_t>(s.C) * s.ld;
+  const int nvec = tick_vectors(s.tuning.max_trajectory_doublings);
+  e.vec_stride = static_cast<long long>(nvec) * s.ld;
+  e.TH.alloc(CL); e.G.alloc(CL); e.LP.alloc(s.C);
+  e.vecs.alloc(static_cast<size_t>(e.vec_stride) * s.C);
+  e.ts.alloc(s.C);
+  e.active.alloc(1);
+  WB200_CUDA(cudaMallocHost(&e.active_host, sizeof(int)));
+  WB200_CUDA(cudaMemsetAsync(e.TH.ptr, 0, CL * 8, s.stream));
+  WB200_CUDA(cudaMemsetAsync(e.G.ptr, 0, CL * 8, s.stream));
+  WB200_CUDA(cudaMemsetAsync(e.vecs.ptr, 0, e.vecs.count * 8, s.stream));
+  WB200_CUDA(cudaMemsetAsync(e.ts.ptr, 0, s.C * sizeof(TickState), s.stream));
+  if (s.kind == kLogistic) {
+    if (!model.data0 || !model.data1 || model.N < 1) {
+      throw std::invalid_argument("logistic needs data0 = X[N][D], data1 = y[N], N >= 1");
+    }
+    e.logistic = new LogisticGrad(static_cast<const double*>(model.data0),
+                                  static_cast<const double*>(model.data1), model.N, s.D, s.C,
+                                  s.ld, s.stream);
+  }
+}
+
+void tick_destroy(wb200_session& s) {
+  delete s.tick;
+  s.tick = nullptr;
+}
+
+#define WB200_TICK_INIT_POS(T_, K_, CTA_) \
+  tick_init_positions_kernel<T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(ip)
+#define WB200_TICK_INIT_STATE(T_, K_, CTA_) \
+  tick_init_state_kernel<T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(ip)
+#define WB200_TICK_SEARCH_POST(T_, K_, CTA_) \
+  tick_search_post_kernel<T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(ip)
+#define WB200_TICK_SEARCH_UPDATE(T_, K_, CTA_) \
+  tick_search_update_kernel<T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(ip)
+#define WB200_TICK_RUN(T_, K_, CTA_) \
+  walnuts_tick_kernel<T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(tp)
+
+void tick_init(wb200_session& s, bool have_mass, bool have_steps, bool have_positions,
+               double init_radius) {
+  TickEngine& e = *s.tick;
+  TickInitParams ip{};
+  ip.tp = tick_params(s, 0, 1, false);
+  ip.have_positions = have_positions;
+  ip.have_mass = have_mass;
+  ip.have_steps = have_steps;
+  ip.init_radius = init_radius;
+  ip.smoothing = s.tuning.mass_additive_smoothing;
+  ip.step_init = s.tuning.step_size_init;
+  ip.mass = s.inv_mass.ptr;  // masses staged in the inv_mass buffer until freeze
+  ip.steps = s.red.ptr;
+  const int grid = (s.C + s.shape.chains_per_cta - 1) / s.shape.chains_per_cta;
+  WB200_TICK_SHAPE(s.shape, WB200_TICK_INIT_POS);
+  WB200_CUDA(cudaGetLastError());
+  tick_gradient(s, ip.tp);
+  WB200_TICK_SHAPE(s.shape, WB200_TICK_INIT_STATE);
+  WB200_CUDA(cudaGetLastError());
+  s.launches += 2;
+  if (!have_steps) {
+    for (int it = 0; it < 700; ++it) {
+      WB200_CUDA(cudaMemsetAsync(e.active.ptr, 0, sizeof(int), s.stream));
+      WB200_TICK_SHAPE(s.shape, WB200_TICK_SEARCH_POST);
+      tick_gradient(s, ip.tp);
+      WB200_TICK_SHAPE(s.shape, WB200_TICK_SEARCH_UPDATE);
+      WB200_CUDA(cudaGetLastError());
+      s.launches += 2;
+      if (read_active(s) == 0) break;
+    }
+  }
+}
+
+void tick_run(wb200_session& s, int n_iter, int adapt, bool store) {
+  TickEngine& e = *s.tick;
+  TickParams tp = tick_params(s, n_iter, adapt, store);
+  const int grid = (s.C + s.shape.chains_per_cta - 1) / s.shape.chains_per_cta;
+  tick_begin_kernel<<<(s.C + 255) / 256, 256, 0, s.stream>>>(e.ts.ptr, s.C);
+  WB200_CUDA(cudaEventRecord(s.ev0, s.stream));
+  while (true) {
+    WB200_CUDA(cudaMemsetAsync(e.active.ptr, 0, sizeof(int), s.stream));
+    WB200_TICK_SHAPE(s.shape, WB200_TICK_RUN);
+    WB200_CUDA(cudaGetLastError());
+    s.launches += 1;
+    e.ticks += 1;
+    if (read_active(s) == 0) break;
+    tick_gradient(s, tp);
+  }
+  WB200_CUDA(cudaEventRecord(s.ev1, s.stream));
+  if (store) s.rows_written += n_iter;
+}
+
+unsigned long long tick_count(const wb200_session& s) { return s.tick ? s.tick->ticks : 0; }
+
+}  // namespace wb200

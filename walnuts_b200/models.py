@@ -67,3 +67,14 @@ def ill_conditioned_gaussian(num_params: int, condition: float = 1e4) -> DeviceM
 def funnel(num_params: int) -> DeviceModel:
     """Neal's funnel: x0 ~ N(0, 9), x_i | x0 ~ N(0, exp(x0))."""
     return DeviceModel("funnel", num_params)
+
+
+def logistic(X, y) -> DeviceModel:
+    """Bayesian logistic regression with a N(0, I) prior: logp = sum_n [y_n z_n -
+    softplus(z_n)] - |theta|^2 / 2, z = X theta.  X is rounded to bf16 on the device
+    (the gradient is two tensor-core GEMMs batched over all chains)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    if X.ndim != 2 or y.shape != (X.shape[0],):
+        raise ValueError("X must be [N][D] and y [N]")
+    return DeviceModel("logistic", X.shape[1], X=X, y=y)
