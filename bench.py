@@ -46,6 +46,11 @@ MAX_HALVINGS = 5
 SEED = 20250
 ALG_BYTES_PER_EVAL = 7 * D * 8  # read theta, rho, grad, M^-1; write theta, rho, grad
 
+# --workload c4: Bayesian logistic regression (BASELINE.json configs[3]); not the
+# default line (the driver's N=1 run is c2), used for the tensor-core roofline
+C4 = dict(N=100_000, D=512, chains=8192, warmup_iters=60, iters_per_step=2,
+          max_doublings=8, max_halvings=5)
+
 
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
@@ -110,6 +115,123 @@ def variances():
     return COND ** (np.arange(D, dtype=np.float64) / (D - 1))
 
 
+def bf16_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return (float(j["bf16_tflops_sustained"]), float(j["bf16_tflops"]),
+                "measured (MEASURED_PEAKS.json bf16_tflops_sustained; burst in peak_burst)")
+    return 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def logistic_data(N, Dm):
+    """X iid N(0,1) rounded to bf16, theta* ~ N(0, I/D),
+    y ~ Bernoulli(sigmoid(X theta*)); host generator seeded 20250."""
+    import torch
+    rng = np.random.default_rng(SEED)
+    X = torch.tensor(rng.standard_normal((N, Dm), dtype=np.float32)).to(torch.bfloat16)
+    X = X.to(torch.float64).numpy()
+    tstar = rng.standard_normal(Dm) / np.sqrt(Dm)
+    y = (rng.uniform(size=N) < 1.0 / (1.0 + np.exp(-X @ tstar))).astype(np.float64)
+    return X, y
+
+
+def run_c4(args):
+    """Logistic regression, lock-step tick engine + tcgen05 gradient (1 GPU)."""
+    import torch
+
+    import walnuts_b200 as wb
+    from oracle.binding import Target, default_config
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: walnuts_b200 has no CPU path")
+    cfgw = dict(C4)
+    C = args.chains if args.chains != CHAINS_PER_GPU else cfgw["chains"]
+    N, Dm = cfgw["N"], cfgw["D"]
+    ips = args.iters_per_step if args.iters_per_step != 10 else cfgw["iters_per_step"]
+    K, W = args.steps, args.warmup
+    X, y = logistic_data(N, Dm)
+    tune = dict(max_trajectory_doublings=cfgw["max_doublings"],
+                max_step_halvings=cfgw["max_halvings"])
+    sess = wb.Session(wb.models.logistic(X, y), C, seed=SEED, **tune)
+    sess.init(init_radius=0.5)
+    sess.reserve((W + K) * ips)
+    c0 = sess.counters()
+    t0 = time.perf_counter()
+    sess.warmup(cfgw["warmup_iters"])
+    sess.freeze().sync()
+    warm_s = time.perf_counter() - t0
+    c1 = sess.counters()
+    for _ in range(W):
+        sess.sample(ips)
+    sess.sync()
+    c2 = sess.counters()
+    torch.cuda.synchronize()
+    with ClockSampler(0) as clocks:
+        t0 = time.perf_counter()
+        sess.timer_start()
+        for _ in range(K):
+            sess.sample(ips)
+        total_ms = sess.timer_stop_ms()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+    c3 = sess.counters()
+    evals = c3["grad_evals"] - c2["grad_evals"]
+    launches = c3["kernel_launches"] - c2["kernel_launches"]
+    value = evals / (total_ms * 1e-3)
+    summ = sess.summary(W * ips, K * ips)
+    sess.close()
+    # stand-alone timing of the batched gradient (the dominant kernels)
+    from walnuts_b200.sampler import logistic_logp_grad
+    theta = np.random.default_rng(1).normal(size=(C, Dm)) * 0.05
+    _, _, grad_ms = logistic_logp_grad(X, y, theta, repeats=5)
+    sustained, burst, src = bf16_peaks()
+    flops_alg = 4.0 * N * Dm
+    achieved = value * flops_alg / 1e12
+    # CPU baseline: the oracle port of the same sampler on a bounded sample
+    checker, kind = load_cpu_checker()
+    cores = os.cpu_count() or 1
+    target = Target("logistic", Dm, X=X, y=y)
+    ccfg = default_config(min_warmup_iter=4, max_warmup_iter=4, min_sampling_iter=4,
+                          max_sampling_iter=4, max_trajectory_doublings=cfgw["max_doublings"],
+                          max_step_halvings=cfgw["max_halvings"])
+    pos = checker.init_positions(cores, Dm, SEED, 0.5)
+    mass = np.ones((cores, Dm))
+    steps = np.full(cores, 0.02)
+    t0 = time.perf_counter()
+    r = checker.walnuts(target, ccfg, SEED, pos, mass, steps)
+    cpu_s = time.perf_counter() - t0
+    line = {
+        "metric": "grad_evals_per_sec", "value": value, "unit": "grad_evals/s", "n_gpus": 1,
+        "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tensor cores (hi+lo split), "
+        "fp32 accumulate, fp64 state", "data": "synthetic",
+        "config": {"workload": "c4: Bayesian logistic regression N=100k, D=512, 8192 chains, "
+                               "lock-step tick engine + tcgen05 batched gradient",
+                   "N": N, "dims": Dm, "chains_per_gpu": C, "iters_per_step": ips,
+                   "adaptive_warmup_iters": cfgw["warmup_iters"],
+                   "max_trajectory_doublings": cfgw["max_doublings"],
+                   "l2": "operands (X 102 MB, R^T 1.6 GB) exceed the 126 MB L2"},
+        "min_ess_per_sec": float(np.min(summ["ess"])) / (total_ms * 1e-3),
+        "max_r_hat": float(np.max(summ["r_hat"])),
+        "wall_ms": wall_ms, "gpu_launches": int(launches),
+        "warmup_phase": {"iters": cfgw["warmup_iters"], "seconds": warm_s,
+                         "grad_evals_per_sec": (c1["grad_evals"] - c0["grad_evals"]) / warm_s},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained,
+                     "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": None,
+                     "peak_burst": burst, "peak_source": src,
+                     "algorithmic_flops_per_eval": flops_alg,
+                     "gradient_only_ms_per_batched_eval": grad_ms,
+                     "gradient_only_tflops": C * flops_alg / (grad_ms * 1e-3) / 1e12,
+                     "kernel": "gemm_kmajor_kernel<128,1> + gemm_kmajor_kernel<256,2>"},
+        "cpu_baseline": {"value": r["grad_evals"] / cpu_s, "unit": "grad_evals/s",
+                         "cores": cores, "kind": kind,
+                         "sample": f"{cores} chains x (4 warm-up + 4 sampling) iterations, "
+                                   "same data", "seconds": cpu_s},
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
 # ---------------------------------------------------------------------------
 def reference_step(checker, kind, chains, warm, samp, seed):
     """One bounded sample of the workload on the host cores: `chains` chains of
@@ -142,7 +264,7 @@ def run_reference_arm(args):
         return
     checker, kind = load_cpu_checker()
     cores = os.cpu_count() or 1
-    warm, samp = 100, 10 * args.iters_per_step
+    warm, samp = 100, 50 * args.iters_per_step
     for i in range(args.warmup):
         reference_step(checker, kind, cores, warm, samp, SEED + i)
     evals, secs = 0, 0.0
@@ -289,7 +411,7 @@ def run_ours(args):
     # ---- CPU baseline on a bounded sample of the same workload
     checker, kind = load_cpu_checker()
     cores = os.cpu_count() or 1
-    cpu_warm, cpu_samp = 100, 100
+    cpu_warm, cpu_samp = 300, 1000
     cpu_evals, cpu_s, cpu_draws = reference_step(checker, kind, cores, cpu_warm, cpu_samp, SEED)
     oracle_checker = checker if kind == "port" else __import__(
         "oracle.binding", fromlist=["load_oracle"]).load_oracle()
@@ -362,11 +484,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU)
     ap.add_argument("--iters-per-step", type=int, default=10)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "c4":
+        run_c4(args)
     else:
         run_ours(args)
 
