@@ -48,7 +48,7 @@ ALG_BYTES_PER_EVAL = 7 * D * 8  # read theta, rho, grad, M^-1; write theta, rho,
 
 # --workload c4: Bayesian logistic regression (BASELINE.json configs[3]); not the
 # default line (the driver's N=1 run is c2), used for the tensor-core roofline
-C4 = dict(N=100_000, D=512, chains=8192, warmup_iters=60, iters_per_step=2,
+C4 = dict(N=100_000, D=512, chains=8192, warmup_iters=100, ticks_per_step=40,
           max_doublings=8, max_halvings=5)
 
 
@@ -148,22 +148,25 @@ def run_c4(args):
     cfgw = dict(C4)
     C = args.chains if args.chains != CHAINS_PER_GPU else cfgw["chains"]
     N, Dm = cfgw["N"], cfgw["D"]
-    ips = args.iters_per_step if args.iters_per_step != 10 else cfgw["iters_per_step"]
+    tps = args.iters_per_step if args.iters_per_step != 10 else cfgw["ticks_per_step"]
     K, W = args.steps, args.warmup
     X, y = logistic_data(N, Dm)
     tune = dict(max_trajectory_doublings=cfgw["max_doublings"],
                 max_step_halvings=cfgw["max_halvings"])
     sess = wb.Session(wb.models.logistic(X, y), C, seed=SEED, **tune)
-    sess.init(init_radius=0.5)
-    sess.reserve((W + K) * ips)
+    sess.init(init_radius=0.1)
+    cap = max(8, (W + K) * tps // 8)  # room for the draws of the free-running phase
+    sess.reserve(cap)
     c0 = sess.counters()
     t0 = time.perf_counter()
     sess.warmup(cfgw["warmup_iters"])
     sess.freeze().sync()
     warm_s = time.perf_counter() - t0
     c1 = sess.counters()
+    # a step = `tps` lock-step ticks: one batched gradient evaluation for every chain per
+    # tick; chains roll straight into their next transition (free-running, ragged draws)
     for _ in range(W):
-        sess.sample(ips)
+        sess.sample_ticks(tps)
     sess.sync()
     c2 = sess.counters()
     torch.cuda.synchronize()
@@ -171,14 +174,16 @@ def run_c4(args):
         t0 = time.perf_counter()
         sess.timer_start()
         for _ in range(K):
-            sess.sample(ips)
+            sess.sample_ticks(tps)
         total_ms = sess.timer_stop_ms()
         wall_ms = 1e3 * (time.perf_counter() - t0)
     c3 = sess.counters()
     evals = c3["grad_evals"] - c2["grad_evals"]
     launches = c3["kernel_launches"] - c2["kernel_launches"]
     value = evals / (total_ms * 1e-3)
-    summ = sess.summary(W * ips, K * ips)
+    rows = sess.chain_rows()
+    summ = sess.summary_ragged(0)
+    active_lane_fraction = evals / float(K * tps * C)
     sess.close()
     # stand-alone timing of the batched gradient (the dominant kernels)
     from walnuts_b200.sampler import logistic_logp_grad
@@ -207,12 +212,15 @@ def run_c4(args):
         "fp32 accumulate, fp64 state", "data": "synthetic",
         "config": {"workload": "c4: Bayesian logistic regression N=100k, D=512, 8192 chains, "
                                "lock-step tick engine + tcgen05 batched gradient",
-                   "N": N, "dims": Dm, "chains_per_gpu": C, "iters_per_step": ips,
+                   "N": N, "dims": Dm, "chains_per_gpu": C, "ticks_per_step": tps,
                    "adaptive_warmup_iters": cfgw["warmup_iters"],
                    "max_trajectory_doublings": cfgw["max_doublings"],
                    "l2": "operands (X 102 MB, R^T 1.6 GB) exceed the 126 MB L2"},
         "min_ess_per_sec": float(np.min(summ["ess"])) / (total_ms * 1e-3),
         "max_r_hat": float(np.max(summ["r_hat"])),
+        "active_lane_fraction": active_lane_fraction,
+        "draws_per_chain": {"min": int(rows.min()), "mean": float(rows.mean()),
+                            "max": int(rows.max())},
         "wall_ms": wall_ms, "gpu_launches": int(launches),
         "warmup_phase": {"iters": cfgw["warmup_iters"], "seconds": warm_s,
                          "grad_evals_per_sec": (c1["grad_evals"] - c0["grad_evals"]) / warm_s},

@@ -166,6 +166,15 @@ int wb200_session_warmup(wb200_session* s, int n_iter, int store,
 int wb200_session_freeze(wb200_session* s, WalnutpyError** err);
 int wb200_session_sample(wb200_session* s, int n_iter, int store,
                          WalnutpyError** err);
+/* Lock-step sessions only: exactly n_ticks ticks (one batched gradient each); every
+ * chain completes as many transitions as fit, so draw counts become ragged, as in the
+ * reference's adaptive runs.  wb200_session_chain_rows returns the rows stored per
+ * chain; wb200_session_summary summarises rows [first, rows_c) of every chain. */
+int wb200_session_sample_ticks(wb200_session* s, int n_ticks, int store,
+                               WalnutpyError** err);
+int wb200_session_chain_rows(wb200_session* s, long long* rows, WalnutpyError** err);
+int wb200_session_summary(wb200_session* s, long long first, double* rhat, double* ess,
+                          double* mcse, double* mean, double* var, WalnutpyError** err);
 /* block until the session's stream is idle */
 int wb200_session_sync(wb200_session* s, WalnutpyError** err);
 

@@ -235,6 +235,13 @@ session_warmup = _sess("wb200_session_warmup", [session_p, ctypes.c_int, ctypes.
 session_freeze = _sess("wb200_session_freeze", [session_p])
 session_sample = _sess("wb200_session_sample", [session_p, ctypes.c_int, ctypes.c_int])
 session_sync = _sess("wb200_session_sync", [session_p])
+session_sample_ticks = _sess("wb200_session_sample_ticks",
+                             [session_p, ctypes.c_int, ctypes.c_int])
+session_chain_rows = _sess("wb200_session_chain_rows", [
+    session_p, ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")])
+session_summary = _sess("wb200_session_summary", [
+    session_p, ctypes.c_longlong, nullable_double_array, nullable_double_array,
+    nullable_double_array, nullable_double_array, nullable_double_array])
 session_warmup_sums = _sess("wb200_session_warmup_sums", [session_p, ctypes.c_void_p])
 session_warmup_deviation = _sess("wb200_session_warmup_deviation",
                                  [session_p, ctypes.c_void_p, double_array])
@@ -306,7 +313,8 @@ EXPORTED_SYMBOLS = [
     "walnutpie_destroy_error", "walnuts_b200_default_tuning", "walnuts_b200_version",
     "wb200_session_create", "wb200_session_destroy", "wb200_session_init",
     "wb200_session_reserve_draws", "wb200_session_warmup", "wb200_session_freeze",
-    "wb200_session_sample", "wb200_session_sync", "wb200_session_warmup_sums",
+    "wb200_session_sample", "wb200_session_sync", "wb200_session_sample_ticks",
+    "wb200_session_chain_rows", "wb200_session_summary", "wb200_session_warmup_sums",
     "wb200_session_warmup_deviation", "wb200_session_lp_moments",
     "wb200_session_get_draws", "wb200_session_get_trace", "wb200_session_get_state",
     "wb200_session_device_draws", "wb200_session_counters",

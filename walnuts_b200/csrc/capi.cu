@@ -287,6 +287,52 @@ int wb200_session_sample(wb200_session* s, int n_iter, int store, WalnutpyError*
   });
 }
 
+int wb200_session_sample_ticks(wb200_session* s, int n_ticks, int store,
+                               WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    if (!s->tick) throw std::runtime_error("sample_ticks needs the lock-step engine");
+    if (!s->frozen) throw std::runtime_error("sample before freeze");
+    if (n_ticks < 0) throw std::invalid_argument("n_ticks must be non-negative");
+    if (store && s->draw_cap == 0) throw std::runtime_error("reserve draws first");
+    tick_run_ticks(*s, n_ticks, 0, store != 0);
+  });
+}
+
+int wb200_session_chain_rows(wb200_session* s, long long* rows, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    if (s->tick) {
+      tick_chain_rows(*s, rows);
+      for (int c = 0; c < s->C; ++c) rows[c] = std::max(rows[c], s->rows_written);
+    } else {
+      for (int c = 0; c < s->C; ++c) rows[c] = s->rows_written;
+    }
+  });
+}
+
+int wb200_session_summary(wb200_session* s, long long first, double* rhat, double* ess,
+                          double* mcse, double* mean, double* var, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    std::vector<long long> rows(s->C), start(s->C), len(s->C);
+    WalnutpyError* e = nullptr;
+    if (wb200_session_chain_rows(s, rows.data(), &e) != 0) {
+      std::string msg = e ? e->msg : "chain_rows failed";
+      delete e;
+      throw std::runtime_error(msg);
+    }
+    for (int c = 0; c < s->C; ++c) {
+      start[c] = static_cast<long long>(c) * s->draw_cap + first;
+      len[c] = rows[c] - first;
+      if (len[c] < 1) throw std::invalid_argument("a chain has no draws in the range");
+    }
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+    device_summary(s->draws.ptr, s->ld, s->D, start, len, rhat, ess, mcse, mean, var,
+                   s->stream);
+  });
+}
+
 int wb200_session_sync(wb200_session* s, WalnutpyError** err) {
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));

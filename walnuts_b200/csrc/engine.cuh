@@ -137,6 +137,8 @@ void tick_destroy(wb200_session& s);
 void tick_init(wb200_session& s, bool have_mass, bool have_steps, bool have_positions,
                double init_radius);
 void tick_run(wb200_session& s, int n_iter, int adapt, bool store);
+void tick_run_ticks(wb200_session& s, int n_ticks, int adapt, bool store);
+void tick_chain_rows(wb200_session& s, long long* rows_host);
 unsigned long long tick_count(const wb200_session& s);
 void launch_orbit(int kind, int D, int ld, int C, const double* tparam,
                   double* theta, double* rho, const double* inv_mass, double* grad,

@@ -5,7 +5,7 @@
 //   grad_c = X^T (y - sigmoid(z_c)) - theta_c
 //
 // (the density itself is not in the reference repo — the CPU
-// statement is oracle/targets.hpp `Logistic`.)  Per tick:
+// statement the tests check it against is the `Logistic` target of the test oracle.)  Per tick:
 //
 //   pack      Theta fp64 [C][ld]  ->  bf16 hi / lo planes [Cpad][Dpad]
 //   GEMM 1    Z^T[c][n] = (hi + lo)[c][:] . X[n][:]    (K = 2*Dpad, fp32 in TMEM; a chain

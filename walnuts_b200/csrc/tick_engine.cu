@@ -442,6 +442,48 @@ void tick_run(wb200_session& s, int n_iter, int adapt, bool store) {
   if (store) s.rows_written += n_iter;
 }
 
+// free-running: chains that finished an iteration quota start over; nothing is reset
+__global__ void tick_resume_kernel(TickState* ts, int C, long long rows_floor) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    if (ts[c].pc == PC_DONE) ts[c].pc = PC_START_TRANSITION;
+    if (ts[c].rows < rows_floor) ts[c].rows = rows_floor;
+  }
+}
+
+__global__ void tick_rows_kernel(const TickState* ts, int C, long long* rows) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) rows[c] = ts[c].rows;
+}
+
+// exactly n_ticks lock-step ticks; every chain does as many transitions as fit
+// (ragged draw counts, like the reference's adaptive runs)
+void tick_run_ticks(wb200_session& s, int n_ticks, int adapt, bool store) {
+  TickEngine& e = *s.tick;
+  TickParams tp = tick_params(s, -1, adapt, store);
+  const int grid = (s.C + s.shape.chains_per_cta - 1) / s.shape.chains_per_cta;
+  tick_resume_kernel<<<(s.C + 255) / 256, 256, 0, s.stream>>>(e.ts.ptr, s.C, s.rows_written);
+  WB200_CUDA(cudaEventRecord(s.ev0, s.stream));
+  for (int t = 0; t < n_ticks; ++t) {
+    WB200_TICK_SHAPE(s.shape, WB200_TICK_RUN);
+    WB200_CUDA(cudaGetLastError());
+    tick_gradient(s, tp);
+    s.launches += 1;
+    e.ticks += 1;
+  }
+  WB200_CUDA(cudaEventRecord(s.ev1, s.stream));
+}
+
+void tick_chain_rows(wb200_session& s, long long* rows_host) {
+  TickEngine& e = *s.tick;
+  DeviceBuffer<long long> d;
+  d.alloc(s.C);
+  tick_rows_kernel<<<(s.C + 255) / 256, 256, 0, s.stream>>>(e.ts.ptr, s.C, d.ptr);
+  WB200_CUDA(cudaMemcpyAsync(rows_host, d.ptr, s.C * sizeof(long long),
+                             cudaMemcpyDeviceToHost, s.stream));
+  WB200_CUDA(cudaStreamSynchronize(s.stream));
+}
+
 unsigned long long tick_count(const wb200_session& s) { return s.tick ? s.tick->ticks : 0; }
 
 }  // namespace wb200

@@ -40,6 +40,7 @@ enum : int { PC_START_TRANSITION = 0, PC_IN_INTEGRATE = 1, PC_DONE = 2 };
 struct TickState {
   int pc;
   int done_iters;
+  long long rows;  // draws this chain has stored so far (ragged / free-running mode)
   // transition
   uint32_t sctr;
   int depth, dir, nleaf, leaf_i, sp, regs_dir, first_ext;
@@ -200,7 +201,7 @@ struct TickRunner {
         }
         load_metric(sc, chain);
         if (p.adapt) V::store(vv(TV_IM), ld, tid, im);
-        const long long row = p.draw_base + st.done_iters;
+        const long long row = p.n_iter < 0 ? st.rows : p.draw_base + st.done_iters;
         if (p.im_out) {
           V::store(p.im_out + (static_cast<long long>(chain) * p.draw_cap + row) * ld,
                    ld, tid, im);
@@ -497,7 +498,8 @@ struct TickRunner {
         V::store(vv(TV_CUR), ld, tid, cur);
         V::store(vv(TV_CUR_G), ld, tid, gsel);
         st.lp_cur = st.lp_sel;
-        const long long row = p.draw_base + st.done_iters;
+        const bool ragged = p.n_iter < 0;  // free-running: no iteration quota
+        const long long row = ragged ? st.rows : p.draw_base + st.done_iters;
         if (p.adapt) {
           double* est_row = p.est + static_cast<long long>(chain) * 4 * ld;
           const double gamma =
@@ -544,7 +546,8 @@ struct TickRunner {
           if (p.step_out) p.step_out[o] = p.adapt ? exp_noinline(sc.adam_x) : sc.step;
         }
         st.done_iters += 1;
-        if (st.done_iters >= p.n_iter) {
+        if (p.draws) st.rows = row + 1;
+        if (ragged ? (p.draws && st.rows >= p.draw_cap) : (st.done_iters >= p.n_iter)) {
           st.pc = PC_DONE;
           // keep theta in sync with the chain kernel's convention
           V::store(p.theta + static_cast<long long>(chain) * ld, ld, tid, cur);

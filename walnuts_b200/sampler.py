@@ -215,6 +215,26 @@ class Session:
         _ffi.session_sync(self._h)
         return self
 
+    def sample_ticks(self, n_ticks: int, store: bool = True):
+        """Lock-step sessions: exactly ``n_ticks`` ticks (one batched gradient each);
+        chains complete as many transitions as fit (ragged draw counts)."""
+        _ffi.session_sample_ticks(self._h, int(n_ticks), int(store))
+        return self
+
+    def chain_rows(self) -> np.ndarray:
+        rows = np.zeros(self.num_chains, np.int64)
+        _ffi.session_chain_rows(self._h, rows)
+        return rows
+
+    def summary_ragged(self, first: int = 0):
+        """R-hat / ESS / MCSE / mean / variance over rows [first, rows_c) of every chain."""
+        D = self.num_params
+        out = {k: np.zeros(D) for k in ("r_hat", "ess", "mcse", "mean", "variance")}
+        _ffi.session_summary(self._h, int(first),
+                             out["r_hat"] if self.num_chains > 1 else None, out["ess"],
+                             out["mcse"], out["mean"], out["variance"])
+        return out
+
     def draws(self, first: int, count: int) -> np.ndarray:
         out = np.zeros((self.num_chains, count, self.num_params))
         _ffi.session_get_draws(self._h, first, count, out)
