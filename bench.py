@@ -48,7 +48,7 @@ ALG_BYTES_PER_EVAL = 7 * D * 8  # read theta, rho, grad, M^-1; write theta, rho,
 
 # --workload c4: Bayesian logistic regression (BASELINE.json configs[3]); not the
 # default line (the driver's N=1 run is c2), used for the tensor-core roofline
-C4 = dict(N=100_000, D=512, chains=8192, warmup_iters=100, ticks_per_step=40,
+C4 = dict(N=100_000, D=512, chains=8192, warmup_iters=100, ticks_per_step=100,
           max_doublings=8, max_halvings=5)
 
 

@@ -322,11 +322,19 @@ int wb200_session_summary(wb200_session* s, long long first, double* rhat, doubl
       delete e;
       throw std::runtime_error(msg);
     }
+    // chains that have not yet stored 3 draws in the range (long first transitions in
+    // free-running mode) are left out, as summary.hpp:595-603 would reject them
+    int kept = 0;
     for (int c = 0; c < s->C; ++c) {
-      start[c] = static_cast<long long>(c) * s->draw_cap + first;
-      len[c] = rows[c] - first;
-      if (len[c] < 1) throw std::invalid_argument("a chain has no draws in the range");
+      const long long l = rows[c] - first;
+      if (l < 3) continue;
+      start[kept] = static_cast<long long>(c) * s->draw_cap + first;
+      len[kept] = l;
+      ++kept;
     }
+    if (kept < 2) throw std::invalid_argument("fewer than two chains have 3 draws in the range");
+    start.resize(kept);
+    len.resize(kept);
     WB200_CUDA(cudaStreamSynchronize(s->stream));
     device_summary(s->draws.ptr, s->ld, s->D, start, len, rhat, ess, mcse, mean, var,
                    s->stream);
