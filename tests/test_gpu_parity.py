@@ -435,3 +435,34 @@ def test_logistic_sampler_moments_match_oracle_within_mcse(wb, oracle):
     z = np.abs(summ["mean"] - cpu_mean) / np.sqrt(summ["mcse"] ** 2 + cpu_mcse ** 2)
     assert np.max(z) < 5.0, z
     assert np.max(np.abs(summ["variance"] / cpu_var - 1)) < 0.25
+
+
+def test_free_running_ticks_give_ragged_draws_with_the_same_posterior(wb, oracle):
+    """Lock-step budget mode: exactly n ticks, chains roll straight into their next
+    transition, so draw counts are ragged (as the reference's adaptive runs are) while
+    every lane stays busy; the posterior is the same as with iteration quotas."""
+    N, D, C = 400, 6, 192
+    X, y = make_logistic(N, D, 3)
+    with wb.Session(wb.models.logistic(X, y), C, seed=8, max_trajectory_doublings=7) as s:
+        s.init(init_radius=0.5)
+        s.reserve(400)
+        s.warmup(120).freeze()
+        before = s.counters()["grad_evals"]
+        s.sample_ticks(600).sync()
+        evals = s.counters()["grad_evals"] - before
+        rows = s.chain_rows()
+        ragged = s.summary_ragged(0)
+    assert evals == 600 * C                      # every chain consumed a gradient per tick
+    assert rows.min() >= 3 and rows.max() > rows.min()   # ragged
+    target = Target("logistic", D, X=X, y=y)
+    cfg = default_config(min_warmup_iter=120, max_warmup_iter=120, min_sampling_iter=400,
+                         max_sampling_iter=400, max_trajectory_doublings=7)
+    pos = oracle.init_positions(8, D, 4, 0.5)
+    mass, steps = oracle.init_mass_step(target, pos, 4, 1.0)
+    cpu = oracle.walnuts(target, cfg, 4, pos, mass, steps)
+    chains = [cpu["out"][c, :400] for c in range(8)]
+    cpu_mean = np.mean(np.concatenate(chains), axis=0)
+    cpu_mcse = oracle.mcse(chains)
+    z = np.abs(ragged["mean"] - cpu_mean) / np.sqrt(ragged["mcse"] ** 2 + cpu_mcse ** 2)
+    assert np.max(z) < 5.0, z
+    assert np.max(ragged["r_hat"]) < 1.05

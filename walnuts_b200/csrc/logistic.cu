@@ -10,9 +10,9 @@
 //   pack      Theta fp64 [C][ld]  ->  bf16 hi / lo planes [Cpad][Dpad]
 //   GEMM 1    Z^T[c][n] = (hi + lo)[c][:] . X[n][:]    (K = 2*Dpad, fp32 in TMEM; a chain
 //             is a TMEM lane, so one thread owns one chain's row of the tile)
-//             epilogue: r = y - sigmoid(z) -> R^T[c][n] bf16 ; sum_n softplus(z) -> SP[c]
+//             epilogue: sigmoid(z) -> R^T[c][n] bf16 ; sum_n softplus(z) -> SP[c]
 //   GEMM 2    G[c][d] = R^T[c][:] . X^T[d][:]          (K = Npad, fp32 in TMEM)
-//   finalize  grad = G - theta ; logp = (X^T y).theta - SP - 1/2 |theta|^2   (fp64)
+//   finalize  grad = X^T y - G - theta ; logp = (X^T y).theta - SP - 1/2 |theta|^2 (fp64)
 //
 // Both GEMMs are one kernel: D[m][n] = sum_k A[m][k] B[n][k], A and B bf16 K-major,
 // 128 x BN x 64 tiles, TMA (SWIZZLE_128B) -> shared -> tcgen05.mma.kind::f16 issued by
@@ -117,16 +117,18 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }
 
 constexpr int BM = 128, BK = 64;
-constexpr int kGemmThreads = 256;
+// warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; then the epilogue warps
+// (4 lane quarters x column halves when there are 8)
+template <int EPI> constexpr int epi_warps() { return EPI == 1 ? 8 : 4; }
+template <int EPI> constexpr int gemm_threads() { return 128 + 32 * epi_warps<EPI>(); }
 
 struct GemmParams {
   int num_m_tiles, num_n_tiles;
   int num_k_blocks;        // total K blocks (all planes of A)
   int k_blocks_per_plane;  // K blocks of one plane of A (B wraps around per plane)
-  // epilogue 1 (logistic residual): rows = chains, columns = data rows
-  const float* y;          // [Npad]
+  // epilogue 1 (logistic): rows = chains, columns = data rows
   int n_valid;             // data rows < n_valid are real
-  __nv_bfloat16* RT;       // [Cpad][ldrt]
+  __nv_bfloat16* RT;       // [Cpad][ldrt]  sigmoid(z), 0 for padding rows
   long long ldrt;
   double* SP;              // [Cpad] sum_n softplus
   // epilogue 2 (plain store)
@@ -148,19 +150,30 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// log1p(e) on [0, 1], degree-8 minimax-like fit (max abs error 1.9e-7 in fp32):
-// keeps the per-element epilogue at two MUFU ops (ex2, rcp)
-__device__ __forceinline__ float log1p_unit(float e) {
-  float p = -0.006151470821350813f;
-  p = fmaf(p, e, 0.03484971076250076f);
-  p = fmaf(p, e, -0.0932520404458046f);
-  p = fmaf(p, e, 0.16582275927066803f);
-  p = fmaf(p, e, -0.23982615768909454f);
-  p = fmaf(p, e, 0.33154863119125366f);
-  p = fmaf(p, e, -0.49983856081962585f);
-  p = fmaf(p, e, 0.9999942779541016f);
-  p = fmaf(p, e, 3.3869653748297424e-08f);
-  return p;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// sigmoid(z) and softplus(z) from e = exp(-|z|), inv = 1/(1+e):
+//   sigmoid = z >= 0 ? inv : e*inv ;  softplus = max(z,0) + log1p(e) = max(z,0) - ln(inv)
+// three MUFU ops (ex2, rcp, lg2) and a handful of FP32 ops per element
+__device__ __forceinline__ void sigmoid_softplus(float z, float& sig, float& sp) {
+  const float e = ex2_approx(-1.4426950408889634f * fabsf(z));
+  const float inv = rcp_approx(1.0f + e);
+  sig = z >= 0.0f ? inv : e * inv;
+  sp = fmaf(-0.6931471805599453f, lg2_approx(inv), fmaxf(z, 0.0f));
 }
 
 // D[m][n] = sum_k A[m][k] B[n][k]; A may come in two planes that are summed (hi + lo).
@@ -168,7 +181,7 @@ __device__ __forceinline__ float log1p_unit(float e) {
 // double-buffered TMEM accumulator so the epilogue of tile i overlaps the MMAs of i+1.
 // EPI = 1: logistic residual epilogue; EPI = 2: store fp32 tile
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                    const __grid_constant__ CUtensorMap mapA1,
                    const __grid_constant__ CUtensorMap mapB, const GemmParams gp) {
@@ -193,7 +206,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full + b, 1);
-      mbar_init(tmem_empty + b, 4);  // one arrival per epilogue warp
+      mbar_init(tmem_empty + b, epi_warps<EPI>());  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -262,7 +275,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
     }
   } else if (warp >= 4) {
     // ---------------- epilogue: TMEM -> registers -> global
-    const int wq = warp - 4;  // TMEM lane quarter
+    const int wq = (warp - 4) & 3;   // TMEM lane quarter this warp may read
+    const int part = (warp - 4) >> 2;  // which slice of the columns it handles
+    constexpr int kChunks = BN / 32 / (epi_warps<EPI>() / 4);
     int as = 0;
     uint32_t aph = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -273,34 +288,39 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
       const int row = m0 + wq * 32 + lane;  // A row of this thread (its TMEM lane)
       const uint32_t tmem_acc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * BN;
       if constexpr (EPI == 1) {
-        // row = chain, columns = data rows n0 + ...
+        // row = chain, columns = data rows n0 + ...; R^T holds sigmoid(z) (the y term of
+        // the gradient is the constant X^T y, added by the finalize kernel)
         float sp_acc = 0.0f;
         __nv_bfloat16* rt_row = gp.RT + static_cast<long long>(row) * gp.ldrt + n0;
 #pragma unroll 1
-        for (int j = 0; j < BN / 32; ++j) {
+        for (int jj = 0; jj < kChunks; ++jj) {
+          const int j = part * kChunks + jj;
           uint32_t v[32];
           tmem_ld32(tmem_acc + j * 32, v);
-          const int nbase = n0 + j * 32;
-          const float yl = gp.y[nbase + lane];
-          const int nvalid = gp.n_valid - nbase;  // columns i < nvalid are real data
+          const int nvalid = gp.n_valid - (n0 + j * 32);  // columns i < nvalid are data
           uint32_t packed[16];
+          if (nvalid >= 32) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float r2[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float z = __uint_as_float(v[i + u]);
-              const float yi = __shfl_sync(0xffffffffu, yl, i + u);
-              const float e = exp2f(-1.4426950408889634f * fabsf(z));
-              const float inv = __fdividef(1.0f, 1.0f + e);
-              const float sig = z >= 0.0f ? inv : e * inv;
-              const float sp = fmaxf(z, 0.0f) + log1p_unit(e);
-              const bool ok = (i + u) < nvalid;
-              r2[u] = ok ? yi - sig : 0.0f;
-              sp_acc += ok ? sp : 0.0f;
+            for (int i = 0; i < 32; i += 2) {
+              float s0, s1, p0, p1;
+              sigmoid_softplus(__uint_as_float(v[i]), s0, p0);
+              sigmoid_softplus(__uint_as_float(v[i + 1]), s1, p1);
+              sp_acc += p0 + p1;
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(s0, s1);
+              packed[i / 2] = *reinterpret_cast<uint32_t*>(&b2);
             }
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(r2[0], r2[1]);
-            packed[i / 2] = *reinterpret_cast<uint32_t*>(&b2);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float s0, s1, p0, p1;
+              sigmoid_softplus(__uint_as_float(v[i]), s0, p0);
+              sigmoid_softplus(__uint_as_float(v[i + 1]), s1, p1);
+              if (i >= nvalid) { s0 = 0.0f; p0 = 0.0f; }
+              if (i + 1 >= nvalid) { s1 = 0.0f; p1 = 0.0f; }
+              sp_acc += p0 + p1;
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(s0, s1);
+              packed[i / 2] = *reinterpret_cast<uint32_t*>(&b2);
+            }
           }
           uint4* dst = reinterpret_cast<uint4*>(rt_row + j * 32);
 #pragma unroll
@@ -312,7 +332,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
         atomicAdd(gp.SP + row, static_cast<double>(sp_acc));
       } else {
 #pragma unroll 1
-        for (int j = 0; j < BN / 32; ++j) {
+        for (int jj = 0; jj < kChunks; ++jj) {
+          const int j = part * kChunks + jj;
           uint32_t v[32];
           tmem_ld32(tmem_acc + j * 32, v);
           float4* dst = reinterpret_cast<float4*>(
@@ -354,7 +375,7 @@ __global__ void pack_theta_kernel(const double* TH, int ld, int C, int D, int Dp
   lo[i] = __double2bfloat16(rem);
 }
 
-// grad = G32 - theta ; logp = b.theta - SP - 1/2 |theta|^2   (one warp per chain)
+// grad = b - G32 - theta (G32 = sum_n sigmoid x) ; logp = b.theta - SP - 1/2 |theta|^2
 __global__ void logistic_finalize_kernel(const double* TH, int ld, int C, int D,
                                          const float* G32, long long ldg, const double* b,
                                          const double* SP, double* G, double* LP) {
@@ -367,7 +388,7 @@ __global__ void logistic_finalize_kernel(const double* TH, int ld, int C, int D,
     if (d < D) {
       const double t = th[d];
       G[static_cast<long long>(c) * ld + d] =
-          static_cast<double>(G32[static_cast<long long>(c) * ldg + d]) - t;
+          (b[d] - static_cast<double>(G32[static_cast<long long>(c) * ldg + d])) - t;
       bt += b[d] * t;
       ss += t * t;
     } else {
@@ -510,9 +531,9 @@ void LogisticGrad::evaluate(const double* TH, double* G, double* LP, cudaStream_
   g1.num_n_tiles = static_cast<int>(m.Npad / 256);
   g1.k_blocks_per_plane = static_cast<int>(m.Dpad / BK);
   g1.num_k_blocks = 2 * g1.k_blocks_per_plane;
-  g1.y = m.y.ptr; g1.n_valid = m.N; g1.RT = m.RT.ptr; g1.ldrt = m.Npad; g1.SP = m.SP.ptr;
+  g1.n_valid = m.N; g1.RT = m.RT.ptr; g1.ldrt = m.Npad; g1.SP = m.SP.ptr;
   const int grid1 = std::min(m.sms, g1.num_m_tiles * g1.num_n_tiles);
-  gemm_kmajor_kernel<256, 1><<<grid1, kGemmThreads, GemmSmem<256>::kTotal, stream>>>(
+  gemm_kmajor_kernel<256, 1><<<grid1, gemm_threads<1>(), GemmSmem<256>::kTotal, stream>>>(
       m.mapHi, m.mapLo, m.mapX, g1);
   WB200_CUDA(cudaGetLastError());
   GemmParams g2{};
@@ -523,13 +544,13 @@ void LogisticGrad::evaluate(const double* TH, double* G, double* LP, cudaStream_
   g2.out = m.G32.ptr; g2.ldo = m.Dpad;
   const int grid2 = std::min(m.sms, g2.num_m_tiles * g2.num_n_tiles);
   if (m.bn2 == 256) {
-    gemm_kmajor_kernel<256, 2><<<grid2, kGemmThreads, GemmSmem<256>::kTotal, stream>>>(
+    gemm_kmajor_kernel<256, 2><<<grid2, gemm_threads<2>(), GemmSmem<256>::kTotal, stream>>>(
         m.mapRT, m.mapRT, m.mapXT, g2);
   } else if (m.bn2 == 128) {
-    gemm_kmajor_kernel<128, 2><<<grid2, kGemmThreads, GemmSmem<128>::kTotal, stream>>>(
+    gemm_kmajor_kernel<128, 2><<<grid2, gemm_threads<2>(), GemmSmem<128>::kTotal, stream>>>(
         m.mapRT, m.mapRT, m.mapXT, g2);
   } else {
-    gemm_kmajor_kernel<64, 2><<<grid2, kGemmThreads, GemmSmem<64>::kTotal, stream>>>(
+    gemm_kmajor_kernel<64, 2><<<grid2, gemm_threads<2>(), GemmSmem<64>::kTotal, stream>>>(
         m.mapRT, m.mapRT, m.mapXT, g2);
   }
   WB200_CUDA(cudaGetLastError());
