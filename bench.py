@@ -143,17 +143,35 @@ def run_c4(args):
     import walnuts_b200 as wb
     from oracle.binding import Target, default_config
 
+    import torch.distributed as dist
+    from walnuts_b200.distributed import rhat_from_dimension_moments, shard
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: walnuts_b200 has no CPU path")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     cfgw = dict(C4)
-    C = args.chains if args.chains != CHAINS_PER_GPU else cfgw["chains"]
+    strong = args.workload == "c5"
+    if strong:
+        # c5: 65,536 chains in total, sharded over the GPUs (strong scaling)
+        total = args.chains if args.chains != CHAINS_PER_GPU else 65536
+        chain_offset, C = shard(total, world, rank)
+    else:
+        C = args.chains if args.chains != CHAINS_PER_GPU else cfgw["chains"]
+        chain_offset, total = rank * C, C * world
     N, Dm = cfgw["N"], cfgw["D"]
     tps = args.iters_per_step if args.iters_per_step != 10 else cfgw["ticks_per_step"]
     K, W = args.steps, args.warmup
     X, y = logistic_data(N, Dm)
     tune = dict(max_trajectory_doublings=cfgw["max_doublings"],
                 max_step_halvings=cfgw["max_halvings"])
-    sess = wb.Session(wb.models.logistic(X, y), C, seed=SEED, **tune)
+    sess = wb.Session(wb.models.logistic(X, y), C, seed=SEED, chain_offset=chain_offset,
+                      device=local_rank, **tune)
     sess.init(init_radius=0.1)
     cap = max(8, (W + K) * tps // 8)  # room for the draws of the free-running phase
     sess.reserve(cap)
@@ -170,54 +188,85 @@ def run_c4(args):
     sess.sync()
     c2 = sess.counters()
     torch.cuda.synchronize()
-    with ClockSampler(0) as clocks:
+    if distributed:
+        dist.barrier()
+    with ClockSampler(local_rank) as clocks:
         t0 = time.perf_counter()
         sess.timer_start()
         for _ in range(K):
             sess.sample_ticks(tps)
         total_ms = sess.timer_stop_ms()
         wall_ms = 1e3 * (time.perf_counter() - t0)
+    if distributed:
+        dist.barrier()
     c3 = sess.counters()
     evals = c3["grad_evals"] - c2["grad_evals"]
     launches = c3["kernel_launches"] - c2["kernel_launches"]
-    value = evals / (total_ms * 1e-3)
     rows = sess.chain_rows()
     summ = sess.summary_ragged(0)
-    active_lane_fraction = evals / float(K * tps * C)
+    # the only collective: per-dimension chain-moment sums -> R-hat over ALL ranks' chains
+    mom = torch.tensor(sess.rhat_moments(0), dtype=torch.float64, device="cuda")
+    tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    ee = torch.tensor([float(evals), float(np.min(summ["ess"]))], dtype=torch.float64,
+                      device="cuda")
+    if distributed:
+        dist.all_reduce(mom, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ee, op=dist.ReduceOp.SUM)   # independent chains: evals and ESS add
+    global_rhat = rhat_from_dimension_moments(mom.cpu().numpy())
+    total_ms = float(tt.item())
+    evals_local = evals
+    evals = float(ee[0].item())
+    min_ess_total = float(ee[1].item())
+    value = evals / (total_ms * 1e-3)
+    active_lane_fraction = evals_local / float(K * tps * C)
     sess.close()
+    if rank != 0:
+        if distributed:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     # stand-alone timing of the batched gradient (the dominant kernels)
     from walnuts_b200.sampler import logistic_logp_grad
     theta = np.random.default_rng(1).normal(size=(C, Dm)) * 0.05
     _, _, grad_ms = logistic_logp_grad(X, y, theta, repeats=5)
     sustained, burst, src = bf16_peaks()
     flops_alg = 4.0 * N * Dm
-    achieved = value * flops_alg / 1e12
+    achieved = value / world * flops_alg / 1e12   # per GPU
     # CPU baseline: the oracle port of the same sampler on a bounded sample
     checker, kind = load_cpu_checker()
     cores = os.cpu_count() or 1
     target = Target("logistic", Dm, X=X, y=y)
-    ccfg = default_config(min_warmup_iter=4, max_warmup_iter=4, min_sampling_iter=4,
-                          max_sampling_iter=4, max_trajectory_doublings=cfgw["max_doublings"],
+    ccfg = default_config(min_warmup_iter=2, max_warmup_iter=2, min_sampling_iter=2,
+                          max_sampling_iter=2, max_trajectory_doublings=cfgw["max_doublings"],
                           max_step_halvings=cfgw["max_halvings"])
     pos = checker.init_positions(cores, Dm, SEED, 0.5)
     mass = np.ones((cores, Dm))
     steps = np.full(cores, 0.02)
     t0 = time.perf_counter()
-    r = checker.walnuts(target, ccfg, SEED, pos, mass, steps)
-    cpu_s = time.perf_counter() - t0
+    if args.no_cpu_baseline:
+        r, cpu_s = {"grad_evals": float("nan")}, 1.0
+    else:
+        r = checker.walnuts(target, ccfg, SEED, pos, mass, steps)
+        cpu_s = time.perf_counter() - t0
     line = {
-        "metric": "grad_evals_per_sec", "value": value, "unit": "grad_evals/s", "n_gpus": 1,
+        "metric": "grad_evals_per_sec", "value": value, "unit": "grad_evals/s",
+        "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tensor cores (hi+lo split), "
+        "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "bf16 tensor cores (hi+lo split), "
         "fp32 accumulate, fp64 state", "data": "synthetic",
         "config": {"workload": "c4: Bayesian logistic regression N=100k, D=512, 8192 chains, "
                                "lock-step tick engine + tcgen05 batched gradient",
-                   "N": N, "dims": Dm, "chains_per_gpu": C, "ticks_per_step": tps,
+                   "N": N, "dims": Dm, "chains_per_gpu": C, "chains_total": total,
+                   "ticks_per_step": tps,
+                   "parallelism": f"chains sharded over {world} GPU(s); X replicated; one "
+                                  "NCCL all-reduce of R-hat moments after the timed region",
                    "adaptive_warmup_iters": cfgw["warmup_iters"],
                    "max_trajectory_doublings": cfgw["max_doublings"],
                    "l2": "operands (X 102 MB, R^T 1.6 GB) exceed the 126 MB L2"},
-        "min_ess_per_sec": float(np.min(summ["ess"])) / (total_ms * 1e-3),
-        "max_r_hat": float(np.max(summ["r_hat"])),
+        "min_ess_per_sec": min_ess_total / (total_ms * 1e-3),
+        "max_r_hat": float(np.max(global_rhat)),
         "active_lane_fraction": active_lane_fraction,
         "draws_per_chain": {"min": int(rows.min()), "mean": float(rows.mean()),
                             "max": int(rows.max())},
@@ -233,11 +282,14 @@ def run_c4(args):
                      "kernel": "gemm_kmajor_kernel<128,1> + gemm_kmajor_kernel<256,2>"},
         "cpu_baseline": {"value": r["grad_evals"] / cpu_s, "unit": "grad_evals/s",
                          "cores": cores, "kind": kind,
-                         "sample": f"{cores} chains x (4 warm-up + 4 sampling) iterations, "
+                         "sample": f"{cores} chains x (2 warm-up + 2 sampling) iterations, "
                                    "same data", "seconds": cpu_s},
         "clocks": clocks.summary(),
     }
     print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------
@@ -492,13 +544,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU)
     ap.add_argument("--iters-per-step", type=int, default=10)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true",
+                    help="skip the CPU leg (scaling sweeps of the logistic workloads)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference_arm(args)
-    elif args.workload == "c4":
+    elif args.workload in ("c4", "c5"):
         run_c4(args)
     else:
         run_ours(args)

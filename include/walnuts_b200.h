@@ -175,6 +175,11 @@ int wb200_session_sample_ticks(wb200_session* s, int n_ticks, int store,
 int wb200_session_chain_rows(wb200_session* s, long long* rows, WalnutpyError** err);
 int wb200_session_summary(wb200_session* s, long long first, double* rhat, double* ess,
                           double* mcse, double* mean, double* var, WalnutpyError** err);
+/* moments [3*D + 1] = {sum_c mean_c[D], sum_c mean_c^2[D], sum_c var_c[D], chains}: the
+ * payload a multi-GPU caller all-reduces (NCCL, SUM) to get the R-hat over all ranks'
+ * chains (summary.hpp:594-619) */
+int wb200_session_rhat_moments(wb200_session* s, long long first, double* moments,
+                               WalnutpyError** err);
 /* block until the session's stream is idle */
 int wb200_session_sync(wb200_session* s, WalnutpyError** err);
 

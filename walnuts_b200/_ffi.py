@@ -239,6 +239,8 @@ session_sample_ticks = _sess("wb200_session_sample_ticks",
                              [session_p, ctypes.c_int, ctypes.c_int])
 session_chain_rows = _sess("wb200_session_chain_rows", [
     session_p, ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")])
+session_rhat_moments = _sess("wb200_session_rhat_moments", [
+    session_p, ctypes.c_longlong, double_array])
 session_summary = _sess("wb200_session_summary", [
     session_p, ctypes.c_longlong, nullable_double_array, nullable_double_array,
     nullable_double_array, nullable_double_array, nullable_double_array])
@@ -314,7 +316,7 @@ EXPORTED_SYMBOLS = [
     "wb200_session_create", "wb200_session_destroy", "wb200_session_init",
     "wb200_session_reserve_draws", "wb200_session_warmup", "wb200_session_freeze",
     "wb200_session_sample", "wb200_session_sync", "wb200_session_sample_ticks",
-    "wb200_session_chain_rows", "wb200_session_summary", "wb200_session_warmup_sums",
+    "wb200_session_chain_rows", "wb200_session_summary", "wb200_session_rhat_moments", "wb200_session_warmup_sums",
     "wb200_session_warmup_deviation", "wb200_session_lp_moments",
     "wb200_session_get_draws", "wb200_session_get_trace", "wb200_session_get_state",
     "wb200_session_device_draws", "wb200_session_counters",

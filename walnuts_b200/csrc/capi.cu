@@ -341,6 +341,29 @@ int wb200_session_summary(wb200_session* s, long long first, double* rhat, doubl
   });
 }
 
+int wb200_session_rhat_moments(wb200_session* s, long long first, double* moments,
+                               WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    std::vector<long long> rows(s->C), start, len;
+    WalnutpyError* e = nullptr;
+    if (wb200_session_chain_rows(s, rows.data(), &e) != 0) {
+      std::string msg = e ? e->msg : "chain_rows failed";
+      delete e;
+      throw std::runtime_error(msg);
+    }
+    for (int c = 0; c < s->C; ++c) {
+      const long long l = rows[c] - first;
+      if (l < 3) continue;
+      start.push_back(static_cast<long long>(c) * s->draw_cap + first);
+      len.push_back(l);
+    }
+    if (start.empty()) throw std::invalid_argument("no chain has 3 draws in the range");
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+    device_rhat_moments(s->draws.ptr, s->ld, s->D, start, len, moments, s->stream);
+  });
+}
+
 int wb200_session_sync(wb200_session* s, WalnutpyError** err) {
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));

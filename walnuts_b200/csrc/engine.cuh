@@ -144,6 +144,10 @@ void launch_orbit(int kind, int D, int ld, int C, const double* tparam,
                   double* theta, double* rho, const double* inv_mass, double* grad,
                   double* logp, double* joint, double step, int num_steps,
                   cudaStream_t stream);
+void device_rhat_moments(const double* draws, int ld, int D,
+                         const std::vector<long long>& start,
+                         const std::vector<long long>& len, double* moments_host,
+                         cudaStream_t stream);
 // summaries over ragged chains: chain c = rows start[c] .. start[c]+len[c] of a
 // device matrix with row stride ld; outputs are HOST arrays of D (nullable)
 void device_summary(const double* draws, int ld, int D,

@@ -156,6 +156,48 @@ __global__ void geyer_kernel(SummaryView v, const double* macov, int nlag,
   mcse[d] = sqrt(pvar[d]) / sqrt(e);
 }
 
+// {sum_k mu_k, sum_k mu_k^2, sum_k s2_k}[D] -- the all-reduce payload of a cross-GPU R-hat
+__global__ void rhat_sums_kernel(SummaryView v, const double* mu, const double* s2,
+                                 double* out) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= v.D) return;
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int k = 0; k < v.K; ++k) {
+    const double m = mu[static_cast<long long>(k) * v.D + d];
+    a += m;
+    b += m * m;
+    c += s2[static_cast<long long>(k) * v.D + d];
+  }
+  out[d] = a;
+  out[v.D + d] = b;
+  out[2 * v.D + d] = c;
+}
+
+void device_rhat_moments(const double* draws, int ld, int D,
+                         const std::vector<long long>& start,
+                         const std::vector<long long>& len, double* moments_host,
+                         cudaStream_t stream) {
+  const int K = static_cast<int>(len.size());
+  if (K == 0) throw std::invalid_argument("chains cannot be empty.");
+  long long n_total = 0, min_len = len[0];
+  for (long long l : len) { n_total += l; min_len = std::min(min_len, l); }
+  DeviceBuffer<long long> d_start, d_len;
+  d_start.alloc(K); d_len.alloc(K);
+  WB200_CUDA(cudaMemcpyAsync(d_start.ptr, start.data(), K * 8, cudaMemcpyHostToDevice, stream));
+  WB200_CUDA(cudaMemcpyAsync(d_len.ptr, len.data(), K * 8, cudaMemcpyHostToDevice, stream));
+  SummaryView v{draws, ld, D, K, d_start.ptr, d_len.ptr, n_total, min_len};
+  DeviceBuffer<double> mu, s2, out;
+  mu.alloc(static_cast<size_t>(K) * D); s2.alloc(static_cast<size_t>(K) * D);
+  out.alloc(3 * static_cast<size_t>(D));
+  const int tb = 128;
+  chain_moments_kernel<<<dim3((D + tb - 1) / tb, K), tb, 0, stream>>>(v, mu.ptr, s2.ptr);
+  rhat_sums_kernel<<<(D + tb - 1) / tb, tb, 0, stream>>>(v, mu.ptr, s2.ptr, out.ptr);
+  WB200_CUDA(cudaGetLastError());
+  WB200_CUDA(cudaMemcpyAsync(moments_host, out.ptr, 3 * D * 8, cudaMemcpyDeviceToHost, stream));
+  WB200_CUDA(cudaStreamSynchronize(stream));
+  moments_host[3 * D] = static_cast<double>(K);
+}
+
 constexpr int kLagBlock = 32;
 
 void device_summary(const double* draws, int ld, int D,

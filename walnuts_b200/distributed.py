@@ -143,3 +143,13 @@ def combine_dimension_moments(mean_c: np.ndarray, var_c: np.ndarray,
     M = p[3 * D]
     between = (p[D:2 * D] - p[:D] ** 2 / M) / (M - 1.0)
     return np.sqrt(1.0 + between / (p[2 * D:3 * D] / M))
+
+
+def rhat_from_dimension_moments(m) -> np.ndarray:
+    """Per-dimension R-hat from the (all-reduced) payload of
+    ``Session.rhat_moments``: {sum mu, sum mu^2, sum var}[D] + chain count."""
+    m = np.asarray(m, dtype=np.float64)
+    D = (m.size - 1) // 3
+    M = m[3 * D]
+    between = (m[D:2 * D] - m[:D] ** 2 / M) / (M - 1.0)
+    return np.sqrt(1.0 + between / (m[2 * D:3 * D] / M))

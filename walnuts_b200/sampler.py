@@ -226,6 +226,13 @@ class Session:
         _ffi.session_chain_rows(self._h, rows)
         return rows
 
+    def rhat_moments(self, first: int = 0) -> np.ndarray:
+        """[3*D + 1] per-dimension chain-moment sums + chain count: all-reduce (SUM) over
+        ranks, then walnuts_b200.distributed.rhat_from_dimension_moments."""
+        out = np.zeros(3 * self.num_params + 1)
+        _ffi.session_rhat_moments(self._h, int(first), out)
+        return out
+
     def summary_ragged(self, first: int = 0):
         """R-hat / ESS / MCSE / mean / variance over rows [first, rows_c) of every chain."""
         D = self.num_params
