@@ -159,10 +159,10 @@ def run_c4(args):
     strong = args.workload == "c5"
     if strong:
         # c5: 65,536 chains in total, sharded over the GPUs (strong scaling)
-        total = args.chains if args.chains != CHAINS_PER_GPU else 65536
+        total = args.chains if args.chains else 65536
         chain_offset, C = shard(total, world, rank)
     else:
-        C = args.chains if args.chains != CHAINS_PER_GPU else cfgw["chains"]
+        C = args.chains if args.chains else cfgw["chains"]
         chain_offset, total = rank * C, C * world
     N, Dm = cfgw["N"], cfgw["D"]
     tps = args.iters_per_step if args.iters_per_step != 10 else cfgw["ticks_per_step"]
@@ -377,7 +377,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    C = args.chains
+    C = args.chains if args.chains else CHAINS_PER_GPU
     ips = args.iters_per_step
     K, W = args.steps, args.warmup
     model = wb.models.diag_gaussian(variances())
@@ -542,7 +542,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU)
+    ap.add_argument("--chains", type=int, default=None,
+                    help="chains per GPU (c2, c4) or in total (c5); default per workload")
     ap.add_argument("--iters-per-step", type=int, default=10)
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true",
