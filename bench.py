@@ -46,9 +46,24 @@ MAX_HALVINGS = 5
 SEED = 20250
 ALG_BYTES_PER_EVAL = 7 * D * 8  # read theta, rho, grad, M^-1; write theta, rho, grad
 
+# element-wise workloads of run_ours / the reference arm.  c2 is the default line; c3
+# (BASELINE.json configs[2]) exercises the within-orbit halving ladder.
+ELEMENTWISE = {
+    "c2": dict(label="c2: 1000-dim ill-conditioned diagonal Gaussian (cond 1e4), "
+                     "4096 chains per GPU, fp64",
+               kind="diag_gaussian", D=D, chains=CHAINS_PER_GPU, init_radius=2.0,
+               warmup_iters=WARMUP_ITERS, max_doublings=MAX_DOUBLINGS,
+               max_halvings=MAX_HALVINGS, cpu_warm=300, cpu_samp=1000,
+               kernel="walnuts_chain_kernel<DiagGaussianTarget<128,4>>"),
+    "c3": dict(label="c3: Neal's funnel D=100, 16384 chains per GPU, fp64",
+               kind="funnel", D=100, chains=16384, init_radius=1.0, warmup_iters=300,
+               max_doublings=10, max_halvings=8, cpu_warm=300, cpu_samp=300,
+               kernel="walnuts_chain_kernel<FunnelTarget<32,2>>"),
+}
+
 # --workload c4: Bayesian logistic regression (BASELINE.json configs[3]); not the
 # default line (the driver's N=1 run is c2), used for the tensor-core roofline
-C4 = dict(N=100_000, D=512, chains=8192, warmup_iters=100, ticks_per_step=100,
+C4 = dict(N=100_000, D=512, chains=8192, warmup_ticks=3000, ticks_per_step=100,
           max_doublings=8, max_halvings=5)
 
 
@@ -177,7 +192,9 @@ def run_c4(args):
     sess.reserve(cap)
     c0 = sess.counters()
     t0 = time.perf_counter()
-    sess.warmup(cfgw["warmup_iters"])
+    # free-running adaptive warm-up: every chain adapts over the transitions that fit
+    # (about 100 on average); an iteration quota would idle the batch on its slowest chain
+    sess.warmup_ticks(cfgw["warmup_ticks"])
     sess.freeze().sync()
     warm_s = time.perf_counter() - t0
     c1 = sess.counters()
@@ -262,7 +279,7 @@ def run_c4(args):
                    "ticks_per_step": tps,
                    "parallelism": f"chains sharded over {world} GPU(s); X replicated; one "
                                   "NCCL all-reduce of R-hat moments after the timed region",
-                   "adaptive_warmup_iters": cfgw["warmup_iters"],
+                   "adaptive_warmup_ticks": cfgw["warmup_ticks"],
                    "max_trajectory_doublings": cfgw["max_doublings"],
                    "l2": "operands (X 102 MB, R^T 1.6 GB) exceed the 126 MB L2"},
         "min_ess_per_sec": min_ess_total / (total_ms * 1e-3),
@@ -271,7 +288,7 @@ def run_c4(args):
         "draws_per_chain": {"min": int(rows.min()), "mean": float(rows.mean()),
                             "max": int(rows.max())},
         "wall_ms": wall_ms, "gpu_launches": int(launches),
-        "warmup_phase": {"iters": cfgw["warmup_iters"], "seconds": warm_s,
+        "warmup_phase": {"ticks": cfgw["warmup_ticks"], "seconds": warm_s,
                          "grad_evals_per_sec": (c1["grad_evals"] - c0["grad_evals"]) / warm_s},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained,
                      "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": None,
@@ -293,16 +310,20 @@ def run_c4(args):
 
 
 # ---------------------------------------------------------------------------
-def reference_step(checker, kind, chains, warm, samp, seed):
+def reference_step(checker, kind, chains, warm, samp, seed, wl=None):
     """One bounded sample of the workload on the host cores: `chains` chains of
     (warm + samp) fixed iterations through the reference's own threaded driver
     (api.hpp:33-69).  Returns (gradient evaluations, seconds, draws)."""
     from oracle.binding import Target, default_config
-    target = Target("diag_gaussian", D, prec=1.0 / variances())
+    wl = wl or ELEMENTWISE["c2"]
+    Dw = wl["D"]
+    target = (Target("diag_gaussian", Dw, prec=1.0 / variances())
+              if wl["kind"] == "diag_gaussian" else Target(wl["kind"], Dw))
     cfg = default_config(min_warmup_iter=warm, max_warmup_iter=warm, min_sampling_iter=samp,
-                         max_sampling_iter=samp, max_trajectory_doublings=MAX_DOUBLINGS,
-                         max_step_halvings=MAX_HALVINGS)
-    pos = checker.init_positions(chains, D, seed, 2.0)
+                         max_sampling_iter=samp,
+                         max_trajectory_doublings=wl["max_doublings"],
+                         max_step_halvings=wl["max_halvings"])
+    pos = checker.init_positions(chains, Dw, seed, wl["init_radius"])
     mass, steps = checker.init_mass_step(target, pos, seed, 1.0)
     t0 = time.perf_counter()
     r = checker.walnuts(target, cfg, seed, pos, mass, steps)
@@ -324,27 +345,28 @@ def run_reference_arm(args):
         return
     checker, kind = load_cpu_checker()
     cores = os.cpu_count() or 1
+    wl = ELEMENTWISE[args.workload if args.workload in ELEMENTWISE else "c2"]
     warm, samp = 100, 50 * args.iters_per_step
     for i in range(args.warmup):
-        reference_step(checker, kind, cores, warm, samp, SEED + i)
+        reference_step(checker, kind, cores, warm, samp, SEED + i, wl)
     evals, secs = 0, 0.0
     for i in range(args.steps):
-        e, dt, _ = reference_step(checker, kind, cores, warm, samp, SEED + 100 + i)
+        e, dt, _ = reference_step(checker, kind, cores, warm, samp, SEED + 100 + i, wl)
         evals += e
         secs += dt
     value = evals / secs
     sample = (f"{cores} chains (one per core) x ({warm} warm-up + {samp} sampling) fixed "
-              f"iterations per step, D={D} ill-conditioned Gaussian")
+              f"iterations per step, {wl['label']}")
     line = {
         "impl": "reference", "metric": "grad_evals_per_sec", "value": value,
         "unit": "grad_evals/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "c2: 1000-dim ill-conditioned diagonal Gaussian (cond 1e4), "
-                               "CPU threads, one chain per core", "dims": D,
-                   "chains": cores, "max_trajectory_doublings": MAX_DOUBLINGS,
-                   "max_step_halvings": MAX_HALVINGS},
+        "config": {"workload": wl["label"] + " -- reference: CPU threads, one chain per core",
+                   "dims": wl["D"], "chains": cores,
+                   "max_trajectory_doublings": wl["max_doublings"],
+                   "max_step_halvings": wl["max_halvings"]},
         "cpu_baseline": {"value": value, "unit": "grad_evals/s", "cores": cores,
                          "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "grad_evals/s", "h2d_bytes_per_step": 0,
@@ -377,13 +399,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    C = args.chains if args.chains else CHAINS_PER_GPU
+    wl = ELEMENTWISE[args.workload]
+    D, WARMUP_ITERS = wl["D"], wl["warmup_iters"]
+    MAX_DOUBLINGS, MAX_HALVINGS = wl["max_doublings"], wl["max_halvings"]
+    ALG_BYTES_PER_EVAL = 7 * D * 8
+    C = args.chains if args.chains else wl["chains"]
     ips = args.iters_per_step
     K, W = args.steps, args.warmup
-    model = wb.models.diag_gaussian(variances())
+    model = (wb.models.diag_gaussian(variances()) if wl["kind"] == "diag_gaussian"
+             else wb.models.funnel(D))
     tune = dict(max_trajectory_doublings=MAX_DOUBLINGS, max_step_halvings=MAX_HALVINGS)
     sess = wb.Session(model, C, seed=SEED, chain_offset=rank * C, device=local_rank, **tune)
-    sess.init(init_radius=2.0)
+    sess.init(init_radius=wl["init_radius"])
     sess.reserve((W + K) * ips)
     # ---- untimed set-up: adaptive warm-up (device time reported separately)
     sess.sync()
@@ -437,7 +464,11 @@ def run_ours(args):
         post_mean, post_var = mom[0].cpu().numpy(), mom[1].cpu().numpy()
     else:
         min_ess, post_mean, post_var = min_ess_local, summ["mean"], summ["variance"]
-    true_var = variances()
+    if wl["kind"] == "diag_gaussian":
+        true_var = variances()
+    else:  # funnel: x0 ~ N(0, 9); x_i has mean 0 (its variance e^{4.5} is never reached)
+        true_var = np.full(D, np.nan)
+        true_var[0] = 9.0
     clock_summary = clocks.summary()
     sess.close()
 
@@ -450,16 +481,18 @@ def run_ours(args):
     # ---- e2e: the C-ABI one-shot call with host buffers (rank 0's GPU)
     torch.cuda.synchronize()
     e2e_samp = K * ips
-    inits = np.ascontiguousarray(
-        np.random.default_rng(SEED).normal(size=(C, D)) * 2.0)
-    out = np.zeros((C, e2e_samp, D))
+    # host buffers are page-locked (wb200_host_alloc), as the bench contract asks
+    inits = _ffi.pinned_empty((C, D))
+    inits[...] = np.random.default_rng(SEED).normal(size=(C, D)) * wl["init_radius"]
+    out = _ffi.pinned_empty((C, e2e_samp, D))
     lengths = np.zeros(2 * C, np.int32)
     stepsize = np.zeros(C)
     desc = model.desc()
     import ctypes
     t0 = time.perf_counter()
     _ffi._ffi_sample_device(
-        ctypes.byref(desc), D, inits, C, SEED, 1, 2.0, None, WARMUP_ITERS, WARMUP_ITERS,
+        ctypes.byref(desc), D, inits, C, SEED, 1, wl["init_radius"], None, WARMUP_ITERS,
+        WARMUP_ITERS,
         e2e_samp, e2e_samp, MAX_DOUBLINGS, MAX_HALVINGS, 1, 0.5, 0.1, 1.0, 1.01, 4.0, 1e-5,
         15.0, 1.0, 0.8, 0.05, 0.8, 0.9, 1e-4, 0.5, False, out, out.size, lengths, stepsize,
         None, 0, _ffi.print_callback)
@@ -471,8 +504,9 @@ def run_ours(args):
     # ---- CPU baseline on a bounded sample of the same workload
     checker, kind = load_cpu_checker()
     cores = os.cpu_count() or 1
-    cpu_warm, cpu_samp = 300, 1000
-    cpu_evals, cpu_s, cpu_draws = reference_step(checker, kind, cores, cpu_warm, cpu_samp, SEED)
+    cpu_warm, cpu_samp = wl["cpu_warm"], wl["cpu_samp"]
+    cpu_evals, cpu_s, cpu_draws = reference_step(checker, kind, cores, cpu_warm, cpu_samp,
+                                                 SEED, wl)
     oracle_checker = checker if kind == "port" else __import__(
         "oracle.binding", fromlist=["load_oracle"]).load_oracle()
     cpu_min_ess = float(np.min(oracle_checker.ess([cpu_draws[c] for c in range(cores)])))
@@ -486,8 +520,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {
-            "workload": "c2: 1000-dim ill-conditioned diagonal Gaussian (cond 1e4), "
-                        "4096 chains per GPU, fp64",
+            "workload": wl["label"],
             "dims": D, "chains_per_gpu": C, "chains_total": C * world,
             "iters_per_step": ips, "adaptive_warmup_iters": WARMUP_ITERS,
             "max_trajectory_doublings": MAX_DOUBLINGS, "max_step_halvings": MAX_HALVINGS,
@@ -500,21 +533,23 @@ def run_ours(args):
         "grad_evals_per_transition": total_evals / (C * world * K * ips),
         "wall_ms": wall_ms,
         "posterior_check": {
-            "max_abs_mean_over_sd": float(np.max(np.abs(post_mean) / np.sqrt(true_var))),
-            "max_rel_var_error": float(np.max(np.abs(post_var / true_var - 1.0))),
+            "max_abs_mean_over_sd": float(np.nanmax(np.abs(post_mean) / np.sqrt(true_var))),
+            "max_rel_var_error": float(np.nanmax(np.abs(post_var / true_var - 1.0))),
         },
         "warmup_phase": {"iters": WARMUP_ITERS, "ms": warm_ms,
                          "grad_evals_per_sec": warm_evals / (warm_ms * 1e-3)},
         "e2e": {"value": e2e_value, "unit": "grad_evals/s",
                 "h2d_bytes_per_step": int(inits.nbytes / e2e_steps),
                 "d2h_bytes_per_step": int(out.nbytes / e2e_steps),
-                "seconds": e2e_s, "api": "walnutpie_sample_device (C-ABI, host buffers)",
+                "seconds": e2e_s, "api": "walnutpie_sample_device (C-ABI, pinned host buffers; "
+                       "session set-up, initialisation, adaptive warm-up, sampling and the "
+                       "overlapped read-back of every draw are all inside the timed call)",
                 "grad_evals": st["grad_evals"], "steps": e2e_steps},
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-            "kernel": "walnuts_chain_kernel<DiagGaussianTarget<256,2>>",
+            "kernel": wl["kernel"],
             "algorithmic_bytes_per_eval": ALG_BYTES_PER_EVAL,
             "ms_per_launch": ms_per_launch,
             "note": "the chain-resident kernel keeps theta/rho/grad/M^-1 in registers "
@@ -545,7 +580,7 @@ def main():
     ap.add_argument("--chains", type=int, default=None,
                     help="chains per GPU (c2, c4) or in total (c5); default per workload")
     ap.add_argument("--iters-per-step", type=int, default=10)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true",
                     help="skip the CPU leg (scaling sweeps of the logistic workloads)")
     args = ap.parse_args()

@@ -172,6 +172,11 @@ int wb200_session_sample(wb200_session* s, int n_iter, int store,
  * chain; wb200_session_summary summarises rows [first, rows_c) of every chain. */
 int wb200_session_sample_ticks(wb200_session* s, int n_ticks, int store,
                                WalnutpyError** err);
+/* The same for the adaptive phase (AdaptiveWalnuts::operator(), adaptive_walnuts.hpp:234):
+ * every chain adapts on its own transition count, like the reference's per-thread
+ * chains.  wb200_session_freeze abandons the transitions still in flight. */
+int wb200_session_warmup_ticks(wb200_session* s, int n_ticks, int store,
+                               WalnutpyError** err);
 int wb200_session_chain_rows(wb200_session* s, long long* rows, WalnutpyError** err);
 int wb200_session_summary(wb200_session* s, long long first, double* rhat, double* ess,
                           double* mcse, double* mean, double* var, WalnutpyError** err);
@@ -227,6 +232,17 @@ int wb200_session_timer_elapsed_ms(wb200_session* s, float* ms, WalnutpyError** 
 int wb200_last_run_stats(unsigned long long* grad_evals, unsigned long long* macro_steps,
                          unsigned long long* kernel_launches, int* warmup_iters,
                          int* sampling_iters);
+
+/* Page-locked host memory for the `out` / `inits` buffers of
+ * walnutpie_sample_device (the reference's callers allocate these with numpy,
+ * util.py:16-32): with a pinned `out` the draw read-back is a direct DMA that
+ * overlaps sampling.  Pageable buffers work too, only slower. */
+int wb200_host_alloc(size_t bytes, void** ptr, WalnutpyError** err);
+void wb200_host_free(void* ptr);
+/* Device memory of destroyed sessions stays cached in the device's memory pool for
+ * the next session; this returns it to the driver (e.g. before handing the GPU to
+ * another library in the same process). */
+int wb200_trim_memory(int device, WalnutpyError** err);
 
 /* Fixed-step leapfrog orbit (walnuts.hpp:329-332) for parity checks:
  * theta/rho/inv_mass HOST [C][D]; advances `num_steps` micro-steps. */

@@ -28,9 +28,13 @@ def build():
     return C.CDLL(str(SO))
 
 
-def run_chain(lib, kind, D, tparam, cfg, seed, chain, th0, m0, step0, nw, ns, engine="chain"):
+def run_chain(lib, kind, D, tparam, cfg, seed, chain, th0, m0, step0, nw, ns, engine="chain",
+              warm_ticks=-1, samp_ticks=-1):
     """cfg is an oracle.binding.OracleConfig; returns the device-code results.
-    engine: "chain" (chain_kernel.cuh) or "tick" (tick_kernel.cuh)."""
+    engine: "chain" (chain_kernel.cuh) or "tick" (tick_kernel.cuh).
+    engine "tick" with warm_ticks / samp_ticks >= 0: that phase runs free for exactly
+    that many ticks (nw + ns is then the draw capacity); result["rows"] = (rows after
+    warm-up, rows at the end)."""
     t = EmuTuning(cfg.max_trajectory_doublings, cfg.max_step_halvings, cfg.min_micro_steps,
                   cfg.max_hamiltonian_error, cfg.mass_init_count,
                   cfg.max_macro_steps_target, cfg.step_accept_rate_target,
@@ -49,13 +53,22 @@ def run_chain(lib, kind, D, tparam, cfg, seed, chain, th0, m0, step0, nw, ns, en
     tp = None if tparam is None else np.ascontiguousarray(tparam, np.float64)
     th0 = np.ascontiguousarray(th0, np.float64)
     m0 = np.ascontiguousarray(m0, np.float64)
-    fn = lib.emu_run_chain if engine == "chain" else lib.emu_run_chain_tick
-    rc = fn(KIND[kind], D, None if tp is None else dp(tp), C.byref(t),
-                           C.c_uint32(seed), C.c_uint32(chain), dp(th0), dp(m0),
-                           C.c_double(step0), nw, ns, dp(draws), dp(lp),
-                           depth.ctypes.data_as(C.POINTER(C.c_int)), dp(st), dp(im),
-                           dp(imo), C.byref(so), C.byref(mm), C.byref(ev))
+    rows = (C.c_longlong * 2)(nw, nw + ns)
+    if warm_ticks >= 0 or samp_ticks >= 0:
+        assert engine == "tick"
+        rc = lib.emu_run_chain_tick_free(
+            KIND[kind], D, None if tp is None else dp(tp), C.byref(t), C.c_uint32(seed),
+            C.c_uint32(chain), dp(th0), dp(m0), C.c_double(step0), nw, ns, warm_ticks,
+            samp_ticks, dp(draws), dp(lp), depth.ctypes.data_as(C.POINTER(C.c_int)), dp(st),
+            dp(im), dp(imo), C.byref(so), C.byref(mm), C.byref(ev), rows)
+    else:
+        fn = lib.emu_run_chain if engine == "chain" else lib.emu_run_chain_tick
+        rc = fn(KIND[kind], D, None if tp is None else dp(tp), C.byref(t),
+                C.c_uint32(seed), C.c_uint32(chain), dp(th0), dp(m0),
+                C.c_double(step0), nw, ns, dp(draws), dp(lp),
+                depth.ctypes.data_as(C.POINTER(C.c_int)), dp(st), dp(im),
+                dp(imo), C.byref(so), C.byref(mm), C.byref(ev))
     if rc != 0:
         raise RuntimeError(f"emu_run_chain rc={rc}")
-    return dict(draws=draws, lp=lp, depth=depth, step_trace=st, warmup_inv_mass=im[:nw],
+    return dict(rows=(rows[0], rows[1]), draws=draws, lp=lp, depth=depth, step_trace=st, warmup_inv_mass=im[:nw],
                 inv_mass=imo, step=so.value, min_micro=mm.value, grad_evals=ev.value)

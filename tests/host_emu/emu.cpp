@@ -126,7 +126,11 @@ static void run_tick(const EmuTuning& t, int D, const double* tparam, uint32_t s
                      uint32_t chain, const double* theta0, const double* mass0,
                      double step0, int n_warmup, int n_sampling, double* draws, double* lp,
                      int* depth, double* step_trace, double* im_trace, double* inv_mass_out,
-                     double* step_out, int* min_micro_out, unsigned long long* evals) {
+                     double* step_out, int* min_micro_out, unsigned long long* evals,
+                     int warm_ticks = -1, int samp_ticks = -1, long long* rows_out = nullptr) {
+  // warm_ticks / samp_ticks >= 0: that phase runs free (exactly that many ticks, as
+  // tick_run_ticks does) instead of an iteration quota; n_warmup + n_sampling is then
+  // only the draw capacity and rows_out = {rows after warm-up, rows at the end}.
   const int ld = (D + 1) & ~1;
   const int total = n_warmup + n_sampling;
   const int nvec = tick_vectors(t.max_depth);
@@ -194,7 +198,24 @@ static void run_tick(const EmuTuning& t, int D, const double* tparam, uint32_t s
       gradient_stage(TH.data(), G.data(), LP);
     }
   };
-  run_batch(n_warmup, 1, 0);
+  auto run_free = [&](int n_ticks, int adapt) {
+    p.n_iter = -1; p.adapt = adapt; p.draw_base = 0;
+    p.im_out = adapt ? d_im.data() : nullptr;
+    if (ts.pc == PC_DONE) ts.pc = PC_START_TRANSITION;  // tick_resume_kernel
+    for (int k = 0; k < n_ticks; ++k) {
+      active = 0;
+      TickRunner<1, kEmuK> r(tp, grp);
+      r.tick(0);
+      gradient_stage(TH.data(), G.data(), LP);
+    }
+  };
+  if (warm_ticks >= 0) {
+    run_free(warm_ticks, 1);
+    ts.pc = PC_DONE;  // freeze abandons the transition in flight (tick_abort_kernel)
+  } else {
+    run_batch(n_warmup, 1, 0);
+  }
+  if (rows_out) rows_out[0] = warm_ticks >= 0 ? ts.rows : n_warmup;
   for (int i = 0; i < ld; ++i) {
     inv_mass[i] = std::sqrt((est[1 * ld + i] / sc.est_w) / (est[3 * ld + i] / sc.est_w));
   }
@@ -203,7 +224,13 @@ static void run_tick(const EmuTuning& t, int D, const double* tparam, uint32_t s
   *step_out = sc.step;
   *min_micro_out = sc.min_micro;
   std::memcpy(inv_mass_out, inv_mass.data(), D * 8);
-  run_batch(n_sampling, 0, n_warmup);
+  if (samp_ticks >= 0) {
+    if (warm_ticks < 0 && ts.rows < n_warmup) ts.rows = n_warmup;  // rows_floor
+    run_free(samp_ticks, 0);
+  } else {
+    run_batch(n_sampling, 0, warm_ticks >= 0 ? ts.rows : n_warmup);
+  }
+  if (rows_out) rows_out[1] = samp_ticks >= 0 ? ts.rows : rows_out[0] + n_sampling;
   for (int i = 0; i < total; ++i) {
     std::memcpy(draws + static_cast<size_t>(i) * D, d_draws.data() + static_cast<size_t>(i) * ld, D * 8);
     if (i < n_warmup && im_trace) {
@@ -232,6 +259,35 @@ extern "C" int emu_run_chain_tick(int kind, int D, const double* tparam, const E
     case 2: run_tick<FunnelTarget>(*t, D, tparam, seed, chain, theta0, mass0, step0, n_warmup,
                                    n_sampling, draws, lp, depth, step_trace, im_trace,
                                    inv_mass_out, step_out, min_micro_out, evals); break;
+    default: return -2;
+  }
+  return 0;
+}
+
+// free-running variant: see run_tick
+extern "C" int emu_run_chain_tick_free(int kind, int D, const double* tparam,
+                                       const EmuTuning* t, uint32_t seed, uint32_t chain,
+                                       const double* theta0, const double* mass0,
+                                       double step0, int n_warmup, int n_sampling,
+                                       int warm_ticks, int samp_ticks, double* draws,
+                                       double* lp, int* depth, double* step_trace,
+                                       double* im_trace, double* inv_mass_out,
+                                       double* step_out, int* min_micro_out,
+                                       unsigned long long* evals, long long* rows_out) {
+  if (D > 2 * kEmuK || t->max_depth > kMaxDepth) return -1;
+  switch (kind) {
+    case 0: run_tick<StdNormalTarget>(*t, D, tparam, seed, chain, theta0, mass0, step0,
+                                      n_warmup, n_sampling, draws, lp, depth, step_trace,
+                                      im_trace, inv_mass_out, step_out, min_micro_out, evals,
+                                      warm_ticks, samp_ticks, rows_out); break;
+    case 1: run_tick<DiagGaussianTarget>(*t, D, tparam, seed, chain, theta0, mass0, step0,
+                                         n_warmup, n_sampling, draws, lp, depth, step_trace,
+                                         im_trace, inv_mass_out, step_out, min_micro_out,
+                                         evals, warm_ticks, samp_ticks, rows_out); break;
+    case 2: run_tick<FunnelTarget>(*t, D, tparam, seed, chain, theta0, mass0, step0, n_warmup,
+                                   n_sampling, draws, lp, depth, step_trace, im_trace,
+                                   inv_mass_out, step_out, min_micro_out, evals, warm_ticks,
+                                   samp_ticks, rows_out); break;
     default: return -2;
   }
   return 0;

@@ -467,3 +467,69 @@ def test_free_running_ticks_give_ragged_draws_with_the_same_posterior(wb, oracle
     z = np.abs(ragged["mean"] - cpu_mean) / np.sqrt(ragged["mcse"] ** 2 + cpu_mcse ** 2)
     assert np.max(z) < 5.0, z
     assert np.max(ragged["r_hat"]) < 1.05
+
+
+def test_free_running_warmup_adapts_every_chain(wb, oracle):
+    """wb200_session_warmup_ticks: adaptive warm-up on a tick budget; chains adapt over
+    ragged transition counts, freeze abandons the transitions in flight, and the frozen
+    step sizes / metrics give the same posterior as an iteration-quota warm-up."""
+    N, D, C = 400, 6, 192
+    X, y = make_logistic(N, D, 3)
+    with wb.Session(wb.models.logistic(X, y), C, seed=21, max_trajectory_doublings=7) as s:
+        s.init(init_radius=0.5)
+        s.reserve(400)
+        s.warmup_ticks(2500).freeze()
+        st = s.state()
+        s.sample_ticks(800).sync()
+        ragged = s.summary_ragged(0)
+    with wb.Session(wb.models.logistic(X, y), C, seed=21, max_trajectory_doublings=7) as s:
+        s.init(init_radius=0.5)
+        s.warmup(150).freeze()
+        quota = s.state()
+    # the adapted step sizes and metrics agree in distribution with the quota warm-up's
+    assert np.all(np.isfinite(st["step"])) and np.all(st["step"] > 0)
+    assert abs(np.median(st["step"]) / np.median(quota["step"]) - 1) < 0.15
+    assert np.max(np.abs(np.median(st["inv_mass"], axis=0) /
+                         np.median(quota["inv_mass"], axis=0) - 1)) < 0.25
+    target = Target("logistic", D, X=X, y=y)
+    cfg = default_config(min_warmup_iter=120, max_warmup_iter=120, min_sampling_iter=400,
+                         max_sampling_iter=400, max_trajectory_doublings=7)
+    pos = oracle.init_positions(8, D, 4, 0.5)
+    mass, steps = oracle.init_mass_step(target, pos, 4, 1.0)
+    cpu = oracle.walnuts(target, cfg, 4, pos, mass, steps)
+    chains = [cpu["out"][c, :400] for c in range(8)]
+    cpu_mean = np.mean(np.concatenate(chains), axis=0)
+    cpu_mcse = oracle.mcse(chains)
+    z = np.abs(ragged["mean"] - cpu_mean) / np.sqrt(ragged["mcse"] ** 2 + cpu_mcse ** 2)
+    assert np.max(z) < 5.0, z
+    assert np.max(ragged["r_hat"]) < 1.05
+
+
+def test_one_shot_readback_is_identical_for_pinned_and_pageable_buffers(wb):
+    """walnutpie_sample_device copies the draws back block by block while sampling runs
+    (2-D copies when D is even, 3-D strided copies when rows are padded): the result
+    must not depend on the kind of host buffer, and must equal the session's draws."""
+    import ctypes
+    from walnuts_b200 import _ffi
+    for D in (6, 7):
+        C, nw, ns = 12, 23, 37
+        model = wb.models.diag_gaussian(np.linspace(0.5, 3.0, D))
+        desc = model.desc()
+        outs = []
+        for pinned in (False, True):
+            out = _ffi.pinned_empty((C, nw + ns, D)) if pinned else np.zeros((C, nw + ns, D))
+            out[...] = -7.0
+            lengths, stepsize = np.zeros(2 * C, np.int32), np.zeros(C)
+            _ffi._ffi_sample_device(
+                ctypes.byref(desc), D, None, C, 31, 2, 2.0, None, nw, nw, ns, ns, 10, 5, 1,
+                0.5, 0.1, 1.0, 1.01, 4.0, 1e-5, 15.0, 1.0, 0.8, 0.05, 0.8, 0.9, 1e-4, 0.5,
+                True, out, out.size, lengths, stepsize, None, 0, _ffi.print_callback)
+            assert np.all(lengths[:C] == nw) and np.all(lengths[C:] == ns)
+            outs.append(np.array(out))
+        np.testing.assert_array_equal(outs[0], outs[1])
+        assert not np.any(outs[0] == -7.0)
+        with wb.Session(model, C, seed=31 + 2 + C) as s:
+            s.init(init_radius=2.0)
+            s.reserve(nw + ns)
+            s.warmup(nw, store=True).freeze().sample(ns).sync()
+            np.testing.assert_array_equal(s.draws(0, nw + ns), outs[0])

@@ -57,6 +57,53 @@ def test_device_state_machine_equals_oracle_bitwise(emu, oracle, engine, kind, D
         assert e["grad_evals"] == o["grad_evals"]
 
 
+FREE_CASES = [
+    ("std_normal", 10, dict(), 0.4),
+    ("diag_gaussian", 12, dict(max_trajectory_doublings=8), 0.7),
+    ("funnel", 11, dict(max_step_halvings=8, max_trajectory_doublings=7), 0.5),
+]
+
+
+@pytest.mark.parametrize("kind,D,over,step0", FREE_CASES)
+def test_free_running_sampling_equals_oracle_bitwise(emu, oracle, kind, D, over, step0):
+    """free-running lock-step mode (wb200_session_sample_ticks): after a tick budget the
+    chain has completed some k transitions, and those are the oracle's first k draws"""
+    rng = np.random.default_rng(7 * D)
+    prec = rng.uniform(0.05, 20.0, D) if kind == "diag_gaussian" else None
+    target, cfg = Target(kind, D, prec=prec), default_config(**over)
+    th0, m0 = rng.normal(size=D), rng.uniform(0.3, 3.0, D)
+    nw, cap = 40, 400
+    e = host_emu.run_chain(emu, kind, D, prec, cfg, 99, 3, th0, m0, step0, nw, cap,
+                           engine="tick", samp_ticks=1500)
+    k = e["rows"][1] - nw
+    assert 10 < k < cap
+    o = oracle.run_chain(target, cfg, 99, 3, th0, m0, step0, nw, k, rng_policy=1)
+    np.testing.assert_array_equal(e["draws"][:nw + k],
+                                  np.concatenate([o["warmup_draws"], o["draws"]]))
+    np.testing.assert_array_equal(e["lp"][nw:nw + k], o["lp"])
+    np.testing.assert_array_equal(e["depth"][nw:nw + k], o["depth"])
+
+
+@pytest.mark.parametrize("kind,D,over,step0", FREE_CASES)
+def test_free_running_warmup_equals_oracle_bitwise(emu, oracle, kind, D, over, step0):
+    """free-running adaptive warm-up (wb200_session_warmup_ticks): the k warm-up
+    transitions completed within the tick budget are the oracle's first k"""
+    rng = np.random.default_rng(11 * D)
+    prec = rng.uniform(0.05, 20.0, D) if kind == "diag_gaussian" else None
+    target, cfg = Target(kind, D, prec=prec), default_config(**over)
+    th0, m0 = rng.normal(size=D), rng.uniform(0.3, 3.0, D)
+    cap = 400
+    e = host_emu.run_chain(emu, kind, D, prec, cfg, 17, 1, th0, m0, step0, cap, 0,
+                           engine="tick", warm_ticks=1200, samp_ticks=0)
+    k = e["rows"][0]
+    assert 10 < k < cap
+    o = oracle.run_chain(target, cfg, 17, 1, th0, m0, step0, k, 0, rng_policy=1)
+    np.testing.assert_array_equal(e["draws"][:k], o["warmup_draws"])
+    np.testing.assert_array_equal(e["lp"][:k], o["warmup_lp"])
+    np.testing.assert_array_equal(e["step_trace"][:k], o["warmup_step"])
+    np.testing.assert_array_equal(e["warmup_inv_mass"][:k], o["warmup_inv_mass"])
+
+
 def test_trajectories_exercise_every_branch(emu, oracle):
     """the cases above must actually reach halvings, reversibility ladders, deep
     trees and rejected extensions, or the bitwise agreement proves little"""

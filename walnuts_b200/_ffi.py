@@ -237,6 +237,8 @@ session_sample = _sess("wb200_session_sample", [session_p, ctypes.c_int, ctypes.
 session_sync = _sess("wb200_session_sync", [session_p])
 session_sample_ticks = _sess("wb200_session_sample_ticks",
                              [session_p, ctypes.c_int, ctypes.c_int])
+session_warmup_ticks = _sess("wb200_session_warmup_ticks",
+                             [session_p, ctypes.c_int, ctypes.c_int])
 session_chain_rows = _sess("wb200_session_chain_rows", [
     session_p, ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")])
 session_rhat_moments = _sess("wb200_session_rhat_moments", [
@@ -287,6 +289,26 @@ def last_run_stats():
                 warmup_iters=w.value, sampling_iters=s_.value)
 
 
+_host_alloc = _sess("wb200_host_alloc", [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)])
+trim_memory = _sess("wb200_trim_memory", [ctypes.c_int])
+_lib.wb200_host_free.restype = None
+_lib.wb200_host_free.argtypes = [ctypes.c_void_p]
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """A numpy array over page-locked host memory (wb200_host_alloc); freed with the
+    array.  Contents are uninitialised."""
+    import weakref
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape, dtype=np.int64))
+    p = ctypes.c_void_p()
+    _host_alloc(max(n, 1) * dtype.itemsize, ctypes.byref(p))
+    buf = (ctypes.c_char * (max(n, 1) * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    weakref.finalize(buf, _lib.wb200_host_free, p.value)
+    return arr
+
+
 orbit = _sess("wb200_orbit", [
     ctypes.POINTER(WalnutModelDesc), ctypes.c_size_t, double_array, double_array,
     double_array, ctypes.c_double, ctypes.c_int, double_array, double_array,
@@ -316,11 +338,13 @@ EXPORTED_SYMBOLS = [
     "wb200_session_create", "wb200_session_destroy", "wb200_session_init",
     "wb200_session_reserve_draws", "wb200_session_warmup", "wb200_session_freeze",
     "wb200_session_sample", "wb200_session_sync", "wb200_session_sample_ticks",
+    "wb200_session_warmup_ticks",
     "wb200_session_chain_rows", "wb200_session_summary", "wb200_session_rhat_moments", "wb200_session_warmup_sums",
     "wb200_session_warmup_deviation", "wb200_session_lp_moments",
     "wb200_session_get_draws", "wb200_session_get_trace", "wb200_session_get_state",
     "wb200_session_device_draws", "wb200_session_counters",
     "wb200_session_last_kernel_ms", "wb200_session_timer_record",
-    "wb200_session_timer_elapsed_ms", "wb200_last_run_stats", "wb200_orbit", "wb200_philox",
+    "wb200_session_timer_elapsed_ms", "wb200_host_alloc", "wb200_host_free", "wb200_trim_memory",
+    "wb200_last_run_stats", "wb200_orbit", "wb200_philox",
     "wb200_philox_normals", "wb200_device_summary", "wb200_logistic_logp_grad",
 ]

@@ -266,10 +266,23 @@ int wb200_session_warmup(wb200_session* s, int n_iter, int store, WalnutpyError*
   });
 }
 
+int wb200_session_warmup_ticks(wb200_session* s, int n_ticks, int store,
+                               WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    if (!s->tick) throw std::runtime_error("warmup_ticks needs the lock-step engine");
+    if (s->frozen) throw std::runtime_error("warm-up after freeze");
+    if (n_ticks < 0) throw std::invalid_argument("n_ticks must be non-negative");
+    if (store && s->draw_cap == 0) throw std::runtime_error("reserve draws first");
+    tick_run_ticks(*s, n_ticks, 1, store != 0);
+  });
+}
+
 int wb200_session_freeze(wb200_session* s, WalnutpyError** err) {
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));
     if (!s->initialised) throw std::runtime_error("session is not initialised");
+    if (s->tick) tick_abort_inflight(*s);
     launch_freeze(*s);
     s->frozen = true;
   });

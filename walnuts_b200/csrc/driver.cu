@@ -9,6 +9,9 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -285,6 +288,16 @@ int walnutpie_sample_device(
       }
     };
     WalnutpyError* e = nullptr;
+    const bool trace_phases = std::getenv("WB200_TRACE_PHASES") != nullptr;
+    auto t_phase = std::chrono::steady_clock::now();
+    auto phase = [&](const char* name) {  // host-side phase timing, diagnostics only
+      if (!trace_phases) return;
+      if (s) cudaStreamSynchronize(s->stream);
+      auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[wb200] %-12s %8.2f ms\n", name,
+                   std::chrono::duration<double, std::milli>(now - t_phase).count());
+      t_phase = now;
+    };
     // per-chain streams are keyed by (seed + id + num_chains, chain): the same
     // mixing of seed and id as walnutpy.cpp:82
     const unsigned int run_seed = seed + id + static_cast<unsigned int>(num_chains);
@@ -292,6 +305,7 @@ int walnutpie_sample_device(
     check(wb200_session_init(s, inits, init_radius, init_inv_metric, nullptr, &e), e);
     check(wb200_session_reserve_draws(s, static_cast<long long>(rows_per_chain), 0, &e), e);
 
+    phase("setup+init");
     auto say = [&](const std::string& m) {
       if (print) print(m.c_str(), m.size(), false);
     };
@@ -308,6 +322,64 @@ int walnutpie_sample_device(
       }
     };
 
+    // Draw read-back overlaps sampling: the rows a block of iterations stored are
+    // copied on a second stream while the next block runs (one strided 3-D copy
+    // per block: D doubles x rows x chains).  The copy of block k is issued
+    // after block k+1 is launched so that it overlaps even when `out` is
+    // pageable and the copy call blocks the host; with a pinned `out` (see
+    // wb200_host_alloc) it is a plain DMA at PCIe rate.
+    WB200_CUDA(cudaSetDevice(s->device));
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t block_done = nullptr;
+    WB200_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    WB200_CUDA(cudaEventCreateWithFlags(&block_done, cudaEventDisableTiming));
+    struct Cleanup {
+      cudaStream_t& st; cudaEvent_t& ev;
+      ~Cleanup() {
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+        if (ev) cudaEventDestroy(ev);
+      }
+    } cleanup{copy_stream, block_done};
+    long long pending_from = 0, pending_to = 0;  // rows [from, to) stored, not yet copied
+    bool pending_marked = false;
+    auto mark_block = [&](long long rows_now) {  // after launching a storing block
+      pending_to = rows_now;
+      WB200_CUDA(cudaEventRecord(block_done, s->stream));
+      pending_marked = true;
+    };
+    auto flush_pending = [&] {  // copy every row whose block has been marked
+      if (!pending_marked || pending_to <= pending_from) return;
+      WB200_CUDA(cudaStreamWaitEvent(copy_stream, block_done, 0));
+      const long long n_rows = pending_to - pending_from;
+      const size_t src_pitch = static_cast<size_t>(s->draw_cap) * s->ld * sizeof(double);
+      const size_t dst_pitch = draws_offset * sizeof(double);
+      const size_t max_pitch = (size_t{1} << 31) - 1;  // cudaDeviceProp::memPitch
+      if (s->ld == num_params && src_pitch <= max_pitch && dst_pitch <= max_pitch) {
+        // rows of a chain are contiguous on both sides: one 2-D copy whose
+        // "row" is the chain's whole block
+        WB200_CUDA(cudaMemcpy2DAsync(
+            out + static_cast<size_t>(pending_from) * num_params,
+            dst_pitch,
+            s->draws.ptr + static_cast<size_t>(pending_from) * s->ld,
+            src_pitch,
+            static_cast<size_t>(n_rows) * num_params * sizeof(double), C,
+            cudaMemcpyDeviceToHost, copy_stream));
+      } else {
+        cudaMemcpy3DParms cp{};
+        cp.srcPtr = make_cudaPitchedPtr(s->draws.ptr, s->ld * sizeof(double),
+                                        num_params * sizeof(double), s->draw_cap);
+        cp.srcPos = make_cudaPos(0, pending_from, 0);
+        cp.dstPtr = make_cudaPitchedPtr(out, num_params * sizeof(double),
+                                        num_params * sizeof(double), rows_per_chain);
+        cp.dstPos = make_cudaPos(0, pending_from, 0);
+        cp.extent = make_cudaExtent(num_params * sizeof(double), n_rows, C);
+        cp.kind = cudaMemcpyDeviceToHost;
+        WB200_CUDA(cudaMemcpy3DAsync(&cp, copy_stream));
+      }
+      pending_from = pending_to;
+      pending_marked = false;
+    };
+
     // ---- warm-up: blocks of publish_stride iterations, controller between
     const int stride = t.publish_stride > 0 ? t.publish_stride : 5;
     int warm_done = 0;
@@ -316,6 +388,10 @@ int walnutpie_sample_device(
     while (warm_done < max_warmup_iter) {
       const int n = std::min(stride, max_warmup_iter - warm_done);
       check(wb200_session_warmup(s, n, save_warmup ? 1 : 0, &e), e);
+      if (save_warmup) {
+        flush_pending();
+        mark_block(warm_done + n);
+      }
       progress(warm_done, warm_done + n, true);
       warm_done += n;
       if (warm_done >= min_warmup_iter && warm_done < max_warmup_iter) {
@@ -326,11 +402,15 @@ int walnutpie_sample_device(
       }
     }
     check(wb200_session_freeze(s, &e), e);
+    phase("warmup");
+    const int saved_warm = save_warmup ? warm_done : 0;
     // ---- sampling: R-hat of lp between blocks (sampler.hpp:132-151)
     int samp_done = 0;
     while (samp_done < max_sampling_iter) {
       const int n = std::min(stride, max_sampling_iter - samp_done);
       check(wb200_session_sample(s, n, 1, &e), e);
+      flush_pending();
+      mark_block(saved_warm + samp_done + n);
       progress(warm_done + samp_done, warm_done + samp_done + n, false);
       samp_done += n;
       if (samp_done >= min_sampling_iter && samp_done < max_sampling_iter) {
@@ -349,16 +429,13 @@ int walnutpie_sample_device(
         if (r_hat <= rhat_converge_tol) break;
       }
     }
+    flush_pending();
     check(wb200_session_sync(s, &e), e);
+    phase("sampling");
+    WB200_CUDA(cudaStreamSynchronize(copy_stream));
+    phase("copy tail");
     // ---- outputs (walnutpy.cpp:196-221; handlers.hpp:73-100)
-    const int saved_warm = save_warmup ? warm_done : 0;
-    const long long rows = saved_warm + samp_done;
-    WB200_CUDA(cudaSetDevice(s->device));
     for (size_t c = 0; c < C; ++c) {
-      WB200_CUDA(cudaMemcpy2DAsync(
-          out + draws_offset * c, num_params * sizeof(double),
-          s->draws.ptr + c * s->draw_cap * s->ld, s->ld * sizeof(double),
-          num_params * sizeof(double), rows, cudaMemcpyDeviceToHost, s->stream));
       final_lengths[c] = saved_warm;
       final_lengths[c + C] = samp_done;
     }
@@ -369,8 +446,39 @@ int walnutpie_sample_device(
     g_last_run.warmup_iters = warm_done;
     g_last_run.sampling_iters = samp_done;
   });
+  const auto t_destroy = std::chrono::steady_clock::now();
   wb200_session_destroy(s);
+  if (std::getenv("WB200_TRACE_PHASES")) {
+    std::fprintf(stderr, "[wb200] %-12s %8.2f ms\n", "destroy",
+                 std::chrono::duration<double, std::milli>(
+                     std::chrono::steady_clock::now() - t_destroy).count());
+  }
   return rc;
+}
+
+// Page-locked host memory for `out` / `inits`: makes the read-back of
+// walnutpie_sample_device a direct DMA that overlaps sampling.
+int wb200_host_alloc(size_t bytes, void** ptr, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    require_gpu();
+    if (!ptr) throw std::invalid_argument("ptr is null");
+    *ptr = nullptr;
+    WB200_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+  });
+}
+void wb200_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+// Return the cached device memory of destroyed sessions to the driver.
+int wb200_trim_memory(int device, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    require_gpu();
+    cudaMemPool_t pool;
+    WB200_CUDA(cudaDeviceSynchronize());
+    WB200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    WB200_CUDA(cudaMemPoolTrimTo(pool, 0));
+  });
 }
 
 }  // extern "C"

@@ -33,6 +33,39 @@ struct CudaError : std::runtime_error {
     }                                                                           \
   } while (0)
 
+// Device memory comes from the device's stream-ordered pool with an unlimited
+// release threshold: a session's buffers (GBs of stored draws) go back to the
+// pool when it is destroyed and the next session reuses them, instead of a
+// cudaMalloc/cudaFree pair per one-shot call (cudaFree of multi-GB buffers was
+// measured at 50-500 ms).  wb200_trim_memory() returns the pool to the driver.
+inline void* pool_alloc(size_t bytes) {
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess && dev >= 0 && dev < 64 && !configured[dev]) {
+    cudaMemPool_t pool;
+    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured[dev] = true;
+  }
+  void* ptr = nullptr;
+  if (e == cudaSuccess) e = cudaMallocAsync(&ptr, bytes, cudaStream_t{0});
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStream_t{0});
+  if (e != cudaSuccess) {
+    throw CudaError(std::string("CUDA error: ") + cudaGetErrorString(e) +
+                    " allocating " + std::to_string(bytes) + " bytes of device memory");
+  }
+  return ptr;
+}
+inline void pool_free(void* ptr) {
+  // like cudaFree: nothing in flight may still use the buffer
+  cudaDeviceSynchronize();
+  cudaFreeAsync(ptr, cudaStream_t{0});
+}
+
 template <class T>
 struct DeviceBuffer {
   T* ptr = nullptr;
@@ -43,11 +76,11 @@ struct DeviceBuffer {
   ~DeviceBuffer() { release(); }
   void alloc(size_t n) {
     release();
-    if (n) WB200_CUDA(cudaMalloc(&ptr, n * sizeof(T)));
+    if (n) ptr = static_cast<T*>(pool_alloc(n * sizeof(T)));
     count = n;
   }
   void release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) pool_free(ptr);
     ptr = nullptr;
     count = 0;
   }
@@ -139,6 +172,7 @@ void tick_init(wb200_session& s, bool have_mass, bool have_steps, bool have_posi
 void tick_run(wb200_session& s, int n_iter, int adapt, bool store);
 void tick_run_ticks(wb200_session& s, int n_ticks, int adapt, bool store);
 void tick_chain_rows(wb200_session& s, long long* rows_host);
+void tick_abort_inflight(wb200_session& s);
 unsigned long long tick_count(const wb200_session& s);
 void launch_orbit(int kind, int D, int ld, int C, const double* tparam,
                   double* theta, double* rho, const double* inv_mass, double* grad,

@@ -474,6 +474,20 @@ void tick_run_ticks(wb200_session& s, int n_ticks, int adapt, bool store) {
   WB200_CUDA(cudaEventRecord(s.ev1, s.stream));
 }
 
+// freeze after a free-running warm-up: the transition a chain has in flight was
+// started under the adapting step / metric and is abandoned; the chain restarts from
+// its last completed draw (TV_CUR, its gradient and log density are only written at
+// the end of a transition)
+__global__ void tick_abort_kernel(TickState* ts, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) ts[c].pc = PC_DONE;
+}
+
+void tick_abort_inflight(wb200_session& s) {
+  tick_abort_kernel<<<(s.C + 255) / 256, 256, 0, s.stream>>>(s.tick->ts.ptr, s.C);
+  WB200_CUDA(cudaGetLastError());
+}
+
 void tick_chain_rows(wb200_session& s, long long* rows_host) {
   TickEngine& e = *s.tick;
   DeviceBuffer<long long> d;

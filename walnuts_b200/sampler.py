@@ -104,7 +104,7 @@ def walnuts_device(
     out = prepare_output_buffer(num_chains=num_chains, num_params=num_params,
                                 max_sampling_iter=max_sampling_iter,
                                 max_warmup_iter=max_warmup_iter,
-                                save_warmup=save_warmup)
+                                save_warmup=save_warmup, pinned=True)
     if inits is not None:
         inits = np.ascontiguousarray(inits, dtype=np.float64)
         if inits.shape == (num_params,):
@@ -219,6 +219,12 @@ class Session:
         """Lock-step sessions: exactly ``n_ticks`` ticks (one batched gradient each);
         chains complete as many transitions as fit (ragged draw counts)."""
         _ffi.session_sample_ticks(self._h, int(n_ticks), int(store))
+        return self
+
+    def warmup_ticks(self, n_ticks: int, store: bool = False):
+        """Lock-step sessions: adaptive warm-up for exactly ``n_ticks`` ticks; every chain
+        adapts over as many transitions as fit.  ``freeze`` abandons those in flight."""
+        _ffi.session_warmup_ticks(self._h, int(n_ticks), int(store))
         return self
 
     def chain_rows(self) -> np.ndarray:

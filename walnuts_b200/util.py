@@ -15,8 +15,11 @@ def prepare_seed(seed: Optional[int]) -> int:
 
 
 def prepare_output_buffer(*, num_chains: int, num_params: int, max_sampling_iter: int,
-                          max_warmup_iter: int, save_warmup: bool) -> np.ndarray:
-    # util.py:16-32
+                          max_warmup_iter: int, save_warmup: bool,
+                          pinned: bool = False) -> np.ndarray:
+    # util.py:16-32; pinned=True places the buffer in page-locked memory so that the
+    # library's draw read-back is a DMA overlapping sampling (rows beyond the returned
+    # lengths are then uninitialised instead of zero; callers slice by length)
     if num_chains < 1:
         raise ValueError("num_chains must be at least 1")
     if max_warmup_iter < 0:
@@ -24,7 +27,14 @@ def prepare_output_buffer(*, num_chains: int, num_params: int, max_sampling_iter
     if max_sampling_iter < 1:
         raise ValueError("max_sampling_iter must be at least 1")
     num_draws = max_sampling_iter + max_warmup_iter * save_warmup
-    return np.zeros((num_chains, num_draws, num_params), dtype=np.float64)
+    shape = (num_chains, num_draws, num_params)
+    if pinned:
+        from . import _ffi
+        try:
+            return _ffi.pinned_empty(shape)
+        except (RuntimeError, MemoryError):
+            pass  # page-locking refused (size limits): a pageable buffer still works
+    return np.zeros(shape, dtype=np.float64)
 
 
 def prepare_inv_metric(init_inv_metric: Optional[np.ndarray], metric_size: tuple,
