@@ -185,10 +185,17 @@ def run_c4(args):
     X, y = logistic_data(N, Dm)
     tune = dict(max_trajectory_doublings=cfgw["max_doublings"],
                 max_step_halvings=cfgw["max_halvings"])
+    cap = max(8, (W + K) * tps // 8)  # room for the draws of the free-running phase
+    from walnuts_b200 import _ffi
+    import psutil
+    if C * cap * Dm * 8 > 0.25 * psutil.virtual_memory().available:
+        raise SystemExit("not enough host memory for the draw read-back buffer")
+    host_draws = _ffi.pinned_empty((C, cap, Dm))   # the caller's result buffer
+    # e2e: everything a user of the C-ABI session pays, from host X / y to host draws
+    t_e2e = time.perf_counter()
     sess = wb.Session(wb.models.logistic(X, y), C, seed=SEED, chain_offset=chain_offset,
                       device=local_rank, **tune)
     sess.init(init_radius=0.1)
-    cap = max(8, (W + K) * tps // 8)  # room for the draws of the free-running phase
     sess.reserve(cap)
     c0 = sess.counters()
     t0 = time.perf_counter()
@@ -214,24 +221,28 @@ def run_c4(args):
             sess.sample_ticks(tps)
         total_ms = sess.timer_stop_ms()
         wall_ms = 1e3 * (time.perf_counter() - t0)
+    sess.draws(0, cap, out=host_draws)
+    rows = sess.chain_rows()
+    e2e_s = time.perf_counter() - t_e2e
     if distributed:
         dist.barrier()
     c3 = sess.counters()
     evals = c3["grad_evals"] - c2["grad_evals"]
     launches = c3["kernel_launches"] - c2["kernel_launches"]
-    rows = sess.chain_rows()
     summ = sess.summary_ragged(0)
     # the only collective: per-dimension chain-moment sums -> R-hat over ALL ranks' chains
     mom = torch.tensor(sess.rhat_moments(0), dtype=torch.float64, device="cuda")
-    tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    ee = torch.tensor([float(evals), float(np.min(summ["ess"]))], dtype=torch.float64,
-                      device="cuda")
+    tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+    ee = torch.tensor([float(evals), float(np.min(summ["ess"])), float(c3["grad_evals"])],
+                      dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(mom, op=dist.ReduceOp.SUM)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ee, op=dist.ReduceOp.SUM)   # independent chains: evals and ESS add
     global_rhat = rhat_from_dimension_moments(mom.cpu().numpy())
-    total_ms = float(tt.item())
+    total_ms, e2e_s = float(tt[0].item()), float(tt[1].item())
+    e2e_evals = float(ee[2].item())
+    e2e_steps = (cfgw["warmup_ticks"] + (W + K) * tps) / tps
     evals_local = evals
     evals = float(ee[0].item())
     min_ess_total = float(ee[1].item())
@@ -262,7 +273,7 @@ def run_c4(args):
     steps = np.full(cores, 0.02)
     t0 = time.perf_counter()
     if args.no_cpu_baseline:
-        r, cpu_s = {"grad_evals": float("nan")}, 1.0
+        r, cpu_s = {"grad_evals": 0}, 1.0
     else:
         r = checker.walnuts(target, ccfg, SEED, pos, mass, steps)
         cpu_s = time.perf_counter() - t0
@@ -273,7 +284,11 @@ def run_c4(args):
         "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "bf16 tensor cores (hi+lo split), "
         "fp32 accumulate, fp64 state", "data": "synthetic",
-        "config": {"workload": "c4: Bayesian logistic regression N=100k, D=512, 8192 chains, "
+        "config": {"workload": ("c5: Bayesian logistic regression N=100k, D=512, "
+                                f"{total} chains sharded over the GPUs, "
+                                if strong else
+                                "c4: Bayesian logistic regression N=100k, D=512, 8192 chains "
+                                "per GPU, ") +
                                "lock-step tick engine + tcgen05 batched gradient",
                    "N": N, "dims": Dm, "chains_per_gpu": C, "chains_total": total,
                    "ticks_per_step": tps,
@@ -297,10 +312,19 @@ def run_c4(args):
                      "gradient_only_ms_per_batched_eval": grad_ms,
                      "gradient_only_tflops": C * flops_alg / (grad_ms * 1e-3) / 1e12,
                      "kernel": "gemm_kmajor_kernel<128,1> + gemm_kmajor_kernel<256,2>"},
-        "cpu_baseline": {"value": r["grad_evals"] / cpu_s, "unit": "grad_evals/s",
-                         "cores": cores, "kind": kind,
-                         "sample": f"{cores} chains x (2 warm-up + 2 sampling) iterations, "
-                                   "same data", "seconds": cpu_s},
+        "e2e": {"value": e2e_evals / e2e_s, "unit": "grad_evals/s",
+                "h2d_bytes_per_step": int((X.nbytes + y.nbytes) / e2e_steps),
+                "d2h_bytes_per_step": int(host_draws.nbytes / e2e_steps),
+                "seconds": e2e_s, "grad_evals": e2e_evals, "steps": e2e_steps,
+                "api": "C-ABI session (wb200_session_create with host X / y, init, "
+                       "warmup_ticks, freeze, sample_ticks, get_draws into a pinned host "
+                       "buffer): upload, adaptive warm-up, every sampling step of this run "
+                       "and the read-back of all stored draws inside the timed region"},
+        "cpu_baseline": (None if args.no_cpu_baseline else {
+            "value": r["grad_evals"] / cpu_s, "unit": "grad_evals/s",
+            "cores": cores, "kind": kind,
+            "sample": f"{cores} chains x (2 warm-up + 2 sampling) iterations, same data",
+            "seconds": cpu_s}),
         "clocks": clocks.summary(),
     }
     print(json.dumps(line), flush=True)

@@ -275,6 +275,7 @@ int wb200_session_warmup_ticks(wb200_session* s, int n_ticks, int store,
     if (n_ticks < 0) throw std::invalid_argument("n_ticks must be non-negative");
     if (store && s->draw_cap == 0) throw std::runtime_error("reserve draws first");
     tick_run_ticks(*s, n_ticks, 1, store != 0);
+    if (store) s->ragged = true;
   });
 }
 
@@ -309,6 +310,7 @@ int wb200_session_sample_ticks(wb200_session* s, int n_ticks, int store,
     if (n_ticks < 0) throw std::invalid_argument("n_ticks must be non-negative");
     if (store && s->draw_cap == 0) throw std::runtime_error("reserve draws first");
     tick_run_ticks(*s, n_ticks, 0, store != 0);
+    if (store) s->ragged = true;
   });
 }
 
@@ -388,7 +390,10 @@ int wb200_session_get_draws(wb200_session* s, long long first, long long count,
                             double* out, WalnutpyError** err) {
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));
-    if (first < 0 || count < 0 || first + count > s->rows_written) {
+    // after a free-running phase chains hold different numbers of rows
+    // (wb200_session_chain_rows); any range inside the capacity may be read
+    const long long limit = s->ragged ? s->draw_cap : s->rows_written;
+    if (first < 0 || count < 0 || first + count > limit) {
       throw std::invalid_argument("draw range out of bounds");
     }
     for (int c = 0; c < s->C; ++c) {

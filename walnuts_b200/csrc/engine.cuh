@@ -147,6 +147,7 @@ struct wb200_session {
   bool frozen = false, initialised = false;
   long long draw_cap = 0, rows_written = 0;
   bool trace = false;
+  bool ragged = false;  // a free-running phase has stored draws: per-chain row counts
   unsigned long long launches = 0;
 
   wb200::DeviceBuffer<double> theta, inv_mass, est, tparam, scratch, draws,

@@ -68,6 +68,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// shared -> global tile store through the TMA (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src,
+                                             int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+      "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+      : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {  // staging buffer may be rewritten
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {  // generic writes -> async proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -97,6 +116,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// the same load without the wait, and the wait as a separate step that the registers
+// pass through (so no use of them can be scheduled above it): lets an epilogue warp
+// fetch its next 32 columns while it works on the current ones
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]),
+                 "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]),
+                 "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]),
+                 "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                 "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor:
@@ -143,8 +189,13 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTileBytes = kStages * kStageBytes;
-  static constexpr int kTotal = kTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kBarrierBytes = 1024;  // keeps the staging area 1024-aligned
+  // GEMM 1 epilogue staging: 8 warps x [32 rows][128 B] in the SWIZZLE_128B layout
+  static constexpr int kStagingPerWarp = 32 * 128;
+  static constexpr int kStagingBytes = 8 * kStagingPerWarp;
+  static constexpr int kTotal = kTileBytes + 1024 /*align*/ + kBarrierBytes + kStagingBytes;
 };
+static_assert(GemmSmem<256>::kTotal <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -166,14 +217,46 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return r;
 }
 
-// sigmoid(z) and softplus(z) from e = exp(-|z|), inv = 1/(1+e):
-//   sigmoid = z >= 0 ? inv : e*inv ;  softplus = max(z,0) + log1p(e) = max(z,0) - ln(inv)
-// three MUFU ops (ex2, rcp, lg2) and a handful of FP32 ops per element
-__device__ __forceinline__ void sigmoid_softplus(float z, float& sig, float& sp) {
-  const float e = ex2_approx(-1.4426950408889634f * fabsf(z));
-  const float inv = rcp_approx(1.0f + e);
-  sig = z >= 0.0f ? inv : e * inv;
-  sp = fmaf(-0.6931471805599453f, lg2_approx(inv), fmaxf(z, 0.0f));
+// GEMM 1 works in base-2 units: Theta is scaled by log2(e) when it is packed, so the
+// accumulator holds w = z * log2(e).  With t = 2^-w, d = 1 + t:
+//   sigmoid(z) = 1 / d ;  softplus(z) = ln2 * (w + log2(d)) =: ln2 * u
+// three MUFU ops (ex2, rcp, lg2), one clamp and three adds per element.  The clamp
+// keeps t finite for very negative z (w >= -115: t <= 2^115, u -> 0); for large
+// positive z, t underflows to 0 and u = w, both correct to fp32 rounding.
+__device__ __forceinline__ void sigmoid_softplus2(float w, float& sig, float& u) {
+  w = fmaxf(w, -115.0f);
+  const float d = 1.0f + ex2_approx(-w);
+  sig = rcp_approx(d);
+  u = w + lg2_approx(d);
+}
+
+// GEMM 1 epilogue for 32 columns of one chain: sigmoid -> bf16, base-2 softplus sum.
+// Padded data rows (n >= N) are zero rows of X: w = 0, sigmoid = 1/2 (meets the zero
+// columns of X^T in GEMM 2) and u = 1 exactly, which the finalize kernel subtracts --
+// so there is no masking here.
+// The 64 bytes go to the warp's staging tile ([32 rows][128 B], SWIZZLE_128B: 16-byte
+// slot s of row r lives at slot s ^ (r & 7)), `half` selects columns 0-31 / 32-63; the
+// tile leaves through a TMA store, so R^T is written in whole 128-byte lines.  (Direct
+// per-thread stores, one row per lane, held the tensor pipe at 65-78 %: measured with
+// the stores removed it runs at 94 %.)
+__device__ __forceinline__ void epi1_chunk(const uint32_t (&v)[32], uint8_t* stage_row,
+                                           int lane, int half, float& sp_acc) {
+  uint32_t packed[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float s0, s1, u0, u1;
+    sigmoid_softplus2(__uint_as_float(v[i]), s0, u0);
+    sigmoid_softplus2(__uint_as_float(v[i + 1]), s1, u1);
+    sp_acc += u0 + u1;
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(s0, s1);
+    packed[i / 2] = *reinterpret_cast<uint32_t*>(&b2);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int slot = (4 * half + q) ^ (lane & 7);
+    *reinterpret_cast<uint4*>(stage_row + 16 * slot) =
+        make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+  }
 }
 
 // D[m][n] = sum_k A[m][k] B[n][k]; A may come in two planes that are summed (hi + lo).
@@ -184,7 +267,8 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
                    const __grid_constant__ CUtensorMap mapA1,
-                   const __grid_constant__ CUtensorMap mapB, const GemmParams gp) {
+                   const __grid_constant__ CUtensorMap mapB,
+                   const __grid_constant__ CUtensorMap mapOut, const GemmParams gp) {
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
@@ -195,6 +279,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
   uint64_t* tmem_full = empty_bar + S::kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* staging = smem + S::kTileBytes + S::kBarrierBytes;  // EPI 1 only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = gp.num_m_tiles * gp.num_n_tiles;
@@ -291,42 +376,27 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
         // row = chain, columns = data rows n0 + ...; R^T holds sigmoid(z) (the y term of
         // the gradient is the constant X^T y, added by the finalize kernel)
         float sp_acc = 0.0f;
-        __nv_bfloat16* rt_row = gp.RT + static_cast<long long>(row) * gp.ldrt + n0;
-#pragma unroll 1
-        for (int jj = 0; jj < kChunks; ++jj) {
-          const int j = part * kChunks + jj;
-          uint32_t v[32];
-          tmem_ld32(tmem_acc + j * 32, v);
-          const int nvalid = gp.n_valid - (n0 + j * 32);  // columns i < nvalid are data
-          uint32_t packed[16];
-          if (nvalid >= 32) {
+        static_assert(kChunks % 2 == 0, "the epilogue is software-pipelined in pairs");
+        const int j0 = part * kChunks;
+        uint8_t* stage = staging + (warp - 4) * S::kStagingPerWarp;
+        uint8_t* stage_row = stage + lane * 128;
+        uint32_t va[32], vb[32];
+        tmem_ld32_issue(tmem_acc + j0 * 32, va);
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float s0, s1, p0, p1;
-              sigmoid_softplus(__uint_as_float(v[i]), s0, p0);
-              sigmoid_softplus(__uint_as_float(v[i + 1]), s1, p1);
-              sp_acc += p0 + p1;
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(s0, s1);
-              packed[i / 2] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float s0, s1, p0, p1;
-              sigmoid_softplus(__uint_as_float(v[i]), s0, p0);
-              sigmoid_softplus(__uint_as_float(v[i + 1]), s1, p1);
-              if (i >= nvalid) { s0 = 0.0f; p0 = 0.0f; }
-              if (i + 1 >= nvalid) { s1 = 0.0f; p1 = 0.0f; }
-              sp_acc += p0 + p1;
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(s0, s1);
-              packed[i / 2] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-          }
-          uint4* dst = reinterpret_cast<uint4*>(rt_row + j * 32);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2],
-                                packed[4 * q + 3]);
+        for (int jj = 0; jj < kChunks; jj += 2) {
+          tmem_ld_wait(va);
+          tmem_ld32_issue(tmem_acc + (j0 + jj + 1) * 32, vb);
+          // the previous TMA store must have read the staging tile before it is rewritten
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+          epi1_chunk(va, stage_row, lane, 0, sp_acc);
+          tmem_ld_wait(vb);
+          if (jj + 2 < kChunks) tmem_ld32_issue(tmem_acc + (j0 + jj + 2) * 32, va);
+          epi1_chunk(vb, stage_row, lane, 1, sp_acc);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&mapOut, stage, n0 + (j0 + jj) * 32, m0 + wq * 32);
           }
         }
         atomicAdd(gp.SP + row, static_cast<double>(sp_acc));
@@ -352,6 +422,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
+    if constexpr (EPI == 1) {
+      if (lane == 0) tma_store_wait_all();
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -368,7 +441,8 @@ __global__ void pack_theta_kernel(const double* TH, int ld, int C, int D, int Dp
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(C) * Dpad) return;
   const int c = static_cast<int>(i / Dpad), d = static_cast<int>(i % Dpad);
-  const double t = d < D ? TH[static_cast<long long>(c) * ld + d] : 0.0;
+  // scaled by log2(e): GEMM 1 accumulates z in base-2 units (see sigmoid_softplus2)
+  const double t = d < D ? 1.4426950408889634 * TH[static_cast<long long>(c) * ld + d] : 0.0;
   const __nv_bfloat16 h = __double2bfloat16(t);
   const double rem = t - static_cast<double>(__bfloat162float(h));
   hi[i] = h;
@@ -378,7 +452,8 @@ __global__ void pack_theta_kernel(const double* TH, int ld, int C, int D, int Dp
 // grad = b - G32 - theta (G32 = sum_n sigmoid x) ; logp = b.theta - SP - 1/2 |theta|^2
 __global__ void logistic_finalize_kernel(const double* TH, int ld, int C, int D,
                                          const float* G32, long long ldg, const double* b,
-                                         const double* SP, double* G, double* LP) {
+                                         const double* SP, double n_pad, double* G,
+                                         double* LP) {
   const int c = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -399,7 +474,8 @@ __global__ void logistic_finalize_kernel(const double* TH, int ld, int C, int D,
     bt += __shfl_xor_sync(0xffffffffu, bt, m);
     ss += __shfl_xor_sync(0xffffffffu, ss, m);
   }
-  if (lane == 0) LP[c] = bt - SP[c] - 0.5 * ss;
+  // SP = sum over the Npad data rows of u (base-2 softplus); the n_pad zero rows add 1 each
+  if (lane == 0) LP[c] = bt - 0.6931471805599453 * (SP[c] - n_pad) - 0.5 * ss;
 }
 
 // ---------------------------------------------------------------------------
@@ -447,7 +523,7 @@ struct LogisticGrad::Impl {
   DeviceBuffer<__nv_bfloat16> X, XT, hi, lo, RT;
   DeviceBuffer<float> y, G32;
   DeviceBuffer<double> b, SP;
-  CUtensorMap mapX, mapHi, mapLo, mapRT, mapXT;
+  CUtensorMap mapX, mapHi, mapLo, mapRT, mapXT, mapRTst;
   int bn2;
   int device = 0, sms = 148;
 };
@@ -495,6 +571,7 @@ LogisticGrad::LogisticGrad(const double* Xh, const double* yh, size_t N, int D, 
   m.mapHi = make_map(m.hi.ptr, m.Cpad, m.Dpad, BM);        // GEMM 1 A planes (chains)
   m.mapLo = make_map(m.lo.ptr, m.Cpad, m.Dpad, BM);
   m.mapRT = make_map(m.RT.ptr, m.Cpad, m.Npad, BM);        // GEMM 2 A
+  m.mapRTst = make_map(m.RT.ptr, m.Cpad, m.Npad, 32);      // GEMM 1 epilogue stores
   m.mapXT = make_map(m.XT.ptr, m.Dpad, m.Npad, m.bn2);     // GEMM 2 B
   WB200_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<256, 1>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -534,7 +611,7 @@ void LogisticGrad::evaluate(const double* TH, double* G, double* LP, cudaStream_
   g1.n_valid = m.N; g1.RT = m.RT.ptr; g1.ldrt = m.Npad; g1.SP = m.SP.ptr;
   const int grid1 = std::min(m.sms, g1.num_m_tiles * g1.num_n_tiles);
   gemm_kmajor_kernel<256, 1><<<grid1, gemm_threads<1>(), GemmSmem<256>::kTotal, stream>>>(
-      m.mapHi, m.mapLo, m.mapX, g1);
+      m.mapHi, m.mapLo, m.mapX, m.mapRTst, g1);
   WB200_CUDA(cudaGetLastError());
   GemmParams g2{};
   g2.num_m_tiles = static_cast<int>(m.Cpad / BM);
@@ -545,17 +622,18 @@ void LogisticGrad::evaluate(const double* TH, double* G, double* LP, cudaStream_
   const int grid2 = std::min(m.sms, g2.num_m_tiles * g2.num_n_tiles);
   if (m.bn2 == 256) {
     gemm_kmajor_kernel<256, 2><<<grid2, gemm_threads<2>(), GemmSmem<256>::kTotal, stream>>>(
-        m.mapRT, m.mapRT, m.mapXT, g2);
+        m.mapRT, m.mapRT, m.mapXT, m.mapRT, g2);
   } else if (m.bn2 == 128) {
     gemm_kmajor_kernel<128, 2><<<grid2, gemm_threads<2>(), GemmSmem<128>::kTotal, stream>>>(
-        m.mapRT, m.mapRT, m.mapXT, g2);
+        m.mapRT, m.mapRT, m.mapXT, m.mapRT, g2);
   } else {
     gemm_kmajor_kernel<64, 2><<<grid2, gemm_threads<2>(), GemmSmem<64>::kTotal, stream>>>(
-        m.mapRT, m.mapRT, m.mapXT, g2);
+        m.mapRT, m.mapRT, m.mapXT, m.mapRT, g2);
   }
   WB200_CUDA(cudaGetLastError());
   logistic_finalize_kernel<<<(m.C + 7) / 8, 256, 0, stream>>>(
-      TH, m.ld, m.C, m.D, m.G32.ptr, m.Dpad, m.b.ptr, m.SP.ptr, G, LP);
+      TH, m.ld, m.C, m.D, m.G32.ptr, m.Dpad, m.b.ptr, m.SP.ptr,
+      static_cast<double>(m.Npad - m.N), G, LP);
   WB200_CUDA(cudaGetLastError());
 }
 

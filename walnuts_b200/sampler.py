@@ -248,8 +248,14 @@ class Session:
                              out["mcse"], out["mean"], out["variance"])
         return out
 
-    def draws(self, first: int, count: int) -> np.ndarray:
-        out = np.zeros((self.num_chains, count, self.num_params))
+    def draws(self, first: int, count: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Stored draws [chains][count][D] on the host (``out``: a caller-owned, e.g.
+        pinned, buffer).  After a free-running phase use ``chain_rows`` for the number of
+        valid rows of each chain."""
+        if out is None:
+            out = np.zeros((self.num_chains, count, self.num_params))
+        elif out.shape != (self.num_chains, count, self.num_params):
+            raise ValueError("out has the wrong shape")
         _ffi.session_get_draws(self._h, first, count, out)
         return out
 
