@@ -62,11 +62,13 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   p.ticket = &ticket; p.tparam = tp.data();
   Group<1> grp{};
   ChainScalars sc_shared{};  // stands in for the per-chain record in shared memory
+  DecisionCache decision_cache{};
   using Target = TargetT<1, kEmuK>;
   // warm-up launch
   p.n_iter = n_warmup; p.adapt = 1; p.draw_base = 0;
   {
     ChainRunner<Target, 1, kEmuK> r(p, grp, scratch.data(), sc_shared);
+    r.dc = &decision_cache;
     if (n_warmup > 0) r.run(0);
   }
   // freeze_kernel
@@ -81,6 +83,7 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   p.n_iter = n_sampling; p.adapt = 0; p.draw_base = n_warmup; p.im_out = nullptr;
   {
     ChainRunner<Target, 1, kEmuK> r(p, grp, scratch.data(), sc_shared);
+    r.dc = &decision_cache;
     if (n_sampling > 0) r.run(0);
   }
   for (int i = 0; i < total; ++i) {

@@ -79,6 +79,11 @@ struct ChainParams {
   double max_error;
   double mass_init_count, macro_target;
   double adam_target, adam_lr, adam_b1, adam_b2, adam_eps, adam_decay;
+  // adam_lr / pow(t, adam_decay) for t = 1 .. adam_tab_n: the decayed learning rate
+  // depends on the update count only, and pow is the longest link of the scalar chain
+  // every macro step of the adaptive phase waits for (null: computed on the spot)
+  const double* adam_tab;
+  int adam_tab_n;
   uint32_t seed, chain_offset;
   double* theta;        // [C][ld]
   double* inv_mass;     // [C][ld]  fixed metric used when adapt == 0
@@ -320,7 +325,9 @@ __device__ __noinline__ inline void adam_update(ChainScalars& sc, const ChainPar
   sc.adam_v = p.adam_b2 * sc.adam_v + (1 - p.adam_b2) * grad * grad;
   double m_hat = sc.adam_m / (1 - sc.adam_b1p);
   double v_hat = sc.adam_v / (1 - sc.adam_b2p);
-  double decayed = p.adam_lr / pow(sc.adam_t, p.adam_decay);
+  double decayed = (p.adam_tab != nullptr && sc.adam_t <= static_cast<double>(p.adam_tab_n))
+                       ? p.adam_tab[static_cast<int>(sc.adam_t) - 1]
+                       : p.adam_lr / pow(sc.adam_t, p.adam_decay);
   double denom = sqrt(v_hat) + p.adam_eps;
   sc.adam_x -= decayed * m_hat / denom;
 }
@@ -338,6 +345,16 @@ __device__ __forceinline__ int min_micro_steps(const ChainScalars& sc,
   return min_micro_steps(sc.mm_total, sc.mm_count, p);
 }
 
+// The scalar stream is stateless (Philox keyed by (chain, iteration, index)), so the
+// control warp can evaluate log(u) for the next 32 decision indices at once, one per
+// lane, instead of one Philox block + one log() on the critical path of every merge:
+// every other warp of the group waits at a barrier for that scalar chain.
+struct DecisionCache {
+  double logu[32];
+  uint32_t base, iter;  // covers indices [base, base + lanes) of iteration `iter`
+  uint32_t valid;
+};
+
 // combine<U> (walnuts.hpp:368-387): logW of the union and whether the new span's
 // selection wins; one uniform from the chain's scalar stream
 struct MergeResult { double logW; bool take_new; };
@@ -349,6 +366,19 @@ __device__ __noinline__ inline MergeResult merge_scalar(bool metropolis, double 
   const double u = philox_uniform(seed, gchain, iter, index);
   const double denom = metropolis ? logW_old : lw;
   return MergeResult{lw, log(u) < logW_new - denom};
+}
+
+// the same with log(u) already known
+__device__ __noinline__ inline MergeResult merge_scalar_logu(bool metropolis, double logW_old,
+                                                      double logW_new, double log_u) {
+  const double lw = log_sum_exp2(logW_old, logW_new);
+  const double denom = metropolis ? logW_old : lw;
+  return MergeResult{lw, log_u < logW_new - denom};
+}
+
+__device__ __noinline__ inline double log_uniform(uint32_t seed, uint32_t gchain, uint32_t iter,
+                                           uint32_t index) {
+  return log(philox_uniform(seed, gchain, iter, index));
 }
 
 __device__ __noinline__ inline bool direction_bit(uint32_t seed, uint32_t gchain, uint32_t iter,
@@ -382,6 +412,7 @@ struct ChainRunner {
   // read by others only after a barrier.  The few values every thread needs for
   // its own vector work are mirrored in registers (u_*), updated redundantly.
   ChainScalars& sc;
+  DecisionCache* dc = nullptr;  // shared memory, control warp only (null: no look-ahead)
   uint32_t u_iter, u_warm_iter;
   double u_est_w, u_mm_total, u_mm_count;
   unsigned long long evals;
@@ -549,8 +580,22 @@ struct ChainRunner {
                                                  bool& take_new, double& logW) {
     double r[2] = {0.0, 0.0};
     if (grp.ctl()) {
-      const MergeResult m =
-          merge_scalar(metropolis, logW_old, logW_new, p.seed, gchain, iter, index);
+      MergeResult m;
+      if (dc != nullptr) {
+        constexpr uint32_t kLanes = T >= 32 ? 32u : static_cast<uint32_t>(T);
+        if (!(dc->valid && dc->iter == iter && index - dc->base < kLanes)) {
+          __syncwarp();
+          if (static_cast<uint32_t>(grp.lane) < kLanes) {
+            dc->logu[grp.lane] = log_uniform(p.seed, gchain, iter, index + grp.lane);
+          }
+          __syncwarp();
+          if (grp.lane == 0) { dc->base = index; dc->iter = iter; dc->valid = 1; }
+          __syncwarp();
+        }
+        m = merge_scalar_logu(metropolis, logW_old, logW_new, dc->logu[index - dc->base]);
+      } else {
+        m = merge_scalar(metropolis, logW_old, logW_new, p.seed, gchain, iter, index);
+      }
       r[0] = m.take_new ? 1.0 : 0.0;
       r[1] = m.logW;
     }
@@ -839,6 +884,7 @@ __global__ void __launch_bounds__(CTA, MINB)
 walnuts_chain_kernel(const ChainParams p) {
   __shared__ double red_smem[group_smem_doubles<T>()];
   __shared__ ChainScalars sc_smem[CTA / T];
+  __shared__ DecisionCache dc_smem[CTA / T];
   __shared__ int next_chain;
   Group<T> grp;
   grp.lane = threadIdx.x & 31;
@@ -857,6 +903,9 @@ walnuts_chain_kernel(const ChainParams p) {
   }
   double* scr = p.scratch + static_cast<long long>(slot) * p.scratch_stride;
   ChainRunner<Target, T, K> runner(p, grp, scr, sc_smem[threadIdx.x / T]);
+  if (grp.tid == 0) dc_smem[threadIdx.x / T].valid = 0;
+  grp.sync();
+  runner.dc = &dc_smem[threadIdx.x / T];
   while (true) {
     int chain;
     if constexpr (T == 32) {

@@ -367,8 +367,25 @@ void launch_orbit(int kind, int D, int ld, int C, const double* tparam,
 
 }  // namespace wb200
 
+namespace wb200 {
+// adam.hpp:82: learning_rate / pow(t, decay), the same expression adam_update evaluates
+__global__ void adam_table_kernel(double* tab, int n, double lr, double decay) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tab[i] = lr / pow(static_cast<double>(i + 1), decay);
+}
+}  // namespace wb200
+
 wb200::ChainParams wb200_session::params(int n_iter, int adapt, bool store) {
   wb200::ChainParams p{};
+  if (adapt && adam_tab.count == 0) {
+    constexpr int kAdamTable = 1 << 16;  // updates per chain covered; beyond: pow on the spot
+    adam_tab.alloc(kAdamTable);
+    wb200::adam_table_kernel<<<(kAdamTable + 255) / 256, 256, 0, stream>>>(
+        adam_tab.ptr, kAdamTable, tuning.step_learning_rate, tuning.step_learn_rate_decay);
+    WB200_CUDA(cudaGetLastError());
+  }
+  p.adam_tab = adapt ? adam_tab.ptr : nullptr;
+  p.adam_tab_n = adapt ? static_cast<int>(adam_tab.count) : 0;
   p.C = C; p.D = D; p.ld = ld;
   p.n_iter = n_iter;
   p.adapt = adapt;
