@@ -306,12 +306,16 @@ def run_c4(args):
         "warmup_phase": {"ticks": cfgw["warmup_ticks"], "seconds": warm_s,
                          "grad_evals_per_sec": (c1["grad_evals"] - c0["grad_evals"]) / warm_s},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained,
-                     "unit": "TFLOP/s", "frac": achieved / sustained, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / sustained,
+                     # DRAM bytes of one batched evaluation at 8192 chains (GEMM 1 1.72 GB:
+                     # R^T written once; GEMM 2 1.75 GB: R^T read once), ncu --set full
+                     "traffic": 3.47e9 if C == 8192 else None,
+                     "traffic_source": "profiles/r1_ncu_gemm_logistic_final_c4.csv",
                      "peak_burst": burst, "peak_source": src,
                      "algorithmic_flops_per_eval": flops_alg,
                      "gradient_only_ms_per_batched_eval": grad_ms,
                      "gradient_only_tflops": C * flops_alg / (grad_ms * 1e-3) / 1e12,
-                     "kernel": "gemm_kmajor_kernel<128,1> + gemm_kmajor_kernel<256,2>"},
+                     "kernel": "gemm_kmajor_kernel<256,1> + gemm_kmajor_kernel<256,2>"},
         "e2e": {"value": e2e_evals / e2e_s, "unit": "grad_evals/s",
                 "h2d_bytes_per_step": int((X.nbytes + y.nbytes) / e2e_steps),
                 "d2h_bytes_per_step": int(host_draws.nbytes / e2e_steps),
@@ -572,7 +576,12 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-            "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / hbm_peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one timed launch (10
+            # transitions x 4096 chains) from the committed ncu --set full capture
+            "traffic": 3.55e9 if args.workload == "c2" and ips == 10 and C == 4096 else None,
+            "traffic_source": "profiles/r1_ncu_chain_kernel_final_c2.csv",
+            "peak_source": peak_src,
             "kernel": wl["kernel"],
             "algorithmic_bytes_per_eval": ALG_BYTES_PER_EVAL,
             "ms_per_launch": ms_per_launch,
