@@ -605,6 +605,10 @@ def run_ours(args):
 
 
 def main():
+    # NCCL announces its version on stdout at INFO/VERSION verbosity; stdout carries
+    # exactly one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
