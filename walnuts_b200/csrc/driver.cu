@@ -385,8 +385,14 @@ int walnutpie_sample_device(
     int warm_done = 0;
     DeviceBuffer<double> sums;
     sums.alloc(static_cast<size_t>(num_params) + 2);
+    // The lock-step engine idles finished chains until the slowest one has done its
+    // quota, so it gets the longest block that needs no controller decision.
+    auto block = [&](int done, int min_iter, int max_iter) {
+      if (s->tick && done < min_iter) return min_iter - done;
+      return std::min(stride, max_iter - done);
+    };
     while (warm_done < max_warmup_iter) {
-      const int n = std::min(stride, max_warmup_iter - warm_done);
+      const int n = block(warm_done, min_warmup_iter, max_warmup_iter);
       check(wb200_session_warmup(s, n, save_warmup ? 1 : 0, &e), e);
       if (save_warmup) {
         flush_pending();
@@ -407,7 +413,7 @@ int walnutpie_sample_device(
     // ---- sampling: R-hat of lp between blocks (sampler.hpp:132-151)
     int samp_done = 0;
     while (samp_done < max_sampling_iter) {
-      const int n = std::min(stride, max_sampling_iter - samp_done);
+      const int n = block(samp_done, min_sampling_iter, max_sampling_iter);
       check(wb200_session_sample(s, n, 1, &e), e);
       flush_pending();
       mark_block(saved_warm + samp_done + n);
