@@ -605,10 +605,9 @@ def run_ours(args):
 
 
 def main():
-    # NCCL announces its version on stdout at INFO/VERSION verbosity; stdout carries
-    # exactly one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # NCCL writes its version banner and warnings to stdout unless told otherwise;
+    # stdout carries exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
