@@ -567,7 +567,7 @@ struct TickRunner {
 
 #if defined(__CUDACC__)
 template <int T, int K, int CTA>
-__global__ void __launch_bounds__(CTA) walnuts_tick_kernel(const TickParams tp) {
+__global__ void __launch_bounds__(CTA, (CTA <= 128 ? 512 / CTA : 1)) walnuts_tick_kernel(const TickParams tp) {
   __shared__ double red_smem[group_smem_doubles<T>()];
   Group<T> grp;
   grp.lane = threadIdx.x & 31;
