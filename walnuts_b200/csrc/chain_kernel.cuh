@@ -637,6 +637,7 @@ struct ChainRunner {
           }
         }
         double r[1] = {0.0};
+        grp.sync();  // thread 0's Adam updates of the previous transition are visible
         if (grp.ctl()) r[0] = exp_noinline(sc.adam_x);  // Adam state: thread 0 writes it
         grp.bcast(r);
         step = r[0];
