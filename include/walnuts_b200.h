@@ -42,7 +42,18 @@ typedef void (*PRINT_CALLBACK)(const char* msg, size_t len, bool bad);
  * kind 2  Neal's funnel (x0 ~ N(0,9), x_i | x0 ~ N(0, exp(x0)))
  * kind 3  Bayesian logistic regression, data0 = X[N][D] row-major host fp64,
  *         data1 = y[N] host fp64 in {0,1}, prior N(0, I)
+ * kind 4  the caller's own density, batched on the device: data0 = a
+ *         WB200_BATCH_LOGP_GRAD function, data1 = its `data` argument.  This is
+ *         LOGP_CFUNC (walnutpy.cpp:127-130) for a whole batch of chains: once per
+ *         lock-step tick the sampler posts the positions of all chains and the
+ *         function ENQUEUES, on the CUDA stream it is given, work that fills
+ *         grad and lp.  Everything is device memory: theta, grad [num_chains][ld]
+ *         fp64 row-major (columns >= num_params are padding), lp [num_chains].
+ *         Return 0, or non-zero to abort the run with a runtime error.
  */
+typedef int (*WB200_BATCH_LOGP_GRAD)(size_t num_chains, size_t num_params, size_t ld,
+                                     const double* theta, double* grad, double* lp,
+                                     void* cuda_stream, void* data);
 typedef struct {
   int kind;
   int D;

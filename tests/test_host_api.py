@@ -142,3 +142,29 @@ def test_product_never_imports_the_oracle():
     for p in (ROOT / "walnuts_b200").rglob("*"):
         if p.suffix in {".py", ".cu", ".cuh", ".hpp", ".cpp", ".h"} or p.name == "Makefile":
             assert not uses.search(p.read_text()), p
+
+
+def test_batch_callback_descriptor():
+    """WalnutModelDesc kind 4 carries the function pointer of the batched density; the
+    Python trampoline turns exceptions into a non-zero return and keeps them for the
+    caller (no GPU needed to check the plumbing)."""
+    import ctypes
+    from walnuts_b200 import models
+
+    seen = []
+
+    def fn(C, D, ld, theta, grad, lp, stream):
+        seen.append((C, D, ld))
+        if C == 13:
+            raise ValueError("unlucky")
+
+    m = models.batch_callback(7, fn)
+    d = m.desc()
+    assert d.kind == 4 and d.D == 7 and d.data0
+    f = ctypes.cast(d.data0, models.BATCH_LOGP_GRAD)
+    assert f(3, 7, 8, None, None, None, None, None) == 0
+    assert f(13, 7, 8, None, None, None, None, None) == 1
+    assert seen == [(3, 7, 8), (13, 7, 8)]
+    assert isinstance(m.errors[0], ValueError)
+    iface = models._DevicePointer(4096, (2, 8)).__cuda_array_interface__
+    assert iface["data"] == (4096, False) and iface["typestr"] == "<f8"

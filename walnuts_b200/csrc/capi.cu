@@ -141,7 +141,8 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
       WB200_CUDA(cudaMemsetAsync(s->tparam.ptr, 0, s->ld * 8, s->stream));
       WB200_CUDA(cudaMemcpyAsync(s->tparam.ptr, prec, s->D * 8,
                                  cudaMemcpyHostToDevice, s->stream));
-    } else if (s->kind != kStdNormal && s->kind != kFunnel && s->kind != kLogistic) {
+    } else if (s->kind != kStdNormal && s->kind != kFunnel && s->kind != kLogistic &&
+               s->kind != kBatchCallback) {
       throw std::invalid_argument("unsupported model kind for the device sampler");
     }
     if (s->kind == kFunnel && s->D < 2) {
@@ -150,7 +151,8 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
     // engine: chain-resident kernel for element-wise targets, lock-step ticks where the
     // gradient is a cross-chain batched contraction (or when forced, for testing)
     const char* eng = std::getenv("WB200_ENGINE");
-    const bool use_tick = s->kind == kLogistic || (eng && std::string(eng) == "tick");
+    const bool use_tick = s->kind == kLogistic || s->kind == kBatchCallback ||
+                          (eng && std::string(eng) == "tick");
     if (use_tick) {
       tick_create(*s, *model);
       WB200_CUDA(cudaStreamSynchronize(s->stream));

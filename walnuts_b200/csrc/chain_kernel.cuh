@@ -46,7 +46,7 @@ namespace wb200 {
 constexpr int kMaxDepth = 12;  // max_trajectory_doublings supported on device
 
 enum TargetKind : int { kStdNormal = 0, kDiagGaussian = 1, kFunnel = 2,
-                        kLogistic = 3 };
+                        kLogistic = 3, kBatchCallback = 4 };
 
 // persistent per-chain scalars (SoA would not help: one group reads one record)
 struct ChainScalars {

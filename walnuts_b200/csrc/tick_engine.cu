@@ -20,6 +20,8 @@ struct TickEngine {
   int* active_host = nullptr;  // pinned
   long long vec_stride = 0;
   LogisticGrad* logistic = nullptr;
+  WB200_BATCH_LOGP_GRAD batch_fn = nullptr;  // kind 4: the caller's batched density
+  void* batch_data = nullptr;
   unsigned long long ticks = 0, grad_batches = 0;
   ~TickEngine() {
     delete logistic;
@@ -327,11 +329,31 @@ static TickParams tick_params(wb200_session& s, int n_iter, int adapt, bool stor
       elementwise_grad_kernel<FunnelTarget, T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(tp); \
   } while (0)
 
+// columns D .. ld of the gradient rows are padding the kernels expect to be zero
+__global__ void zero_padding_kernel(double* G, int C, int D, int ld) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    for (int d = D; d < ld; ++d) G[static_cast<long long>(c) * ld + d] = 0.0;
+  }
+}
+
 static void tick_gradient(wb200_session& s, const TickParams& tp) {
   TickEngine& e = *s.tick;
   if (s.kind == kLogistic) {
     e.logistic->evaluate(e.TH.ptr, e.G.ptr, e.LP.ptr, s.stream);
     s.launches += e.logistic->kernels_per_eval();
+  } else if (s.kind == kBatchCallback) {
+    const int rc = e.batch_fn(static_cast<size_t>(s.C), static_cast<size_t>(s.D),
+                              static_cast<size_t>(s.ld), e.TH.ptr, e.G.ptr, e.LP.ptr,
+                              static_cast<void*>(s.stream), e.batch_data);
+    if (rc != 0) {
+      throw std::runtime_error("the batched log density callback failed with code " +
+                               std::to_string(rc));
+    }
+    if (s.ld != s.D) {
+      zero_padding_kernel<<<(s.C + 255) / 256, 256, 0, s.stream>>>(e.G.ptr, s.C, s.D, s.ld);
+      WB200_CUDA(cudaGetLastError());
+    }
   } else {
     const int grid = (s.C + s.shape.chains_per_cta - 1) / s.shape.chains_per_cta;
     WB200_TICK_SHAPE(s.shape, WB200_EW_GRAD);
@@ -364,6 +386,11 @@ void tick_create(wb200_session& s, const WalnutModelDesc& model) {
   WB200_CUDA(cudaMemsetAsync(e.G.ptr, 0, CL * 8, s.stream));
   WB200_CUDA(cudaMemsetAsync(e.vecs.ptr, 0, e.vecs.count * 8, s.stream));
   WB200_CUDA(cudaMemsetAsync(e.ts.ptr, 0, s.C * sizeof(TickState), s.stream));
+  if (s.kind == kBatchCallback) {
+    if (!model.data0) throw std::invalid_argument("kind 4 needs data0 = the density function");
+    e.batch_fn = reinterpret_cast<WB200_BATCH_LOGP_GRAD>(const_cast<void*>(model.data0));
+    e.batch_data = const_cast<void*>(model.data1);
+  }
   if (s.kind == kLogistic) {
     if (!model.data0 || !model.data1 || model.N < 1) {
       throw std::invalid_argument("logistic needs data0 = X[N][D], data1 = y[N], N >= 1");

@@ -14,7 +14,13 @@ import numpy as np
 
 from ._ffi import WalnutModelDesc
 
-KINDS = {"std_normal": 0, "diag_gaussian": 1, "funnel": 2, "logistic": 3}
+KINDS = {"std_normal": 0, "diag_gaussian": 1, "funnel": 2, "logistic": 3, "batch_callback": 4}
+
+# WB200_BATCH_LOGP_GRAD (include/walnuts_b200.h): num_chains, num_params, ld, theta, grad,
+# lp (device pointers), cuda_stream, data -> 0 on success
+BATCH_LOGP_GRAD = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t,
+                                   ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
 
 
 @dataclass
@@ -24,6 +30,8 @@ class DeviceModel:
     precision: Optional[np.ndarray] = None   # diag_gaussian: 1 / sigma_d^2
     X: Optional[np.ndarray] = None           # logistic: [N][D]
     y: Optional[np.ndarray] = None           # logistic: [N]
+    callback: Optional[object] = None        # batch_callback: a BATCH_LOGP_GRAD instance
+    errors: list = field(default_factory=list, repr=False)  # exceptions raised inside it
     _keep: list = field(default_factory=list, repr=False)
 
     def desc(self) -> WalnutModelDesc:
@@ -42,6 +50,8 @@ class DeviceModel:
             d.N = X.shape[0]
             d.data0 = X.ctypes.data
             d.data1 = y.ctypes.data
+        elif self.kind == "batch_callback":
+            d.data0 = ctypes.cast(self.callback, ctypes.c_void_p).value
         return d
 
 
@@ -78,3 +88,63 @@ def logistic(X, y) -> DeviceModel:
     if X.ndim != 2 or y.shape != (X.shape[0],):
         raise ValueError("X must be [N][D] and y [N]")
     return DeviceModel("logistic", X.shape[1], X=X, y=y)
+
+
+def batch_callback(num_params: int, fn) -> DeviceModel:
+    """The caller's own density, batched on the device (WalnutModelDesc kind 4).
+
+    ``fn(num_chains, num_params, ld, theta_ptr, grad_ptr, lp_ptr, stream_ptr)`` is called
+    once per lock-step tick with raw device pointers (fp64; ``theta`` / ``grad`` are
+    ``[num_chains][ld]`` row-major, ``lp`` is ``[num_chains]``) and the CUDA stream on which
+    it must enqueue the work that fills ``grad`` and ``lp``.  An exception raised inside
+    ``fn`` aborts the run and is re-raised by the sampler call."""
+    model = DeviceModel("batch_callback", int(num_params))
+
+    def trampoline(C, D, ld, theta, grad, lp, stream, _data):
+        try:
+            fn(C, D, ld, theta, grad, lp, stream)
+            return 0
+        except BaseException as exc:  # must not propagate through the C frames
+            model.errors.append(exc)
+            return 1
+
+    model.callback = BATCH_LOGP_GRAD(trampoline)
+    return model
+
+
+class _DevicePointer:
+    """A raw device allocation as ``__cuda_array_interface__`` (fp64, C order)."""
+
+    def __init__(self, ptr: int, shape: tuple):
+        self.__cuda_array_interface__ = {
+            "shape": shape, "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+            "strides": None}
+
+
+def torch_density(num_params: int, logp_fn, grad_fn=None) -> DeviceModel:
+    """A density written with PyTorch, evaluated for all chains at once on the GPU.
+
+    ``logp_fn(theta)`` maps a float64 CUDA tensor ``[num_chains, num_params]`` to the log
+    densities ``[num_chains]``; the gradient comes from autograd unless ``grad_fn(theta)``
+    -> ``(logp, grad)`` is given.  This is what ``walnuts_pyfunc``'s Python ``logp``
+    callback (pyfunc.py:45-83) becomes when the chains live on the device."""
+    import torch
+
+    def fn(C, D, ld, theta_ptr, grad_ptr, lp_ptr, stream_ptr):
+        stream = torch.cuda.ExternalStream(int(stream_ptr or 0))
+        with torch.cuda.stream(stream):
+            theta = torch.as_tensor(_DevicePointer(theta_ptr, (C, ld)), device="cuda")[:, :D]
+            grad = torch.as_tensor(_DevicePointer(grad_ptr, (C, ld)), device="cuda")
+            lp = torch.as_tensor(_DevicePointer(lp_ptr, (C,)), device="cuda")
+            if grad_fn is not None:
+                with torch.no_grad():
+                    value, g = grad_fn(theta)
+            else:
+                x = theta.detach().clone().requires_grad_(True)
+                with torch.enable_grad():
+                    value = logp_fn(x)
+                    (g,) = torch.autograd.grad(value.sum(), x)
+            grad[:, :D].copy_(g)
+            lp.copy_(value.detach().reshape(C))
+
+    return batch_callback(num_params, fn)

@@ -8,6 +8,7 @@ chains kept in HBM) for callers that do not want the draws copied back.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from typing import Optional
 
@@ -43,6 +44,21 @@ def make_tuning(**kw) -> _ffi.WalnutTuning:
             raise TypeError(f"unknown tuning argument {k!r}")
         setattr(t, k, v)
     return t
+
+
+@contextlib.contextmanager
+def _reraise_callback_errors(model):
+    errors = getattr(model, "errors", None)
+    if errors:
+        errors.clear()
+    try:
+        yield
+    except RuntimeError as failure:
+        if errors:
+            exc = errors.pop(0)
+            errors.clear()
+            raise exc from failure
+        raise
 
 
 def walnuts_device(
@@ -125,17 +141,18 @@ def walnuts_device(
         inv_metric_out = np.zeros((num_chains, num_params), dtype=np.float64)
 
     desc = logp.desc()
-    _ffi._ffi_sample_device(
-        ctypes.byref(desc), num_params, inits, num_chains, seed, id, init_radius,
-        init_inv_metric, min_warmup_iter, max_warmup_iter, min_sampling_iter,
-        max_sampling_iter, max_trajectory_doublings, max_step_halvings,
-        min_micro_steps, max_hamiltonian_error, step_size_converge_tol,
-        mass_converge_tol, rhat_converge_tol, mass_init_count,
-        mass_additive_smoothing, max_macro_steps_target, step_size_init,
-        step_accept_rate_target, step_learning_rate, step_gradient_decay,
-        step_sq_gradient_decay, step_stabilization, step_learn_rate_decay,
-        save_warmup, out, out.size, lengths_out, stepsize_out, inv_metric_out,
-        refresh, _ffi.print_callback)
+    with _reraise_callback_errors(logp):
+        _ffi._ffi_sample_device(
+            ctypes.byref(desc), num_params, inits, num_chains, seed, id, init_radius,
+            init_inv_metric, min_warmup_iter, max_warmup_iter, min_sampling_iter,
+            max_sampling_iter, max_trajectory_doublings, max_step_halvings,
+            min_micro_steps, max_hamiltonian_error, step_size_converge_tol,
+            mass_converge_tol, rhat_converge_tol, mass_init_count,
+            mass_additive_smoothing, max_macro_steps_target, step_size_init,
+            step_accept_rate_target, step_learning_rate, step_gradient_decay,
+            step_sq_gradient_decay, step_stabilization, step_learn_rate_decay,
+            save_warmup, out, out.size, lengths_out, stepsize_out, inv_metric_out,
+            refresh, _ffi.print_callback)
 
     outputs = []
     for i in range(num_chains):
@@ -190,26 +207,30 @@ class Session:
     def _c(a):
         return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
-    def init(self, positions=None, init_radius: float = 2.0, mass=None, steps=None):
-        _ffi.session_init(self._h, self._c(positions), float(init_radius),
-                          self._c(mass), self._c(steps))
+    def _run(self, fn, *args):
+        """Calls that evaluate the model: an exception raised inside a batch-callback
+        density comes back as the library's runtime error and is re-raised as itself."""
+        with _reraise_callback_errors(self.model):
+            fn(self._h, *args)
         return self
+
+    def init(self, positions=None, init_radius: float = 2.0, mass=None, steps=None):
+        return self._run(_ffi.session_init, self._c(positions), float(init_radius),
+                         self._c(mass), self._c(steps))
 
     def reserve(self, capacity: int, trace: bool = False):
         _ffi.session_reserve(self._h, int(capacity), int(trace))
         return self
 
     def warmup(self, n_iter: int, store: bool = False):
-        _ffi.session_warmup(self._h, int(n_iter), int(store))
-        return self
+        return self._run(_ffi.session_warmup, int(n_iter), int(store))
 
     def freeze(self):
         _ffi.session_freeze(self._h)
         return self
 
     def sample(self, n_iter: int, store: bool = True):
-        _ffi.session_sample(self._h, int(n_iter), int(store))
-        return self
+        return self._run(_ffi.session_sample, int(n_iter), int(store))
 
     def sync(self):
         _ffi.session_sync(self._h)
@@ -218,14 +239,12 @@ class Session:
     def sample_ticks(self, n_ticks: int, store: bool = True):
         """Lock-step sessions: exactly ``n_ticks`` ticks (one batched gradient each);
         chains complete as many transitions as fit (ragged draw counts)."""
-        _ffi.session_sample_ticks(self._h, int(n_ticks), int(store))
-        return self
+        return self._run(_ffi.session_sample_ticks, int(n_ticks), int(store))
 
     def warmup_ticks(self, n_ticks: int, store: bool = False):
         """Lock-step sessions: adaptive warm-up for exactly ``n_ticks`` ticks; every chain
         adapts over as many transitions as fit.  ``freeze`` abandons those in flight."""
-        _ffi.session_warmup_ticks(self._h, int(n_ticks), int(store))
-        return self
+        return self._run(_ffi.session_warmup_ticks, int(n_ticks), int(store))
 
     def chain_rows(self) -> np.ndarray:
         rows = np.zeros(self.num_chains, np.int64)
