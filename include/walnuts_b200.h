@@ -108,7 +108,8 @@ int walnutpie_sample_device(
 
 /* walnutpie_sample_cfunc / walnutpie_sample_bridgestan (walnutpy.cpp:134, :227):
  * exported for link compatibility; a host callback cannot feed a device batch,
- * so both fail with a `generic` error that names walnutpie_sample_device. */
+ * so it fails with a `generic` error that names walnutpie_sample_device and the
+ * batched device callback (WalnutModelDesc kind 4), its device-side counterpart. */
 int walnutpie_sample_cfunc(
     LOGP_CFUNC logp_c, void* data, int num_params, const double* inits,
     size_t num_chains, unsigned int seed, unsigned int id, double init_radius,

@@ -616,3 +616,47 @@ def test_exceptions_inside_a_batched_density_surface_as_themselves(wb):
         with pytest.raises(KeyError, match="boom"):
             s.init(init_radius=1.0)
             s.warmup(5)
+
+
+# ---- BASELINE.json sizes ---------------------------------------------------------------
+def test_c4_size_gradient_operator_matches_oracle(wb, oracle):
+    """The tensor-core gradient at the full c4 shape (N = 100 000 data rows: 391 column
+    tiles with 96 padded rows, D = 512, 8192 chains: 64 row tiles) against the fp64 CPU
+    density for chains spread over the batch."""
+    import sys
+    sys.path.insert(0, ".")
+    import bench
+    from walnuts_b200.sampler import logistic_logp_grad
+    N, D, C = 100_000, 512, 8192
+    X, y = bench.logistic_data(N, D)
+    theta = np.random.default_rng(4).normal(size=(C, D)) / np.sqrt(D)
+    lp, g, _ = logistic_logp_grad(X, y, theta)
+    assert np.all(np.isfinite(lp)) and np.all(np.isfinite(g))
+    t = Target("logistic", D, X=X, y=y)
+    for c in (0, 127, 128, 4095, 4096, C - 1):
+        olp, og = oracle.logp_grad(t, theta[c])
+        assert abs(lp[c] - olp) <= 1e-5 * abs(olp)
+        assert np.max(np.abs(g[c] - og)) <= 3e-3 * np.max(np.abs(og))
+
+
+def test_c2_size_posterior_and_sharding(wb):
+    """c2 at full size (D = 1000, cond 1e4, 4096 chains): variances within 10 % after a
+    short run, and the last 64 chains equal those of a 64-chain session with the same
+    global chain ids (what another rank would hold)."""
+    D, C = 1000, 4096
+    model = wb.models.ill_conditioned_gaussian(D, 1e4)
+    tune = dict(max_trajectory_doublings=10, max_step_halvings=5)
+    with wb.Session(model, C, seed=11, **tune) as s:
+        s.init(init_radius=2.0)
+        s.reserve(40)
+        s.warmup(150).freeze().sample(40).sync()
+        summ = s.summary(0, 40)
+        tail = s.draws(0, 40)[C - 64:]
+    var = 1e4 ** (np.arange(D) / (D - 1))
+    assert np.max(np.abs(summ["variance"] / var - 1)) < 0.10
+    assert np.max(np.abs(summ["mean"]) / np.sqrt(var)) < 0.05
+    with wb.Session(model, 64, seed=11, chain_offset=C - 64, **tune) as s:
+        s.init(init_radius=2.0)
+        s.reserve(40)
+        s.warmup(150).freeze().sample(40).sync()
+        np.testing.assert_array_equal(s.draws(0, 40), tail)

@@ -544,8 +544,9 @@ int walnutpie_sample_cfunc(
   return catch_exceptions(err, [&] {
     throw std::runtime_error(
         "walnuts_b200 runs device-resident models only: a host LOGP_CFUNC cannot "
-        "feed a GPU batch. Describe the model with WalnutModelDesc and call "
-        "walnutpie_sample_device (same trailing arguments).");
+        "feed a GPU batch. Describe the model with WalnutModelDesc (a built-in kind, or "
+        "kind 4 with a WB200_BATCH_LOGP_GRAD that evaluates all chains on the device) "
+        "and call walnutpie_sample_device (same trailing arguments).");
   });
 }
 
