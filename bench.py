@@ -67,6 +67,30 @@ C4 = dict(N=100_000, D=512, chains=8192, warmup_ticks=3000, ticks_per_step=100,
           max_doublings=8, max_halvings=5)
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: keep a private copy of fd 1 for it and point
+    fd 1 at stderr, so that banners of native libraries (NCCL prints its version to stdout
+    at NCCL_DEBUG=VERSION) cannot get in front of it."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -331,7 +355,7 @@ def run_c4(args):
             "seconds": cpu_s}),
         "clocks": clocks.summary(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
@@ -401,7 +425,7 @@ def run_reference_arm(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------
@@ -598,16 +622,14 @@ def run_ours(args):
         },
         "clocks": clock_summary,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
-    # NCCL writes its version banner and warnings to stdout unless told otherwise;
-    # stdout carries exactly one JSON line
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
