@@ -188,6 +188,9 @@ struct TickRunner {
     double* g_row = tp.G + static_cast<long long>(chain) * ld;
     unsigned long long evals = 0;
     bool request = false;  // a new position has been posted
+    // the live registers (th, rho, g) equal the stored macro-step start state (THS, RHOS,
+    // GS) and im is loaded: the next macro step can start without reading them back
+    bool live_is_start = false;
 
     while (!request) {
       if (st.pc == PC_START_TRANSITION) {
@@ -233,6 +236,7 @@ struct TickRunner {
         V::store(vv(TV_A_SEL), ld, tid, th);    V::store(vv(TV_A_SEL_G), ld, tid, g);
         V::store(vv(TV_THS), ld, tid, th); V::store(vv(TV_RHOS), ld, tid, rho);
         V::store(vv(TV_GS), ld, tid, g);
+        live_is_start = true;
         st.H_bk = H0; st.H_fw = H0; st.logW = H0; st.lp_sel = lp0;
         st.regs_dir = 0; st.first_ext = 1; st.sctr = 0;
         st.depth = 0;  // incremented by the doubling step below
@@ -397,6 +401,7 @@ struct TickRunner {
             V::store(vv(TV_THS), ld, tid, th);
             V::store(vv(TV_RHOS), ld, tid, rho);
             V::store(vv(TV_GS), ld, tid, g);
+            live_is_start = true;
             st.Hs = st.Hn;
             st.lps = st.lpn;
             st.leaf_i += 1;
@@ -448,6 +453,7 @@ struct TickRunner {
             copy_vec(TV_THS, b);
             copy_vec(TV_RHOS, b + 1);
             copy_vec(TV_GS, b + 2);
+            live_is_start = false;
           }
           st.first_ext = 0;
           st.Hs = fwd ? st.H_fw : st.H_bk;
@@ -471,16 +477,18 @@ struct TickRunner {
         st.cur_n = st.n;
         st.cur_h = st.h;
         st.micro_done = 0;
-        V::load(vv(TV_THS), ld, tid, th);
-        V::load(vv(TV_RHOS), ld, tid, rho);
-        V::load(vv(TV_GS), ld, tid, g);
-        V::load(p.adapt ? vv(TV_IM) : p.inv_mass + static_cast<long long>(chain) * ld,
-                ld, tid, im);
+        if (!live_is_start) {
+          V::load(vv(TV_THS), ld, tid, th);
+          V::load(vv(TV_RHOS), ld, tid, rho);
+          V::load(vv(TV_GS), ld, tid, g);
+          V::load(p.adapt ? vv(TV_IM) : p.inv_mass + static_cast<long long>(chain) * ld,
+                  ld, tid, im);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
+          for (int k = 0; k < K; ++k) {
 #pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            if (2 * (tid + k * T) + v >= p.D) im[k][v] = 1.0;
+            for (int v = 0; v < 2; ++v) {
+              if (2 * (tid + k * T) + v >= p.D) im[k][v] = 1.0;
+            }
           }
         }
         begin_micro_step(st.cur_h, th_row);
