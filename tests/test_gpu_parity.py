@@ -176,6 +176,46 @@ def test_seeded_trajectories_match_oracle(wb, oracle, kind, D, C, over, nw, ns):
     assert full >= (C + 1) // 2
 
 
+@pytest.mark.parametrize("engine", ["chain", "tick"])
+@pytest.mark.parametrize("kind,D,scale,step0", [
+    ("std_normal", 6, 1e100, 0.5), ("diag_gaussian", 4, 1e140, 1.0),
+    ("funnel", 5, 30.0, 2.0), ("funnel", 5, 300.0, 2.0), ("std_normal", 6, 50.0, 1e6)])
+def test_extreme_inputs_take_the_reference_decisions(wb, oracle, monkeypatch, engine, kind, D,
+                                                     scale, step0):
+    """Energies of 1e200, rejected extensions at every doubling, exhausted halving ladders:
+    both engines make the reference's decisions (the same cases run bit for bit against
+    the oracle in tests/test_host_emulation.py)."""
+    if engine == "tick":
+        monkeypatch.setenv("WB200_ENGINE", "tick")
+    rng = np.random.default_rng(1)
+    prec = rng.uniform(0.5, 2.0, D) if kind == "diag_gaussian" else None
+    model = {"std_normal": lambda: wb.models.std_normal(D),
+             "diag_gaussian": lambda: wb.models.diag_gaussian(1.0 / prec),
+             "funnel": lambda: wb.models.funnel(D)}[kind]()
+    target = Target(kind, D, prec=prec)
+    over = dict(max_trajectory_doublings=6, max_step_halvings=4)
+    cfg = default_config(**over)
+    th0, m0 = rng.normal(size=D) * scale, np.ones(D)
+    C = 3
+    with wb.Session(model, C, seed=5, **over) as s:
+        s.init(positions=np.tile(th0, (C, 1)), mass=np.tile(m0, (C, 1)),
+               steps=np.full(C, step0))
+        s.reserve(16, trace=True)
+        s.warmup(8, store=True).freeze().sample(8).sync()
+        draws, tr, st = s.draws(0, 16), s.trace(0, 16), s.state()
+    assert np.all(np.isfinite(draws))
+    for c in range(C):
+        o = oracle.run_chain(target, cfg, 5, c, th0, m0, step0, 8, 8, rng_policy=1)
+        np.testing.assert_allclose(draws[c], np.concatenate([o["warmup_draws"], o["draws"]]),
+                                   rtol=1e-9)
+        np.testing.assert_array_equal(tr["depth"][c],
+                                      np.concatenate([o["warmup_depth"], o["depth"]]))
+        # the lock-step engine carries the gradient of the selected draw instead of
+        # re-evaluating it at the start of each of the 16 transitions (DESIGN.md section 1)
+        assert int(st["grad_evals"][c]) == o["grad_evals"] - (16 if engine == "tick" else 0)
+        assert st["step"][c] == pytest.approx(o["step"], rel=1e-9)
+
+
 def test_fixed_parameter_sampler_matches_oracle_to_rounding(wb, oracle):
     """With frozen tuning, Gaussian dynamics are purely element-wise; the only
     differences from the oracle are the last bits of the Box-Muller normals (CUDA

@@ -57,6 +57,36 @@ def test_device_state_machine_equals_oracle_bitwise(emu, oracle, engine, kind, D
         assert e["grad_evals"] == o["grad_evals"]
 
 
+# Extreme starting points and step sizes: energies of 1e200, rejected extensions at every
+# doubling, halving ladders that run out.  The device logic must make the same decisions
+# as the reference's (the chain stays put, same gradient count, same adaptation state).
+EDGE_CASES = [
+    ("std_normal", 6, 1e100, 0.5),
+    ("diag_gaussian", 4, 1e140, 1.0),
+    ("funnel", 5, 30.0, 2.0),
+    ("funnel", 5, 300.0, 2.0),
+    ("std_normal", 6, 50.0, 1e6),
+]
+
+
+@pytest.mark.parametrize("engine", ["chain", "tick"])
+@pytest.mark.parametrize("kind,D,scale,step0", EDGE_CASES)
+def test_extreme_inputs_take_the_reference_decisions(emu, oracle, engine, kind, D, scale, step0):
+    rng = np.random.default_rng(1)
+    prec = rng.uniform(0.5, 2.0, D) if kind == "diag_gaussian" else None
+    target = Target(kind, D, prec=prec)
+    cfg = default_config(max_trajectory_doublings=6, max_step_halvings=4)
+    th0, m0 = rng.normal(size=D) * scale, np.ones(D)
+    e = host_emu.run_chain(emu, kind, D, prec, cfg, 5, 0, th0, m0, step0, 8, 8, engine=engine)
+    o = oracle.run_chain(target, cfg, 5, 0, th0, m0, step0, 8, 8, rng_policy=1)
+    np.testing.assert_array_equal(e["draws"], np.concatenate([o["warmup_draws"], o["draws"]]))
+    np.testing.assert_array_equal(e["lp"], np.concatenate([o["warmup_lp"], o["lp"]]))
+    np.testing.assert_array_equal(e["depth"], np.concatenate([o["warmup_depth"], o["depth"]]))
+    np.testing.assert_array_equal(e["inv_mass"], o["inv_mass"])
+    assert e["step"] == o["step"] and e["grad_evals"] == o["grad_evals"]
+    assert np.all(np.isfinite(e["draws"]))
+
+
 FREE_CASES = [
     ("std_normal", 10, dict(), 0.4),
     ("diag_gaussian", 12, dict(max_trajectory_doublings=8), 0.7),
