@@ -89,6 +89,19 @@ def test_signature_matches_walnuts_pyfunc(wb):
     (dict(min_micro_steps=0), "min_micro_steps must be in"),
     (dict(mass_init_count=float("inf")), "mass_init_count must be finite and > 0"),
     (dict(step_size_init=-1.0), "step size must be finite and > 0"),
+    # config.hpp:675-808 (validate.hpp:91-285), one per warm-up knob
+    (dict(step_size_converge_tol=0.0), "step_size_converge_tol must be finite and > 0"),
+    (dict(mass_converge_tol=float("nan")), "mass_converge_tol must be finite and > 0"),
+    (dict(mass_additive_smoothing=-1e-3), "mass_additive_smoothing must be finite and > 0"),
+    (dict(max_macro_steps_target=0.0), "max_macro_steps_target must be finite and > 0"),
+    (dict(step_learning_rate=float("inf")), "step_learning_rate must be finite and > 0"),
+    (dict(step_gradient_decay=1.0), "step_gradient_decay must be in \\(0, 1\\)"),
+    (dict(step_sq_gradient_decay=-0.1), "step_sq_gradient_decay must be in \\(0, 1\\)"),
+    (dict(step_stabilization=0.0), "step_stabilization must be finite and > 0"),
+    (dict(step_learn_rate_decay=1.5), "step_learn_rate_decay must be in \\(0, 1\\)"),
+    (dict(max_trajectory_doublings=0), "max_nuts_depth must be in"),
+    (dict(max_step_halvings=-1), "max_step_halvings must be in"),
+    (dict(min_warmup_iter=-1), "iteration counts must be non-negative"),
 ])
 def test_config_errors_are_value_errors_with_reference_text(wb, kw, msg):
     """Validation fires before any device work, so this runs without a GPU."""
