@@ -323,6 +323,32 @@ def test_device_summaries_on_reference_golden_vectors(wb):
         wb.ess([np.array([[1.0, 2.0], [3.0, 4.0]])])
 
 
+def test_device_summaries_on_long_and_ragged_chains(wb, oracle):
+    """Chains beyond the shared-memory tile of the autocovariance kernel (3200 draws) and
+    of different lengths, against the oracle (summary.hpp:594-769)."""
+    rng = np.random.default_rng(12)
+    chains = []
+    for n, phi in ((5000, 0.9), (4100, 0.5), (3600, -0.3)):
+        x = np.zeros((n, 3))
+        e = rng.normal(size=(n, 3))
+        for i in range(1, n):
+            x[i] = phi * x[i - 1] + e[i]
+        chains.append(x)
+    np.testing.assert_allclose(wb.ess(chains), oracle.ess(chains), rtol=1e-8)
+    np.testing.assert_allclose(wb.r_hat(chains), oracle.r_hat(chains), rtol=1e-10)
+    np.testing.assert_allclose(wb.mcse(chains), oracle.mcse(chains), rtol=1e-8)
+
+
+def test_device_summary_errors_match_the_reference(wb):
+    """summary_test.cpp:780-806, :1019-1035 through the host-buffer entry points."""
+    with pytest.raises(ValueError, match="at least two chains"):
+        wb.r_hat([np.arange(10.0).reshape(5, 2)])
+    with pytest.raises(ValueError, match="at least 3 draws"):
+        wb.r_hat([np.ones((2, 2)), np.ones((3, 2))])
+    with pytest.raises(ValueError, match="at least 3 draws"):
+        wb.ess([np.array([[1.0, 2.0], [3.0, 4.0]])])
+
+
 # ---- the reference's behavioural tests through the drop-in entry point -------
 @pytest.mark.parametrize("MIN,MAX", [(10, 12), (77, 77), (10, 30)])
 def test_warmup_requested_iter(wb, MIN, MAX):  # python/tests/test_pyfunc.py:38-50

@@ -103,6 +103,29 @@ __global__ void acov_kernel(SummaryView v, const double* mu, int lag0, int nlag,
   }
 }
 
+// The same for chains too long for the shared-memory tile: operands come straight from
+// global memory (L1 / L2 serve the re-reads across lags).
+template <int TILE>
+__global__ void acov_global_kernel(SummaryView v, const double* mu, int lag0, int nlag,
+                                   double* acc) {
+  const int k = blockIdx.y;
+  const int d0 = blockIdx.x * TILE;
+  const long long n = v.len[k];
+  const double* base = v.x + v.start[k] * v.ld;
+  for (int p = threadIdx.x; p < nlag * TILE; p += blockDim.x) {
+    const int t = lag0 + p / TILE;
+    const int j = p % TILE;
+    const int d = d0 + j;
+    if (d >= v.D || t >= n) continue;
+    const double m = mu[static_cast<long long>(k) * v.D + d];
+    double s = 0.0;
+    for (long long i = 0; i + t < n; ++i) {
+      s += (base[i * v.ld + d] - m) * (base[(i + t) * v.ld + d] - m);
+    }
+    atomicAdd(acc + static_cast<long long>(t - lag0) * v.D + d, s / static_cast<double>(n));
+  }
+}
+
 // Geyer estimator, one thread per dimension (summary.hpp:700-748).
 // macov[t*D + d] holds the chain SUM of autocovariances for lags < nlag.
 // flag[d] = 1 when a lag >= nlag was needed (caller extends and reruns).
@@ -243,13 +266,12 @@ void device_summary(const double* draws, int ld, int D,
     // lags in blocks until every dimension's Geyer sequence has terminated
     constexpr int TILE = 8;
     const size_t smem = static_cast<size_t>(max_len) * TILE * sizeof(double);
-    if (smem > 200 * 1024) {
-      throw std::invalid_argument("chains longer than 3200 draws are not supported "
-                                  "by the device ESS yet");
+    const bool staged = smem <= 200 * 1024;  // up to 3200 draws per chain
+    if (staged) {
+      WB200_CUDA(cudaFuncSetAttribute(acov_kernel<TILE>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
     }
-    WB200_CUDA(cudaFuncSetAttribute(acov_kernel<TILE>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem)));
     DeviceBuffer<double> macov, rho_buf;
     DeviceBuffer<int> flag;
     flag.alloc(D);
@@ -267,8 +289,13 @@ void device_summary(const double* draws, int ld, int D,
         WB200_CUDA(cudaMemcpyAsync(grown.ptr, macov.ptr, static_cast<size_t>(nlag) * D * 8,
                                    cudaMemcpyDeviceToDevice, stream));
       }
-      acov_kernel<TILE><<<dim3((D + TILE - 1) / TILE, K), 256, smem, stream>>>(
-          v, mu.ptr, nlag, target - nlag, grown.ptr + static_cast<size_t>(nlag) * D);
+      if (staged) {
+        acov_kernel<TILE><<<dim3((D + TILE - 1) / TILE, K), 256, smem, stream>>>(
+            v, mu.ptr, nlag, target - nlag, grown.ptr + static_cast<size_t>(nlag) * D);
+      } else {
+        acov_global_kernel<TILE><<<dim3((D + TILE - 1) / TILE, K), 256, 0, stream>>>(
+            v, mu.ptr, nlag, target - nlag, grown.ptr + static_cast<size_t>(nlag) * D);
+      }
       WB200_CUDA(cudaGetLastError());
       WB200_CUDA(cudaStreamSynchronize(stream));
       std::swap(macov.ptr, grown.ptr);
