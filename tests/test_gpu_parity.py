@@ -726,3 +726,27 @@ def test_c2_size_posterior_and_sharding(wb):
         s.reserve(40)
         s.warmup(150).freeze().sample(40).sync()
         np.testing.assert_array_equal(s.draws(0, 40), tail)
+
+
+def test_ctrl_c_interrupts_a_one_shot_run(wb):
+    """interrupts.hpp / errors.hpp:30-48: SIGINT during sampling ends the call with the
+    `interrupt` error, which the Python layer raises as KeyboardInterrupt; the previous
+    handler is back afterwards."""
+    import os
+    import signal
+    import threading
+    import time
+    before = signal.getsignal(signal.SIGINT)
+    timer = threading.Timer(0.7, lambda: os.kill(os.getpid(), signal.SIGINT))
+    t0 = time.perf_counter()
+    timer.start()
+    try:
+        with pytest.raises(KeyboardInterrupt):
+            wb.walnuts_device(wb.models.ill_conditioned_gaussian(1000, 1e4), num_chains=4096,
+                              seed=1, min_warmup_iter=200000, max_warmup_iter=200000,
+                              max_trajectory_doublings=10, max_sampling_iter=5,
+                              min_sampling_iter=5)
+    finally:
+        timer.cancel()
+    assert time.perf_counter() - t0 < 20.0
+    assert signal.getsignal(signal.SIGINT) is before

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <limits>
 #include <chrono>
+#include <csignal>
 #include <cstdio>
 #include <cstdlib>
 #include <sstream>
@@ -120,6 +121,36 @@ struct LastRun {
   int warmup_iters = 0, sampling_iters = 0;
 } g_last_run;
 }  // namespace
+
+// interrupts.hpp:20-104: while a one-shot run is in flight SIGINT only raises a flag; the
+// controller checks it between blocks of iterations (adapt.hpp:227, sampler.hpp:154) and
+// the run ends with an `interrupt` error (KeyboardInterrupt in Python).  RAII restores
+// the previous handler.
+static volatile std::sig_atomic_t g_interrupted = 0;
+class InterruptHandler {
+ public:
+  InterruptHandler() {
+    g_interrupted = 0;
+    std::memset(&custom_, 0, sizeof(custom_));
+    sigemptyset(&custom_.sa_mask);
+    sigaddset(&custom_.sa_mask, SIGINT);
+    custom_.sa_flags = SA_RESETHAND;
+    custom_.sa_handler = [](int) { g_interrupted = 1; };
+    installed_ = sigaction(SIGINT, &custom_, &before_) == 0;
+  }
+  ~InterruptHandler() {
+    if (installed_) sigaction(SIGINT, &before_, nullptr);
+  }
+  InterruptHandler(const InterruptHandler&) = delete;
+  InterruptHandler& operator=(const InterruptHandler&) = delete;
+  void throw_if_interrupted() const {
+    if (g_interrupted) throw wb200::InterruptException();
+  }
+
+ private:
+  struct sigaction before_, custom_;
+  bool installed_ = false;
+};
 
 extern "C" {
 
@@ -234,6 +265,7 @@ int walnutpie_sample_device(
     double* inv_metric_out, int refresh, PRINT_CALLBACK print,
     WalnutpyError** err) {
   wb200_session* s = nullptr;
+  InterruptHandler interrupt;  // walnutpy.cpp:34
   int rc = catch_exceptions(err, [&] {
     if (refresh < 0) {  // errors.hpp:74-81
       std::stringstream msg;
@@ -340,6 +372,23 @@ int walnutpie_sample_device(
         if (ev) cudaEventDestroy(ev);
       }
     } cleanup{copy_stream, block_done};
+    // at most two blocks of iterations are in flight, so that the host loop (progress
+    // lines, interrupt checks) stays in step with the device
+    cudaEvent_t ring[2] = {nullptr, nullptr};
+    WB200_CUDA(cudaEventCreateWithFlags(&ring[0], cudaEventDisableTiming));
+    WB200_CUDA(cudaEventCreateWithFlags(&ring[1], cudaEventDisableTiming));
+    struct RingCleanup {
+      cudaEvent_t* r;
+      ~RingCleanup() { cudaEventDestroy(r[0]); cudaEventDestroy(r[1]); }
+    } ring_cleanup{ring};
+    long long blocks_launched = 0;
+    auto throttle = [&] {  // call before launching a block
+      if (blocks_launched >= 2) WB200_CUDA(cudaEventSynchronize(ring[blocks_launched % 2]));
+    };
+    auto launched = [&] {  // call after launching a block
+      WB200_CUDA(cudaEventRecord(ring[blocks_launched % 2], s->stream));
+      ++blocks_launched;
+    };
     long long pending_from = 0, pending_to = 0;  // rows [from, to) stored, not yet copied
     bool pending_marked = false;
     auto mark_block = [&](long long rows_now) {  // after launching a storing block
@@ -393,13 +442,16 @@ int walnutpie_sample_device(
     };
     while (warm_done < max_warmup_iter) {
       const int n = block(warm_done, min_warmup_iter, max_warmup_iter);
+      throttle();
       check(wb200_session_warmup(s, n, save_warmup ? 1 : 0, &e), e);
+      launched();
       if (save_warmup) {
         flush_pending();
         mark_block(warm_done + n);
       }
       progress(warm_done, warm_done + n, true);
       warm_done += n;
+      interrupt.throw_if_interrupted();  // adapt.hpp:227
       if (warm_done >= min_warmup_iter && warm_done < max_warmup_iter) {
         double dev[2];
         check(wb200_session_warmup_sums(s, sums.ptr, &e), e);
@@ -414,11 +466,14 @@ int walnutpie_sample_device(
     int samp_done = 0;
     while (samp_done < max_sampling_iter) {
       const int n = block(samp_done, min_sampling_iter, max_sampling_iter);
+      throttle();
       check(wb200_session_sample(s, n, 1, &e), e);
+      launched();
       flush_pending();
       mark_block(saved_warm + samp_done + n);
       progress(warm_done + samp_done, warm_done + samp_done + n, false);
       samp_done += n;
+      interrupt.throw_if_interrupted();  // sampler.hpp:154
       if (samp_done >= min_sampling_iter && samp_done < max_sampling_iter) {
         double m[4];
         check(wb200_session_lp_moments(s, m, &e), e);

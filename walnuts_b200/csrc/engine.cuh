@@ -92,12 +92,17 @@ struct LaunchShape {
 LaunchShape shape_for_dim(int D);
 int occupancy_for(int kind, const LaunchShape& shape);
 
+// errors.hpp:30-33: the user pressed Ctrl+C (interrupts.hpp)
+struct InterruptException {};
+
 // python/src/walnutpie/errors.hpp:42-72: exceptions -> error object + rc
 template <class F>
 int catch_exceptions(WalnutpyError** err, F&& f) {
   try {
     f();
     return 0;
+  } catch (const InterruptException&) {
+    if (err) *err = new WalnutpyError{"", wb200_interrupt};
   } catch (const std::invalid_argument& e) {
     if (err) *err = new WalnutpyError{e.what(), wb200_config};
   } catch (const std::exception& e) {
