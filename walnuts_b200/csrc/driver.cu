@@ -170,6 +170,10 @@ int wb200_session_warmup_sums(wb200_session* s, double* sums_device,
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));
     ChainParams p = s->params(0, 1, false);
+    if (!sums_device) {  // single-GPU callers: the session's own buffer
+      if (s->sums.count == 0) s->sums.alloc(static_cast<size_t>(s->D) + 2);
+      sums_device = s->sums.ptr;
+    }
     warmup_sums_kernel<<<(s->D + 127) / 128, 128, 0, s->stream>>>(p, sums_device);
     WB200_CUDA(cudaGetLastError());
     WB200_CUDA(cudaStreamSynchronize(s->stream));
@@ -182,6 +186,10 @@ int wb200_session_warmup_deviation(wb200_session* s, const double* sums_device,
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));
     ChainParams p = s->params(0, 1, false);
+    if (!sums_device) {
+      if (s->sums.count == 0) throw std::runtime_error("warmup_sums has not been called");
+      sums_device = s->sums.ptr;
+    }
     double* out = s->red.ptr;  // 2 doubles of scratch
     WB200_CUDA(cudaMemsetAsync(out, 0, 2 * sizeof(double), s->stream));
     warmup_deviation_kernel<<<s->C, 256, 0, s->stream>>>(p, sums_device, out);

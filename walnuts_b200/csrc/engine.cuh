@@ -156,7 +156,7 @@ struct wb200_session {
   unsigned long long launches = 0;
 
   wb200::DeviceBuffer<double> theta, inv_mass, est, tparam, scratch, draws,
-      lp_out, step_out, im_out, red, adam_tab;
+      lp_out, step_out, im_out, red, adam_tab, sums;
   wb200::DeviceBuffer<int> depth_out;
   wb200::DeviceBuffer<wb200::ChainScalars> sc;
   wb200::DeviceBuffer<unsigned int> ticket;
