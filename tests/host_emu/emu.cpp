@@ -67,7 +67,7 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   // warm-up launch
   p.n_iter = n_warmup; p.adapt = 1; p.draw_base = 0;
   {
-    ChainRunner<Target, 1, kEmuK> r(p, grp, scratch.data(), sc_shared);
+    ChainRunner<Target, 1, kEmuK, true> r(p, grp, scratch.data(), sc_shared);
     r.dc = &decision_cache;
     if (n_warmup > 0) r.run(0);
   }
@@ -82,7 +82,7 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   std::memcpy(inv_mass_out, inv_mass.data(), D * 8);
   p.n_iter = n_sampling; p.adapt = 0; p.draw_base = n_warmup; p.im_out = nullptr;
   {
-    ChainRunner<Target, 1, kEmuK> r(p, grp, scratch.data(), sc_shared);
+    ChainRunner<Target, 1, kEmuK, false> r(p, grp, scratch.data(), sc_shared);
     r.dc = &decision_cache;
     if (n_sampling > 0) r.run(0);
   }

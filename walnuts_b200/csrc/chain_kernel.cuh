@@ -396,7 +396,9 @@ __device__ __noinline__ inline double2 momentum_normals(uint32_t seed, uint32_t 
 __device__ __noinline__ inline double exp_noinline(double x) { return exp(x); }
 
 // ---------------------------------------------------------------------------
-template <class Target, int T, int K>
+// ADAPT is a compile-time copy of ChainParams::adapt: the sampling instance carries none
+// of the adaptation code (the kernel competes for the instruction cache)
+template <class Target, int T, int K, bool ADAPT = true>
 struct ChainRunner {
   using V = Vec<T, K>;
   const ChainParams& p;
@@ -511,7 +513,7 @@ struct ChainRunner {
       integrate(cur_n, cur_h, lp2, H2, with_dots && !reversing, d_new, d_old);
       if (!reversing) {
         lpn = lp2; Hn = H2; dot_new = d_new; dot_old = d_old;
-        if (rung == 0 && p.adapt && tid == 0) {
+        if (rung == 0 && ADAPT && tid == 0) {
           adam_update(sc, p, exp_noinline(-fabs(Hs - Hn)));  // coarsest attempt only (:335-338)
         }
         if (!(fabs(Hs - Hn) <= p.max_error)) {
@@ -616,7 +618,7 @@ struct ChainRunner {
     double* est_row = p.est + static_cast<long long>(chain) * 4 * ld;
     double cur[K][2];  // current position of the chain
     V::load(theta_row, ld, tid, cur);
-    if (!p.adapt) V::load(p.inv_mass + static_cast<long long>(chain) * ld, ld, tid, im);
+    if (!ADAPT) V::load(p.inv_mass + static_cast<long long>(chain) * ld, ld, tid, im);
 
     for (int it = 0; it < p.n_iter; ++it) {
       const uint32_t iter = u_iter;
@@ -624,7 +626,7 @@ struct ChainRunner {
       double step;
       int min_micro;
       // ---- metric, step, min-micro for this transition
-      if (p.adapt) {
+      if (ADAPT) {
         double Sd[K][2], Ss[K][2];
         V::load(est_row + 1 * ld, ld, tid, Sd);
         V::load(est_row + 3 * ld, ld, tid, Ss);
@@ -673,8 +675,8 @@ struct ChainRunner {
         }
         // adaptive: inverse().sqrt() (adaptive_walnuts.hpp:236);
         // fixed:    sqrt().inverse() (walnuts.hpp:647)
-        double c0 = p.adapt ? sqrt(1.0 / im[k][0]) : 1.0 / sqrt(im[k][0]);
-        double c1 = p.adapt ? sqrt(1.0 / im[k][1]) : 1.0 / sqrt(im[k][1]);
+        double c0 = ADAPT ? sqrt(1.0 / im[k][0]) : 1.0 / sqrt(im[k][0]);
+        double c1 = ADAPT ? sqrt(1.0 / im[k][1]) : 1.0 / sqrt(im[k][1]);
         rho[k][0] = __dmul_rn(c0, z0);
         rho[k][1] = __dmul_rn(c1, z1);
       }
@@ -815,7 +817,7 @@ struct ChainRunner {
       }
       // ---- the draw
       V::load(sv(A_SEL), ld, tid, cur);
-      if (p.adapt) {
+      if (ADAPT) {
         // AdaptiveWalnuts::operator() tail, adaptive_walnuts.hpp:247-250
         double gsel[K][2], lp_dummy;
         tgt.grad(cur, gsel, lp_dummy, grp);  // grad_select (cached by the reference)
@@ -864,7 +866,7 @@ struct ChainRunner {
         const long long o = static_cast<long long>(chain) * p.draw_cap + row;
         if (p.lp_out) p.lp_out[o] = lp_sel;
         if (p.depth_out) p.depth_out[o] = depth;
-        if (p.step_out) p.step_out[o] = p.adapt ? exp_noinline(sc.adam_x) : sc.step;
+        if (p.step_out) p.step_out[o] = ADAPT ? exp_noinline(sc.adam_x) : sc.step;
       }
     }
     V::store(theta_row, ld, tid, cur);
@@ -880,7 +882,7 @@ struct ChainRunner {
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------
-template <class Target, int T, int K, int CTA, int MINB>
+template <class Target, int T, int K, int CTA, int MINB, bool ADAPT>
 __global__ void __launch_bounds__(CTA, MINB)
 walnuts_chain_kernel(const ChainParams p) {
   __shared__ double red_smem[group_smem_doubles<T>()];
@@ -903,7 +905,7 @@ walnuts_chain_kernel(const ChainParams p) {
     slot = blockIdx.x;
   }
   double* scr = p.scratch + static_cast<long long>(slot) * p.scratch_stride;
-  ChainRunner<Target, T, K> runner(p, grp, scr, sc_smem[threadIdx.x / T]);
+  ChainRunner<Target, T, K, ADAPT> runner(p, grp, scr, sc_smem[threadIdx.x / T]);
   if (grp.tid == 0) dc_smem[threadIdx.x / T].valid = 0;
   grp.sync();
   runner.dc = &dc_smem[threadIdx.x / T];

@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(CTA) orbit_kernel(const OrbitParams op) {
   }
   if (chain >= p.C) return;
   ChainScalars unused_sc{};
-  ChainRunner<Target, T, K> r(p, grp, nullptr, unused_sc);
+  ChainRunner<Target, T, K, false> r(p, grp, nullptr, unused_sc);
   r.tgt.init(p, grp.tid);
   const long long off = static_cast<long long>(chain) * p.ld;
   V::load(p.theta + off, p.ld, grp.tid, r.th);
@@ -294,10 +294,17 @@ static int sm_count(int device) {
 }
 
 #define WB200_OCC(TARGET, T_, K_, CTA_, MINB_)                                 \
-  occ = blocks_per_sm(walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_>, CTA_)
+  occ = blocks_per_sm(walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, false>, CTA_)
 #define WB200_LAUNCH_CHAIN(TARGET, T_, K_, CTA_, MINB_)                        \
-  walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_>                    \
-      <<<s.grid, CTA_, 0, s.stream>>>(p)
+  do {                                                                         \
+    if (p.adapt) {                                                             \
+      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, true>          \
+          <<<s.grid, CTA_, 0, s.stream>>>(p);                                  \
+    } else {                                                                   \
+      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, false>         \
+          <<<s.grid, CTA_, 0, s.stream>>>(p);                                  \
+    }                                                                          \
+  } while (0)
 #define WB200_LAUNCH_INIT(TARGET, T_, K_, CTA_, MINB_)                         \
   init_kernel<TARGET, T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(ip)
 #define WB200_LAUNCH_ORBIT(TARGET, T_, K_, CTA_, MINB_)                        \
