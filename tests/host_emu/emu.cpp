@@ -63,12 +63,14 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   Group<1> grp{};
   ChainScalars sc_shared{};  // stands in for the per-chain record in shared memory
   DecisionCache decision_cache{};
+  AdamQueue adam_queue{};
   using Target = TargetT<1, kEmuK>;
   // warm-up launch
   p.n_iter = n_warmup; p.adapt = 1; p.draw_base = 0;
   {
     ChainRunner<Target, 1, kEmuK, true> r(p, grp, scratch.data(), sc_shared);
     r.dc = &decision_cache;
+    r.aq = &adam_queue;
     if (n_warmup > 0) r.run(0);
   }
   // freeze_kernel

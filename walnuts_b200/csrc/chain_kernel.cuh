@@ -332,6 +332,61 @@ __device__ __noinline__ inline void adam_update(ChainScalars& sc, const ChainPar
   sc.adam_x -= decayed * m_hat / denom;
 }
 
+// Adam feeds on one acceptance probability per macro step, but its state is only read at
+// the start of the next transition.  The chain kernel therefore queues |dH| and lets the
+// control warp work the queue off in one go: the expensive, mutually independent parts of
+// every update (exp, three divisions, a square root, the decayed rate) run one update
+// per lane, while the cheap linear recurrences (t, beta powers, m, v, x) run in order --
+// the same IEEE operations on the same operands as adam_update, so the same bits.
+struct AdamQueue {
+  double dH[32];
+  int n;
+};
+
+template <int LANES>
+__device__ __noinline__ inline void adam_flush(ChainScalars& sc, const ChainParams& p,
+                                        AdamQueue& q, int lane) {
+  __syncwarp();
+  const int n = q.n;
+  if (n == 0) return;
+  double alpha = 0.0;
+  if (lane < n) alpha = exp(-q.dH[lane]);
+  double t = sc.adam_t, b1p = sc.adam_b1p, b2p = sc.adam_b2p, m = sc.adam_m, v = sc.adam_v;
+  double my_t = 0.0, my_b1p = 0.0, my_b2p = 0.0, my_m = 0.0, my_v = 0.0;
+  for (int j = 0; j < n; ++j) {
+    const double a_j = LANES > 1 ? __shfl_sync(0xffffffffu, alpha, j) : alpha;
+    t += 1.0;
+    b1p *= p.adam_b1;
+    b2p *= p.adam_b2;
+    const double grad = p.adam_target - a_j;
+    m = p.adam_b1 * m + (1 - p.adam_b1) * grad;
+    v = p.adam_b2 * v + (1 - p.adam_b2) * grad * grad;
+    if (j == lane) { my_t = t; my_b1p = b1p; my_b2p = b2p; my_m = m; my_v = v; }
+  }
+  double term = 0.0;
+  if (lane < n) {
+    const double m_hat = my_m / (1 - my_b1p);
+    const double v_hat = my_v / (1 - my_b2p);
+    const double decayed =
+        (p.adam_tab != nullptr && my_t <= static_cast<double>(p.adam_tab_n))
+            ? p.adam_tab[static_cast<int>(my_t) - 1]
+            : p.adam_lr / pow(my_t, p.adam_decay);
+    const double denom = sqrt(v_hat) + p.adam_eps;
+    term = decayed * m_hat / denom;
+  }
+  double x = sc.adam_x;
+  for (int j = 0; j < n; ++j) {
+    x -= LANES > 1 ? __shfl_sync(0xffffffffu, term, j) : term;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    sc.adam_t = t; sc.adam_b1p = b1p; sc.adam_b2p = b2p;
+    sc.adam_m = m; sc.adam_v = v; sc.adam_x = x;
+    q.n = 0;
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ int min_micro_steps(double mm_total, double mm_count,
                                                const ChainParams& p) {
   // adaptive_walnuts.hpp:152-157
@@ -415,6 +470,8 @@ struct ChainRunner {
   // its own vector work are mirrored in registers (u_*), updated redundantly.
   ChainScalars& sc;
   DecisionCache* dc = nullptr;  // shared memory, control warp only (null: no look-ahead)
+  AdamQueue* aq = nullptr;      // shared memory (null: Adam updated at every macro step)
+  static constexpr int kAdamLanes = T >= 32 ? 32 : T;
   uint32_t u_iter, u_warm_iter;
   double u_est_w, u_mm_total, u_mm_count;
   unsigned long long evals;
@@ -513,8 +570,16 @@ struct ChainRunner {
       integrate(cur_n, cur_h, lp2, H2, with_dots && !reversing, d_new, d_old);
       if (!reversing) {
         lpn = lp2; Hn = H2; dot_new = d_new; dot_old = d_old;
-        if (rung == 0 && ADAPT && tid == 0) {
-          adam_update(sc, p, exp_noinline(-fabs(Hs - Hn)));  // coarsest attempt only (:335-338)
+        if (rung == 0 && ADAPT) {  // coarsest attempt only (:335-338)
+          if (aq == nullptr) {
+            if (tid == 0) adam_update(sc, p, exp_noinline(-fabs(Hs - Hn)));
+          } else {
+            if (tid == 0) aq->dH[aq->n++] = fabs(Hs - Hn);
+            if (grp.ctl()) {
+              __syncwarp();
+              if (aq->n >= kAdamLanes) adam_flush<kAdamLanes>(sc, p, *aq, grp.lane);
+            }
+          }
         }
         if (!(fabs(Hs - Hn) <= p.max_error)) {
           ++rung;
@@ -854,6 +919,7 @@ struct ChainRunner {
         sc.lp_m2 += delta * (lp_sel - sc.lp_mean);
       }
       u_iter += 1;
+      if (ADAPT && aq != nullptr && grp.ctl()) adam_flush<kAdamLanes>(sc, p, *aq, grp.lane);
       if (tid == 0) {
         sc.last_depth = depth;
         sc.last_lp = lp_sel;
@@ -888,6 +954,7 @@ walnuts_chain_kernel(const ChainParams p) {
   __shared__ double red_smem[group_smem_doubles<T>()];
   __shared__ ChainScalars sc_smem[CTA / T];
   __shared__ DecisionCache dc_smem[CTA / T];
+  __shared__ AdamQueue aq_smem[ADAPT ? CTA / T : 1];
   __shared__ int next_chain;
   Group<T> grp;
   grp.lane = threadIdx.x & 31;
@@ -906,9 +973,13 @@ walnuts_chain_kernel(const ChainParams p) {
   }
   double* scr = p.scratch + static_cast<long long>(slot) * p.scratch_stride;
   ChainRunner<Target, T, K, ADAPT> runner(p, grp, scr, sc_smem[threadIdx.x / T]);
-  if (grp.tid == 0) dc_smem[threadIdx.x / T].valid = 0;
+  if (grp.tid == 0) {
+    dc_smem[threadIdx.x / T].valid = 0;
+    if (ADAPT) aq_smem[threadIdx.x / T].n = 0;
+  }
   grp.sync();
   runner.dc = &dc_smem[threadIdx.x / T];
+  if (ADAPT) runner.aq = &aq_smem[threadIdx.x / T];
   while (true) {
     int chain;
     if constexpr (T == 32) {
