@@ -449,6 +449,11 @@ __device__ __noinline__ inline double2 momentum_normals(uint32_t seed, uint32_t 
 }
 
 __device__ __noinline__ inline double exp_noinline(double x) { return exp(x); }
+// fp64 division and square root expand to 35-60 instructions each; the per-transition
+// code uses them 8 elements x several times per thread, so one shared body each keeps
+// the kernel inside the instruction cache (same IEEE operations)
+__device__ __noinline__ inline double div_noinline(double a, double b) { return a / b; }
+__device__ __noinline__ inline double sqrt_noinline(double a) { return sqrt(a); }
 
 // ---------------------------------------------------------------------------
 // ADAPT is a compile-time copy of ChainParams::adapt: the sampling instance carries none
@@ -700,7 +705,8 @@ struct ChainRunner {
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
             // MassEstimator::inv_mass_estimate, adaptive_walnuts.hpp:89-94
-            im[k][v] = sqrt((Sd[k][v] / u_est_w) / (Ss[k][v] / u_est_w));
+            im[k][v] = sqrt_noinline(div_noinline(div_noinline(Sd[k][v], u_est_w),
+                                                  div_noinline(Ss[k][v], u_est_w)));
           }
         }
         double r[1] = {0.0};
@@ -740,8 +746,10 @@ struct ChainRunner {
         }
         // adaptive: inverse().sqrt() (adaptive_walnuts.hpp:236);
         // fixed:    sqrt().inverse() (walnuts.hpp:647)
-        double c0 = ADAPT ? sqrt(1.0 / im[k][0]) : 1.0 / sqrt(im[k][0]);
-        double c1 = ADAPT ? sqrt(1.0 / im[k][1]) : 1.0 / sqrt(im[k][1]);
+        double c0 = ADAPT ? sqrt_noinline(div_noinline(1.0, im[k][0]))
+                          : div_noinline(1.0, sqrt_noinline(im[k][0]));
+        double c1 = ADAPT ? sqrt_noinline(div_noinline(1.0, im[k][1]))
+                          : div_noinline(1.0, sqrt_noinline(im[k][1]));
         rho[k][0] = __dmul_rn(c0, z0);
         rho[k][1] = __dmul_rn(c1, z1);
       }
@@ -900,7 +908,7 @@ struct ChainRunner {
             for (int v = 0; v < 2; ++v) {
               const double y = e == 0 ? cur[k][v] : gsel[k][v];
               // online_moments.hpp:185-191 (both factors see the updated mean)
-              mu[k][v] = __dadd_rn(mu[k][v], __dadd_rn(y, -mu[k][v]) / u_est_w);
+              mu[k][v] = __dadd_rn(mu[k][v], div_noinline(__dadd_rn(y, -mu[k][v]), u_est_w));
               const double d = __dadd_rn(y, -mu[k][v]);
               S[k][v] = __dadd_rn(__dmul_rn(gamma, S[k][v]), __dmul_rn(d, d));
             }
