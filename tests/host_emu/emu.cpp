@@ -29,7 +29,7 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   const int ld = (D + 1) & ~1;
   const int total = n_warmup + n_sampling;
   std::vector<double> theta(ld, 0.0), inv_mass(ld, 0.0), est(4 * ld, 0.0), tp(ld, 0.0);
-  std::vector<double> scratch(static_cast<size_t>(scratch_vectors(t.max_depth)) * ld, 0.0);
+  std::vector<double> scratch(static_cast<size_t>(scratch_doubles(t.max_depth, ld)), 0.0);
   std::vector<double> d_draws(static_cast<size_t>(total) * ld), d_im(static_cast<size_t>(total) * ld);
   std::memcpy(theta.data(), theta0, D * 8);
   if (tparam) std::memcpy(tp.data(), tparam, D * 8);

@@ -168,7 +168,7 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
     s->grid = std::min(max_grid, need);
     s->slots = s->grid * s->shape.chains_per_cta;
     const size_t stride =
-        static_cast<size_t>(scratch_vectors(s->tuning.max_trajectory_doublings)) * s->ld;
+        static_cast<size_t>(scratch_doubles(s->tuning.max_trajectory_doublings, s->ld));
     s->scratch.alloc(stride * s->slots);
     WB200_CUDA(cudaMemsetAsync(s->scratch.ptr, 0, stride * s->slots * 8, s->stream));
     WB200_CUDA(cudaStreamSynchronize(s->stream));

@@ -109,6 +109,11 @@ enum : int { ST_THF = 0, ST_RHOF = 1, ST_SEL = 2 };
 __host__ __device__ inline int scratch_vectors(int max_depth) {
   return ST_BASE + 3 * max_depth;
 }
+// doubles of scratch per resident group: the vectors, then the Adam queue (one |dH| per
+// macro step of a transition, at most 2^max_depth of them)
+__host__ __device__ inline long long scratch_doubles(int max_depth, int ld) {
+  return static_cast<long long>(scratch_vectors(max_depth)) * ld + (1ll << max_depth);
+}
 
 // ---------------------------------------------------------------------------
 // T cooperating threads.  sum(): all-reduce, bitwise identical in every thread.
@@ -339,44 +344,46 @@ __device__ __noinline__ inline void adam_update(ChainScalars& sc, const ChainPar
 // per lane, while the cheap linear recurrences (t, beta powers, m, v, x) run in order --
 // the same IEEE operations on the same operands as adam_update, so the same bits.
 struct AdamQueue {
-  double dH[32];
-  int n;
+  int n;  // entries waiting in the group's scratch queue
 };
 
 template <int LANES>
 __device__ __noinline__ inline void adam_flush(ChainScalars& sc, const ChainParams& p,
-                                        AdamQueue& q, int lane) {
+                                        AdamQueue& q, const double* dH, int lane) {
   __syncwarp();
   const int n = q.n;
   if (n == 0) return;
-  double alpha = 0.0;
-  if (lane < n) alpha = exp(-q.dH[lane]);
   double t = sc.adam_t, b1p = sc.adam_b1p, b2p = sc.adam_b2p, m = sc.adam_m, v = sc.adam_v;
-  double my_t = 0.0, my_b1p = 0.0, my_b2p = 0.0, my_m = 0.0, my_v = 0.0;
-  for (int j = 0; j < n; ++j) {
-    const double a_j = LANES > 1 ? __shfl_sync(0xffffffffu, alpha, j) : alpha;
-    t += 1.0;
-    b1p *= p.adam_b1;
-    b2p *= p.adam_b2;
-    const double grad = p.adam_target - a_j;
-    m = p.adam_b1 * m + (1 - p.adam_b1) * grad;
-    v = p.adam_b2 * v + (1 - p.adam_b2) * grad * grad;
-    if (j == lane) { my_t = t; my_b1p = b1p; my_b2p = b2p; my_m = m; my_v = v; }
-  }
-  double term = 0.0;
-  if (lane < n) {
-    const double m_hat = my_m / (1 - my_b1p);
-    const double v_hat = my_v / (1 - my_b2p);
-    const double decayed =
-        (p.adam_tab != nullptr && my_t <= static_cast<double>(p.adam_tab_n))
-            ? p.adam_tab[static_cast<int>(my_t) - 1]
-            : p.adam_lr / pow(my_t, p.adam_decay);
-    const double denom = sqrt(v_hat) + p.adam_eps;
-    term = decayed * m_hat / denom;
-  }
   double x = sc.adam_x;
-  for (int j = 0; j < n; ++j) {
-    x -= LANES > 1 ? __shfl_sync(0xffffffffu, term, j) : term;
+  for (int base = 0; base < n; base += LANES) {
+    const int cnt = n - base < LANES ? n - base : LANES;
+    double alpha = 0.0;
+    if (lane < cnt) alpha = exp(-dH[base + lane]);
+    double my_t = 0.0, my_b1p = 0.0, my_b2p = 0.0, my_m = 0.0, my_v = 0.0;
+    for (int j = 0; j < cnt; ++j) {
+      const double a_j = LANES > 1 ? __shfl_sync(0xffffffffu, alpha, j) : alpha;
+      t += 1.0;
+      b1p *= p.adam_b1;
+      b2p *= p.adam_b2;
+      const double grad = p.adam_target - a_j;
+      m = p.adam_b1 * m + (1 - p.adam_b1) * grad;
+      v = p.adam_b2 * v + (1 - p.adam_b2) * grad * grad;
+      if (j == lane) { my_t = t; my_b1p = b1p; my_b2p = b2p; my_m = m; my_v = v; }
+    }
+    double term = 0.0;
+    if (lane < cnt) {
+      const double m_hat = my_m / (1 - my_b1p);
+      const double v_hat = my_v / (1 - my_b2p);
+      const double decayed =
+          (p.adam_tab != nullptr && my_t <= static_cast<double>(p.adam_tab_n))
+              ? p.adam_tab[static_cast<int>(my_t) - 1]
+              : p.adam_lr / pow(my_t, p.adam_decay);
+      const double denom = sqrt(v_hat) + p.adam_eps;
+      term = decayed * m_hat / denom;
+    }
+    for (int j = 0; j < cnt; ++j) {
+      x -= LANES > 1 ? __shfl_sync(0xffffffffu, term, j) : term;
+    }
   }
   __syncwarp();
   if (lane == 0) {
@@ -475,8 +482,11 @@ struct ChainRunner {
   // its own vector work are mirrored in registers (u_*), updated redundantly.
   ChainScalars& sc;
   DecisionCache* dc = nullptr;  // shared memory, control warp only (null: no look-ahead)
-  AdamQueue* aq = nullptr;      // shared memory (null: Adam updated at every macro step)
+  AdamQueue* aq = nullptr;      // shared memory; the entries live behind the scratch vectors
   static constexpr int kAdamLanes = T >= 32 ? 32 : T;
+  __device__ __forceinline__ double* adam_dH() const {
+    return scr + static_cast<long long>(scratch_vectors(p.max_depth)) * ld;
+  }
   uint32_t u_iter, u_warm_iter;
   double u_est_w, u_mm_total, u_mm_count;
   unsigned long long evals;
@@ -575,16 +585,8 @@ struct ChainRunner {
       integrate(cur_n, cur_h, lp2, H2, with_dots && !reversing, d_new, d_old);
       if (!reversing) {
         lpn = lp2; Hn = H2; dot_new = d_new; dot_old = d_old;
-        if (rung == 0 && ADAPT) {  // coarsest attempt only (:335-338)
-          if (aq == nullptr) {
-            if (tid == 0) adam_update(sc, p, exp_noinline(-fabs(Hs - Hn)));
-          } else {
-            if (tid == 0) aq->dH[aq->n++] = fabs(Hs - Hn);
-            if (grp.ctl()) {
-              __syncwarp();
-              if (aq->n >= kAdamLanes) adam_flush<kAdamLanes>(sc, p, *aq, grp.lane);
-            }
-          }
+        if (rung == 0 && ADAPT && tid == 0) {  // coarsest attempt only (:335-338)
+          adam_dH()[aq->n++] = fabs(Hs - Hn);  // worked off at the end of the transition
         }
         if (!(fabs(Hs - Hn) <= p.max_error)) {
           ++rung;
@@ -927,7 +929,7 @@ struct ChainRunner {
         sc.lp_m2 += delta * (lp_sel - sc.lp_mean);
       }
       u_iter += 1;
-      if (ADAPT && aq != nullptr && grp.ctl()) adam_flush<kAdamLanes>(sc, p, *aq, grp.lane);
+      if (ADAPT && grp.ctl()) adam_flush<kAdamLanes>(sc, p, *aq, adam_dH(), grp.lane);
       if (tid == 0) {
         sc.last_depth = depth;
         sc.last_lp = lp_sel;

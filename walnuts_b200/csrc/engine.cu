@@ -427,7 +427,7 @@ wb200::ChainParams wb200_session::params(int n_iter, int adapt, bool store) {
   }
   p.scratch = scratch.ptr;
   p.scratch_stride =
-      static_cast<long long>(wb200::scratch_vectors(tuning.max_trajectory_doublings)) * ld;
+      wb200::scratch_doubles(tuning.max_trajectory_doublings, ld);
   p.ticket = ticket.ptr;
   p.tparam = tparam.ptr;
   return p;
