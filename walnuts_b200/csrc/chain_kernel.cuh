@@ -487,8 +487,7 @@ struct ChainRunner {
   __device__ __forceinline__ double* adam_dH() const {
     return scr + static_cast<long long>(scratch_vectors(p.max_depth)) * ld;
   }
-  uint32_t u_iter, u_warm_iter;
-  double u_est_w, u_mm_total, u_mm_count;
+  uint32_t u_iter;
   unsigned long long evals;
 
   __device__ ChainRunner(const ChainParams& p_, Group<T>& grp_, double* scr_,
@@ -682,12 +681,15 @@ struct ChainRunner {
     const uint32_t gchain = p.chain_offset + static_cast<uint32_t>(chain);
     if (tid == 0) sc = p.sc[chain];
     grp.sync();
-    u_iter = sc.iter; u_warm_iter = sc.warm_iter;
-    u_est_w = sc.est_w; u_mm_total = sc.mm_total; u_mm_count = sc.mm_count;
+    u_iter = sc.iter;
     evals = 0;
     tgt.init(p, tid);
     double* theta_row = p.theta + static_cast<long long>(chain) * ld;
-    double* est_row = p.est + static_cast<long long>(chain) * 4 * ld;
+    // the adaptation scalars (estimator weight, min-micro controller, warm-up count) stay
+    // in shared memory and are read where they are used: mirrored in registers they
+    // stayed live through the macro-step loop and pushed whole state arrays out to
+    // local memory
+    auto est_row = [&]() { return p.est + static_cast<long long>(chain) * 4 * ld; };
     double cur[K][2];  // current position of the chain
     V::load(theta_row, ld, tid, cur);
     if (!ADAPT) V::load(p.inv_mass + static_cast<long long>(chain) * ld, ld, tid, im);
@@ -699,24 +701,27 @@ struct ChainRunner {
       int min_micro;
       // ---- metric, step, min-micro for this transition
       if (ADAPT) {
-        double Sd[K][2], Ss[K][2];
-        V::load(est_row + 1 * ld, ld, tid, Sd);
-        V::load(est_row + 3 * ld, ld, tid, Ss);
+        grp.sync();  // thread 0's updates at the end of the previous transition are visible
+        {
+          const double est_w = sc.est_w;
+          double Sd[K][2], Ss[K][2];
+          V::load(est_row() + 1 * ld, ld, tid, Sd);
+          V::load(est_row() + 3 * ld, ld, tid, Ss);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
+          for (int k = 0; k < K; ++k) {
 #pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            // MassEstimator::inv_mass_estimate, adaptive_walnuts.hpp:89-94
-            im[k][v] = sqrt_noinline(div_noinline(div_noinline(Sd[k][v], u_est_w),
-                                                  div_noinline(Ss[k][v], u_est_w)));
+            for (int v = 0; v < 2; ++v) {
+              // MassEstimator::inv_mass_estimate, adaptive_walnuts.hpp:89-94
+              im[k][v] = sqrt_noinline(div_noinline(div_noinline(Sd[k][v], est_w),
+                                                    div_noinline(Ss[k][v], est_w)));
+            }
           }
         }
         double r[1] = {0.0};
-        grp.sync();  // thread 0's Adam updates of the previous transition are visible
         if (grp.ctl()) r[0] = exp_noinline(sc.adam_x);  // Adam state: thread 0 writes it
         grp.bcast(r);
         step = r[0];
-        min_micro = min_micro_steps(u_mm_total, u_mm_count, p);
+        min_micro = min_micro_steps(sc.mm_total, sc.mm_count, p);
       } else {
         step = sc.step;
         min_micro = sc.min_micro;
@@ -897,30 +902,34 @@ struct ChainRunner {
         double gsel[K][2], lp_dummy;
         tgt.grad(cur, gsel, lp_dummy, grp);  // grad_select (cached by the reference)
         const double gamma =
-            1.0 - 1.0 / (p.mass_init_count + static_cast<double>(u_warm_iter));
-        u_est_w = gamma * u_est_w + 1.0;
+            1.0 - 1.0 / (p.mass_init_count + static_cast<double>(sc.warm_iter));
+        const double est_w = gamma * sc.est_w + 1.0;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           double mu[K][2], S[K][2];
-          V::load(est_row + (2 * e) * ld, ld, tid, mu);
-          V::load(est_row + (2 * e + 1) * ld, ld, tid, S);
+          V::load(est_row() + (2 * e) * ld, ld, tid, mu);
+          V::load(est_row() + (2 * e + 1) * ld, ld, tid, S);
 #pragma unroll
           for (int k = 0; k < K; ++k) {
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
               const double y = e == 0 ? cur[k][v] : gsel[k][v];
               // online_moments.hpp:185-191 (both factors see the updated mean)
-              mu[k][v] = __dadd_rn(mu[k][v], div_noinline(__dadd_rn(y, -mu[k][v]), u_est_w));
+              mu[k][v] = __dadd_rn(mu[k][v], div_noinline(__dadd_rn(y, -mu[k][v]), est_w));
               const double d = __dadd_rn(y, -mu[k][v]);
               S[k][v] = __dadd_rn(__dmul_rn(gamma, S[k][v]), __dmul_rn(d, d));
             }
           }
-          V::store(est_row + (2 * e) * ld, ld, tid, mu);
-          V::store(est_row + (2 * e + 1) * ld, ld, tid, S);
+          V::store(est_row() + (2 * e) * ld, ld, tid, mu);
+          V::store(est_row() + (2 * e + 1) * ld, ld, tid, S);
         }
-        u_mm_total += static_cast<double>(1ull << depth);
-        u_mm_count += 1.0;
-        u_warm_iter += 1;
+        grp.sync();  // every thread has read the scalars thread 0 now advances
+        if (tid == 0) {
+          sc.est_w = est_w;
+          sc.mm_total += static_cast<double>(1ull << depth);
+          sc.mm_count += 1.0;
+          sc.warm_iter += 1;
+        }
       } else if (tid == 0) {
         // WelfordAccumulator::observe (sampler.hpp:87-88)
         sc.lp_n += 1;
@@ -948,8 +957,7 @@ struct ChainRunner {
     V::store(theta_row, ld, tid, cur);
     if (tid == 0) {
       sc.grad_evals += evals;
-      sc.iter = u_iter; sc.warm_iter = u_warm_iter;
-      sc.est_w = u_est_w; sc.mm_total = u_mm_total; sc.mm_count = u_mm_count;
+      sc.iter = u_iter;
       p.sc[chain] = sc;
     }
     grp.sync();
