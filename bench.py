@@ -54,11 +54,11 @@ ELEMENTWISE = {
                kind="diag_gaussian", D=D, chains=CHAINS_PER_GPU, init_radius=2.0,
                warmup_iters=WARMUP_ITERS, max_doublings=MAX_DOUBLINGS,
                max_halvings=MAX_HALVINGS, cpu_warm=300, cpu_samp=1000,
-               kernel="walnuts_chain_kernel<DiagGaussianTarget<128,4>>"),
+               kernel="walnuts_chain_kernel<DiagGaussianTarget<128,4>, ADAPT=false>"),
     "c3": dict(label="c3: Neal's funnel D=100, 16384 chains per GPU, fp64",
                kind="funnel", D=100, chains=16384, init_radius=1.0, warmup_iters=300,
                max_doublings=10, max_halvings=8, cpu_warm=300, cpu_samp=300,
-               kernel="walnuts_chain_kernel<FunnelTarget<32,2>>"),
+               kernel="walnuts_chain_kernel<FunnelTarget<32,2>, ADAPT=false>"),
 }
 
 # --workload c4: Bayesian logistic regression (BASELINE.json configs[3]); not the
@@ -603,8 +603,8 @@ def run_ours(args):
             "frac": achieved / hbm_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one timed launch (10
             # transitions x 4096 chains) from the committed ncu --set full capture
-            "traffic": 3.55e9 if args.workload == "c2" and ips == 10 and C == 4096 else None,
-            "traffic_source": "profiles/r1_ncu_chain_kernel_final_c2.csv",
+            "traffic": 1.85e9 if args.workload == "c2" and ips == 10 and C == 4096 else None,
+            "traffic_source": "profiles/r1_ncu_chain_kernel_sampling_final_c2.csv",
             "peak_source": peak_src,
             "kernel": wl["kernel"],
             "algorithmic_bytes_per_eval": ALG_BYTES_PER_EVAL,
