@@ -104,7 +104,7 @@ struct ChainParams {
 
 // scratch vector indices
 enum : int { A_TH_BK = 0, A_RHO_BK, A_G_BK, A_TH_FW, A_RHO_FW, A_G_FW, A_SEL,
-             E_TH, E_RHO, E_G, ST_BASE };
+             E_TH, E_RHO, E_G, A_IM, ST_BASE };
 enum : int { ST_THF = 0, ST_RHOF = 1, ST_SEL = 2 };
 __host__ __device__ inline int scratch_vectors(int max_depth) {
   return ST_BASE + 3 * max_depth;
@@ -463,6 +463,87 @@ __device__ __noinline__ inline double div_noinline(double a, double b) { return 
 __device__ __noinline__ inline double sqrt_noinline(double a) { return sqrt(a); }
 
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// The per-transition adaptation blocks of the chain kernel, out of line and free of the
+// runner's register arrays: inside the function that holds the macro-step loop they
+// raised the register pressure enough to spill whole state arrays (ncu: 5 % of the
+// executed instructions were local loads).  They communicate through the group's
+// scratch row (the metric), the chain's estimator rows and the shared scalars.
+//
+// Start of a transition (adaptive_walnuts.hpp:235-245): M^-1 from the estimators ->
+// scratch row `im_row`; thread 0 publishes step = exp(adam_x) and min-micro in `sc`.
+// Returns the group's barrier parity.
+template <int T, int K>
+__device__ __noinline__ int adapt_begin(const ChainParams& p, Group<T> grp, ChainScalars& sc,
+                                        const double* est_row, double* im_row) {
+  using V = Vec<T, K>;
+  const int ld = p.ld, tid = grp.tid;
+  grp.sync();  // thread 0's updates at the end of the previous transition are visible
+  const double est_w = sc.est_w;
+  double Sd[K][2], Ss[K][2], im[K][2];
+  V::load(est_row + 1 * ld, ld, tid, Sd);
+  V::load(est_row + 3 * ld, ld, tid, Ss);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      // MassEstimator::inv_mass_estimate, adaptive_walnuts.hpp:89-94
+      im[k][v] = sqrt_noinline(div_noinline(div_noinline(Sd[k][v], est_w),
+                                            div_noinline(Ss[k][v], est_w)));
+    }
+  }
+  V::store(im_row, ld, tid, im);
+  if (tid == 0) {
+    sc.step = exp(sc.adam_x);
+    sc.min_micro = min_micro_steps(sc.mm_total, sc.mm_count, p);
+  }
+  grp.sync();
+  return grp.parity;
+}
+
+// End of a transition (adaptive_walnuts.hpp:247-250): gradient at the selected draw,
+// discounted Welford updates of draws and scores, estimator weight, min-micro controller.
+template <class Target, int T, int K>
+__device__ __noinline__ int adapt_end(const ChainParams& p, Group<T> grp, ChainScalars& sc,
+                                      double* est_row, const double* sel_row, int depth) {
+  using V = Vec<T, K>;
+  const int ld = p.ld, tid = grp.tid;
+  Target tgt;
+  tgt.init(p, tid);
+  double cur[K][2], gsel[K][2], lp_dummy;
+  V::load(sel_row, ld, tid, cur);
+  tgt.grad(cur, gsel, lp_dummy, grp);  // grad_select (cached by the reference)
+  const double gamma = 1.0 - 1.0 / (p.mass_init_count + static_cast<double>(sc.warm_iter));
+  const double est_w = gamma * sc.est_w + 1.0;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    double mu[K][2], S[K][2];
+    V::load(est_row + (2 * e) * ld, ld, tid, mu);
+    V::load(est_row + (2 * e + 1) * ld, ld, tid, S);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const double y = e == 0 ? cur[k][v] : gsel[k][v];
+        // online_moments.hpp:185-191 (both factors see the updated mean)
+        mu[k][v] = __dadd_rn(mu[k][v], div_noinline(__dadd_rn(y, -mu[k][v]), est_w));
+        const double d = __dadd_rn(y, -mu[k][v]);
+        S[k][v] = __dadd_rn(__dmul_rn(gamma, S[k][v]), __dmul_rn(d, d));
+      }
+    }
+    V::store(est_row + (2 * e) * ld, ld, tid, mu);
+    V::store(est_row + (2 * e + 1) * ld, ld, tid, S);
+  }
+  grp.sync();  // every thread has read the scalars thread 0 now advances
+  if (tid == 0) {
+    sc.est_w = est_w;
+    sc.mm_total += static_cast<double>(1ull << depth);
+    sc.mm_count += 1.0;
+    sc.warm_iter += 1;
+  }
+  return grp.parity;
+}
+
 // ADAPT is a compile-time copy of ChainParams::adapt: the sampling instance carries none
 // of the adaptation code (the kernel competes for the instruction cache)
 template <class Target, int T, int K, bool ADAPT = true>
@@ -701,31 +782,11 @@ struct ChainRunner {
       int min_micro;
       // ---- metric, step, min-micro for this transition
       if (ADAPT) {
-        grp.sync();  // thread 0's updates at the end of the previous transition are visible
-        {
-          const double est_w = sc.est_w;
-          double Sd[K][2], Ss[K][2];
-          V::load(est_row() + 1 * ld, ld, tid, Sd);
-          V::load(est_row() + 3 * ld, ld, tid, Ss);
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-              // MassEstimator::inv_mass_estimate, adaptive_walnuts.hpp:89-94
-              im[k][v] = sqrt_noinline(div_noinline(div_noinline(Sd[k][v], est_w),
-                                                    div_noinline(Ss[k][v], est_w)));
-            }
-          }
-        }
-        double r[1] = {0.0};
-        if (grp.ctl()) r[0] = exp_noinline(sc.adam_x);  // Adam state: thread 0 writes it
-        grp.bcast(r);
-        step = r[0];
-        min_micro = min_micro_steps(sc.mm_total, sc.mm_count, p);
-      } else {
-        step = sc.step;
-        min_micro = sc.min_micro;
+        grp.parity = adapt_begin<T, K>(p, grp, sc, est_row(), sv(A_IM));
+        V::load(sv(A_IM), ld, tid, im);
       }
+      step = sc.step;
+      min_micro = sc.min_micro;
       // lanes beyond D (padding of the 2*T*K register slots) carry a unit metric so
       // that every quotient below stays finite; their theta / rho / grad stay 0
 #pragma unroll
@@ -898,38 +959,7 @@ struct ChainRunner {
       // ---- the draw
       V::load(sv(A_SEL), ld, tid, cur);
       if (ADAPT) {
-        // AdaptiveWalnuts::operator() tail, adaptive_walnuts.hpp:247-250
-        double gsel[K][2], lp_dummy;
-        tgt.grad(cur, gsel, lp_dummy, grp);  // grad_select (cached by the reference)
-        const double gamma =
-            1.0 - 1.0 / (p.mass_init_count + static_cast<double>(sc.warm_iter));
-        const double est_w = gamma * sc.est_w + 1.0;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          double mu[K][2], S[K][2];
-          V::load(est_row() + (2 * e) * ld, ld, tid, mu);
-          V::load(est_row() + (2 * e + 1) * ld, ld, tid, S);
-#pragma unroll
-          for (int k = 0; k < K; ++k) {
-#pragma unroll
-            for (int v = 0; v < 2; ++v) {
-              const double y = e == 0 ? cur[k][v] : gsel[k][v];
-              // online_moments.hpp:185-191 (both factors see the updated mean)
-              mu[k][v] = __dadd_rn(mu[k][v], div_noinline(__dadd_rn(y, -mu[k][v]), est_w));
-              const double d = __dadd_rn(y, -mu[k][v]);
-              S[k][v] = __dadd_rn(__dmul_rn(gamma, S[k][v]), __dmul_rn(d, d));
-            }
-          }
-          V::store(est_row() + (2 * e) * ld, ld, tid, mu);
-          V::store(est_row() + (2 * e + 1) * ld, ld, tid, S);
-        }
-        grp.sync();  // every thread has read the scalars thread 0 now advances
-        if (tid == 0) {
-          sc.est_w = est_w;
-          sc.mm_total += static_cast<double>(1ull << depth);
-          sc.mm_count += 1.0;
-          sc.warm_iter += 1;
-        }
+        grp.parity = adapt_end<Target, T, K>(p, grp, sc, est_row(), sv(A_SEL), depth);
       } else if (tid == 0) {
         // WelfordAccumulator::observe (sampler.hpp:87-88)
         sc.lp_n += 1;
