@@ -3,6 +3,7 @@
 per second and min-ESS per second vs the CPU reference sampler).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c3|c4|c5]
 
 Workload (config.workload "c2"): BASELINE.json configs[1] — 1000-dimensional
 ill-conditioned diagonal Gaussian (condition number 1e4), 4096 chains per GPU,
@@ -13,13 +14,22 @@ WALNUTS transitions of every chain on the GPU, draws stored in HBM.
  * value      gradient evaluations / s over exactly K steps, state resident in HBM,
               timed with CUDA events on the launching stream (max over ranks)
  * e2e        the same metric through the reference-facing C-ABI call
-              walnutpie_sample_device with HOST buffers: initial positions uploaded,
-              warm-up + K steps of sampling run, every draw copied back to the host
+              walnutpie_sample_device with (pinned) HOST buffers: session set-up, initial
+              positions uploaded, adaptive warm-up + K steps of sampling, every draw copied
+              back to the host (overlapped with sampling), all inside the timed call
  * roofline   7*D*8 algorithmic bytes per gradient evaluation
               against the measured HBM copy bandwidth
  * cpu_baseline  the reference's own sampler (oracle/_ref: unmodified headers on the
               Eigen shim; falls back to the oracle port) one chain per host core
 With --impl reference the reference arm alone is timed (rank 0 only).
+
+Other workloads (not the driver's default line): c3 = Neal's funnel D=100, 16384 chains
+(same code path as c2); c4 = Bayesian logistic regression N=100k, D=512, 8192 chains on the
+lock-step engine with the tcgen05 gradient -- a step is 100 ticks (one batched gradient each),
+the roofline is 4*N*D flops per chain-gradient against the measured sustained bf16 peak, e2e
+goes through the C-ABI session calls from host X / y to host draws; c5 = c4 with 65,536
+chains in total sharded over the ranks (strong scaling, NCCL all-reduce of R-hat moments).
+stdout carries exactly one JSON line.
 """
 from __future__ import annotations
 
