@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _ffi
 from .models import DeviceModel
-from .util import (WarmupInfo, prepare_inv_metric, prepare_output_buffer,
+from .buffers import (WarmupInfo, prepare_inv_metric, prepare_output_buffer,
                    prepare_seed)
 
 
