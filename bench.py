@@ -534,15 +534,12 @@ def run_ours(args):
     clock_summary = clocks.summary()
     sess.close()
 
-    if rank != 0:
-        if distributed:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # ---- e2e: the C-ABI one-shot call with host buffers (rank 0's GPU)
+    # ---- e2e: the C-ABI one-shot call with host buffers, every rank on its own GPU
     torch.cuda.synchronize()
     e2e_samp = K * ips
+    import psutil
+    if world * C * e2e_samp * D * 8 > 0.5 * psutil.virtual_memory().available:
+        raise SystemExit("not enough host memory for the e2e output buffers")
     # host buffers are page-locked (wb200_host_alloc), as the bench contract asks
     inits = _ffi.pinned_empty((C, D))
     inits[...] = np.random.default_rng(SEED).normal(size=(C, D)) * wl["init_radius"]
@@ -551,17 +548,32 @@ def run_ours(args):
     stepsize = np.zeros(C)
     desc = model.desc()
     import ctypes
+    barrier()
     t0 = time.perf_counter()
     _ffi._ffi_sample_device(
-        ctypes.byref(desc), D, inits, C, SEED, 1, wl["init_radius"], None, WARMUP_ITERS,
-        WARMUP_ITERS,
+        ctypes.byref(desc), D, inits, C, SEED, 1 + rank * C, wl["init_radius"], None,
+        WARMUP_ITERS, WARMUP_ITERS,
         e2e_samp, e2e_samp, MAX_DOUBLINGS, MAX_HALVINGS, 1, 0.5, 0.1, 1.0, 1.01, 4.0, 1e-5,
         15.0, 1.0, 0.8, 0.05, 0.8, 0.9, 1e-4, 0.5, False, out, out.size, lengths, stepsize,
         None, 0, _ffi.print_callback)
     e2e_s = time.perf_counter() - t0
     st = _ffi.last_run_stats()
-    e2e_value = st["grad_evals"] / e2e_s
+    e2e_evals = float(st["grad_evals"])
+    if distributed:   # whole job: evaluations of all ranks over the slowest rank's time
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        ee = torch.tensor([e2e_evals], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ee, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_evals = float(te.item()), float(ee.item())
+    e2e_value = e2e_evals / e2e_s
     e2e_steps = (WARMUP_ITERS + e2e_samp) / ips
+    h2d_bytes, d2h_bytes = inits.nbytes * world, out.nbytes * world
+    del out, inits
+    if rank != 0:
+        if distributed:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- CPU baseline on a bounded sample of the same workload
     checker, kind = load_cpu_checker()
@@ -601,12 +613,12 @@ def run_ours(args):
         "warmup_phase": {"iters": WARMUP_ITERS, "ms": warm_ms,
                          "grad_evals_per_sec": warm_evals / (warm_ms * 1e-3)},
         "e2e": {"value": e2e_value, "unit": "grad_evals/s",
-                "h2d_bytes_per_step": int(inits.nbytes / e2e_steps),
-                "d2h_bytes_per_step": int(out.nbytes / e2e_steps),
+                "h2d_bytes_per_step": int(h2d_bytes / e2e_steps),
+                "d2h_bytes_per_step": int(d2h_bytes / e2e_steps),
                 "seconds": e2e_s, "api": "walnutpie_sample_device (C-ABI, pinned host buffers; "
                        "session set-up, initialisation, adaptive warm-up, sampling and the "
                        "overlapped read-back of every draw are all inside the timed call)",
-                "grad_evals": st["grad_evals"], "steps": e2e_steps},
+                "grad_evals": e2e_evals, "steps": e2e_steps},
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

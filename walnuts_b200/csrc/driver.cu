@@ -341,7 +341,10 @@ int walnutpie_sample_device(
     // per-chain streams are keyed by (seed + id + num_chains, chain): the same
     // mixing of seed and id as walnutpy.cpp:82
     const unsigned int run_seed = seed + id + static_cast<unsigned int>(num_chains);
-    check(wb200_session_create(model, C, run_seed, 0, &t, 0, &s, &e), e);
+    // like any CUDA library call, the run uses the calling thread's current device
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    check(wb200_session_create(model, C, run_seed, 0, &t, device, &s, &e), e);
     check(wb200_session_init(s, inits, init_radius, init_inv_metric, nullptr, &e), e);
     check(wb200_session_reserve_draws(s, static_cast<long long>(rows_per_chain), 0, &e), e);
 
