@@ -49,7 +49,12 @@ typedef void (*PRINT_CALLBACK)(const char* msg, size_t len, bool bad);
  *         function ENQUEUES, on the CUDA stream it is given, work that fills
  *         grad and lp.  Everything is device memory: theta, grad [num_chains][ld]
  *         fp64 row-major (columns >= num_params are padding), lp [num_chains].
- *         Return 0, or non-zero to abort the run with a runtime error.
+ *         Return 0.  A non-zero return is what a throwing density is to the reference
+ *         (walnutpy.cpp:162-170): during initialisation it ends the run with the
+ *         error "logp failed with code N"; inside a transition every chain of that
+ *         tick continues with logp = -inf and a zero gradient (NoExceptLogpGrad,
+ *         util.hpp:336-346), the failure is counted (wb200_session_logp_exceptions)
+ *         and reported through the print callback.
  */
 typedef int (*WB200_BATCH_LOGP_GRAD)(size_t num_chains, size_t num_params, size_t ld,
                                      const double* theta, double* grad, double* lp,
@@ -106,13 +111,34 @@ int walnutpie_sample_device(
     double* inv_metric_out, int refresh, PRINT_CALLBACK print,
     WalnutpyError** err);
 
-/* walnutpie_sample_cfunc / walnutpie_sample_bridgestan (walnutpy.cpp:134, :227):
- * exported for link compatibility; a host callback cannot feed a device batch,
- * so it fails with a `generic` error that names walnutpie_sample_device and the
- * batched device callback (WalnutModelDesc kind 4), its device-side counterpart. */
+/* walnutpie_sample_cfunc (walnutpy.cpp:134): exported for link compatibility; a
+ * host callback cannot feed a device batch, so it fails with a `generic` error that
+ * names walnutpie_sample_device and the batched device callback (WalnutModelDesc
+ * kind 4), its device-side counterpart. */
 int walnutpie_sample_cfunc(
     LOGP_CFUNC logp_c, void* data, int num_params, const double* inits,
     size_t num_chains, unsigned int seed, unsigned int id, double init_radius,
+    const double* init_inv_metric, int min_warmup_iter, int max_warmup_iter,
+    int min_sampling_iter, int max_sampling_iter, int max_trajectory_doublings,
+    int max_step_halvings, int min_micro_steps, double max_hamiltonian_error,
+    double step_size_converge_tol, double mass_converge_tol,
+    double rhat_converge_tol, double mass_init_count,
+    double mass_additive_smoothing, double max_macro_steps_target,
+    double step_size_init, double step_accept_rate_target,
+    double step_learning_rate, double step_gradient_decay,
+    double step_sq_gradient_decay, double step_stabilization,
+    double step_learn_rate_decay, bool save_warmup, double* out,
+    size_t out_size, int* final_lengths, double* stepsize_out,
+    double* inv_metric_out, int refresh, PRINT_CALLBACK print,
+    WalnutpyError** err);
+
+/* walnutpy.cpp:227-243 (STREAM_CALLBACK: thirdparty/bridgestan/bridgestan.h:400).
+ * Always fails with a `generic` error: BridgeStan models stay CPU-reference-only. */
+typedef void (*STREAM_CALLBACK)(const char* data, size_t size);
+int walnutpie_sample_bridgestan(
+    const char* bs_dll, const char* json_data, STREAM_CALLBACK callback,
+    unsigned int model_seed, const char* inits, size_t num_chains,
+    unsigned int seed, unsigned int id, double init_radius,
     const double* init_inv_metric, int min_warmup_iter, int max_warmup_iter,
     int min_sampling_iter, int max_sampling_iter, int max_trajectory_doublings,
     int max_step_halvings, int min_micro_steps, double max_hamiltonian_error,
@@ -213,6 +239,18 @@ int wb200_session_warmup_deviation(wb200_session* s, const double* sums_device,
                                    double* out_host2, WalnutpyError** err);
 int wb200_session_lp_moments(wb200_session* s, double* moments_host4,
                              WalnutpyError** err);
+
+/* sampling moments about `center`: {sum (mu - c), sum (mu - c)^2, sum var, count}.
+ * util.hpp:401-404 is a two-pass variance; a multi-GPU caller all-reduces the plain sums
+ * first and passes the global mean of the chain means as the centre, which keeps the
+ * between-chain variance free of cancellation when |lp| is large. */
+int wb200_session_lp_moments_centered(wb200_session* s, double center,
+                                      double* moments_host4, WalnutpyError** err);
+/* kind 4: batched density evaluations that returned non-zero inside a transition.  As
+ * NoExceptLogpGrad does for one chain (util.hpp:336-346), every chain of that tick went
+ * on with logp = -inf and a zero gradient.  (A failure during initialisation ends the
+ * run with "logp failed with code N", walnutpy.cpp:162-170.) */
+int wb200_session_logp_exceptions(wb200_session* s, unsigned long long* count);
 
 /* Read-back (host buffers).  draws: [C][count][D] from row `first`. */
 int wb200_session_get_draws(wb200_session* s, long long first, long long count,

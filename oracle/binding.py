@@ -209,6 +209,53 @@ class Checker:
             _dp(mass), _dp(steps)))
         return mass, steps
 
+    def init_positions_philox(self, num_chains, D, seed, radius, chain_offset=0):
+        """The device's position stream (Philox kind 2); oracle only."""
+        pos = np.zeros((num_chains, D))
+        self._check(self.lib.oracle_init_positions_philox(
+            C.c_size_t(num_chains), C.c_size_t(D), C.c_uint32(seed),
+            C.c_uint32(chain_offset), C.c_double(radius), _dp(pos)))
+        return pos
+
+    def init_mass_step_philox(self, target: Target, positions, seed, step_init,
+                              mass_in=None, smoothing=1e-5, chain_offset=0):
+        """masses(F, s) + adapt_step with the device's per-chain Philox kind-3
+        momentum; oracle only."""
+        positions = np.ascontiguousarray(positions, np.float64)
+        Cn, D = positions.shape
+        t = target.c()
+        if mass_in is not None:
+            mass_in = np.ascontiguousarray(mass_in, np.float64)
+        mass = np.zeros((Cn, D))
+        steps = np.zeros(Cn)
+        self._check(self.lib.oracle_init_mass_step_philox(
+            C.byref(t), C.c_size_t(Cn), C.c_uint32(seed), C.c_uint32(chain_offset),
+            _dp(positions), _dp(mass_in), C.c_double(smoothing), C.c_double(step_init),
+            _dp(mass), _dp(steps)))
+        return mass, steps
+
+    def warmup_controller(self, log_step, log_mass):
+        """(max_m ||(M_m - gm)/gm||_2, max(0, max_m (eps_m - gs)/gs)) of adapt.hpp:186-224
+        from per-chain log step sizes [C] and log masses [C][D]; oracle only."""
+        log_step = np.ascontiguousarray(log_step, np.float64)
+        log_mass = np.ascontiguousarray(log_mass, np.float64)
+        Cn, D = log_mass.shape
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self.lib.oracle_warmup_controller(
+            C.c_size_t(Cn), C.c_size_t(D), _dp(log_step), _dp(log_mass), C.byref(a),
+            C.byref(b)))
+        return a.value, b.value
+
+    def sampling_rhat(self, mean, var):
+        """R-hat of lp from per-chain means and unbiased variances (sampler.hpp:132-151);
+        oracle only."""
+        mean = np.ascontiguousarray(mean, np.float64)
+        var = np.ascontiguousarray(var, np.float64)
+        r = C.c_double(0)
+        self._check(self.lib.oracle_sampling_rhat(C.c_size_t(mean.size), _dp(mean), _dp(var),
+                                                  C.byref(r)))
+        return r.value
+
     def walnuts(self, target: Target, cfg: OracleConfig, seed, positions, mass,
                 steps, save_warmup=False):
         positions = np.ascontiguousarray(positions, np.float64)

@@ -279,6 +279,81 @@ int oracle_init_mass_step(const OracleTarget* target, size_t num_chains,
   });
 }
 
+namespace {
+// Random<RNG>::standard_normal (util.hpp:124-127) over one Philox kind
+struct PhiloxKindRand {
+  oracle::PhiloxRand base;
+  uint32_t kind;
+  std::vector<double> standard_normal(std::size_t n) { return base.normals(n, kind); }
+};
+}  // namespace
+
+int oracle_init_positions_philox(size_t num_chains, size_t D, uint32_t seed,
+                                 uint32_t chain_offset, double radius,
+                                 double* positions) {
+  return guarded([&] {
+    if (!(std::isfinite(radius) && radius > 0)) {
+      throw std::invalid_argument("init_scale must be finite and > 0");
+    }
+    for (size_t c = 0; c < num_chains; ++c) {
+      PhiloxRand rand(seed, chain_offset + static_cast<uint32_t>(c));
+      Vec z = rand.normals(D, kKindInit);  // config.hpp:259-268 per chain
+      for (size_t i = 0; i < D; ++i) positions[c * D + i] = z[i] * radius;
+    }
+  });
+}
+
+int oracle_init_mass_step_philox(const OracleTarget* target, size_t num_chains,
+                                 uint32_t seed, uint32_t chain_offset,
+                                 const double* positions, const double* mass_in,
+                                 double smoothing, double step_init,
+                                 double* mass_out, double* step_out) {
+  return guarded([&] {
+    const size_t D = target->D;
+    with_target(target, [&](const auto& f) {
+      for (size_t c = 0; c < num_chains; ++c) {
+        Vec pos(positions + c * D, positions + (c + 1) * D);
+        Vec mass = mass_in ? Vec(mass_in + c * D, mass_in + (c + 1) * D)
+                           : init_mass_from_gradient(f, pos, smoothing);
+        std::memcpy(mass_out + c * D, mass.data(), D * 8);
+        PhiloxKindRand rand{PhiloxRand(seed, chain_offset + static_cast<uint32_t>(c)),
+                            kKindStepInit};
+        step_out[c] = adapt_step(rand, f, pos, mass, step_init, D);
+      }
+    });
+  });
+}
+
+int oracle_warmup_controller(size_t num_chains, size_t D, const double* log_step,
+                             const double* log_mass, double* max_rel_mass,
+                             double* max_rel_step) {
+  return guarded([&] {
+    std::vector<AdaptSnapshot> latest(num_chains);
+    for (size_t m = 0; m < num_chains; ++m) {
+      latest[m].iter = 1;
+      latest[m].log_step = log_step[m];
+      latest[m].log_mass.assign(log_mass + m * D, log_mass + (m + 1) * D);
+      latest[m].mass.resize(D);
+      for (size_t d = 0; d < D; ++d) latest[m].mass[d] = std::exp(latest[m].log_mass[d]);
+    }
+    WarmupConfig w;
+    w.min_iter = 0;
+    warmup_should_stop(latest, w, max_rel_mass, max_rel_step);
+  });
+}
+
+int oracle_sampling_rhat(size_t num_chains, const double* mean, const double* var,
+                         double* r_hat) {
+  return guarded([&] {
+    std::vector<ChainStats> stats(num_chains);
+    for (size_t m = 0; m < num_chains; ++m) stats[m] = {mean[m], var[m], 1};
+    SamplingConfig s;
+    s.min_iter = 0;
+    bool evaluated = false;
+    sampling_should_stop(stats, s, r_hat, &evaluated);
+  });
+}
+
 double oracle_leapfrog_error(const OracleTarget* target, const double* theta,
                              const double* rho, const double* inv_mass,
                              double step) {

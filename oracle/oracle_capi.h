@@ -99,6 +99,28 @@ int oracle_orbit(const OracleTarget* target, const double* theta,
                  const double* rho, const double* inv_mass, double step,
                  int num_steps, double* theta_out, double* rho_out,
                  double* grad_out, double* logp_out, double* joint_out);
+/* The device's initialisation streams (include/walnuts_b200.h, wb200_session_init):
+ * positions = radius * N(0,1) from Philox (seed, chain_offset + c, iter 0, kind 2);
+ * masses as oracle_init_mass_step; the momentum of adapt_step (util.hpp:285-303) of
+ * chain c from Philox (seed, chain_offset + c, iter 0, kind 3) -- per-chain
+ * streams instead of the reference's one sequential engine (config.hpp:470-474). */
+int oracle_init_positions_philox(size_t num_chains, size_t D, uint32_t seed,
+                                 uint32_t chain_offset, double radius,
+                                 double* positions);
+int oracle_init_mass_step_philox(const OracleTarget* target, size_t num_chains,
+                                 uint32_t seed, uint32_t chain_offset,
+                                 const double* positions, const double* mass_in,
+                                 double smoothing, double step_init,
+                                 double* mass_out, double* step_out);
+/* One evaluation of the warm-up controller's convergence statistics (adapt.hpp:186-224)
+ * from per-chain snapshots {log_step[C], log_mass[C][D]}: max_m ||(M_m - gm)/gm||_2 and
+ * max(0, max_m (eps_m - gs)/gs); and of the sampling controller's R-hat of lp
+ * (sampler.hpp:132-151, util.hpp:401-404) from per-chain {mean, unbiased variance}. */
+int oracle_warmup_controller(size_t num_chains, size_t D, const double* log_step,
+                             const double* log_mass, double* max_rel_mass,
+                             double* max_rel_step);
+int oracle_sampling_rhat(size_t num_chains, const double* mean, const double* var,
+                         double* r_hat);
 int oracle_logp_grad(const OracleTarget* target, const double* theta,
                      double* logp, double* grad);
 void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -30,9 +30,10 @@ def test_library_exports_every_declared_symbol(wb):
 
 
 def test_reference_entry_points_are_present(wb):
-    """The symbols python/src/walnutpie/_ffi.py:148-257 binds (minus BridgeStan)."""
+    """The nine symbols python/src/walnutpie/_ffi.py:148-257 binds."""
     from walnuts_b200 import _ffi
-    for s in ["walnutpie_sample_cfunc", "walnutpie_separator_char", "walnutpie_ess",
+    for s in ["walnutpie_sample_cfunc", "walnutpie_sample_bridgestan",
+              "walnutpie_separator_char", "walnutpie_ess",
               "walnutpie_r_hat", "walnutpie_mcse", "walnutpie_get_error_message",
               "walnutpie_get_error_type", "walnutpie_destroy_error"]:
         assert hasattr(_ffi._lib, s)

@@ -167,3 +167,35 @@ def test_philox_normals_are_standard(oracle):
     z = oracle.philox_normals(7, 3, 11, 0, 200001)
     assert abs(z.mean()) < 0.01 and abs(z.var() - 1) < 0.01
     assert abs((z**4).mean() - 3) < 0.1
+
+
+# ---- the device's initialisation streams (oracle Philox policy) ---------------------
+def test_philox_init_positions_are_the_kind2_normals(oracle):
+    """config.hpp:259-268 per chain on the stateless stream: chain c of a session with
+    chain_offset o draws radius * N(0,1) from (seed, o + c, iteration 0, kind 2)."""
+    pos = oracle.init_positions_philox(3, 7, 99, 2.5, chain_offset=10)
+    for c in range(3):
+        np.testing.assert_array_equal(pos[c], 2.5 * oracle.philox_normals(99, 10 + c, 0, 2, 7))
+    with pytest.raises(ValueError, match="init_scale"):
+        oracle.init_positions_philox(1, 2, 1, -1.0)
+
+
+def test_philox_init_mass_and_step_follow_the_reference_rules(oracle):
+    """config.hpp:360-370 (mass = (1-s)|grad| + s) and util.hpp:285-303 (doubling while the
+    one-step energy error exceeds log 0.9, then sqrt(1/2) while below log 0.6) with the
+    momentum of chain c from Philox kind 3; the properties of tests/config_test.cpp:483-537."""
+    from oracle.binding import Target
+    D = 16
+    t = Target("std_normal", D)
+    pos = oracle.init_positions_philox(4, D, 5, 1.0)
+    mass, steps = oracle.init_mass_step_philox(t, pos, 5, 1.0, smoothing=1e-3)
+    np.testing.assert_allclose(mass, (1 - 1e-3) * np.abs(pos) + 1e-3, rtol=1e-15)
+    # converges from both sides to within a factor 2 (config_test.cpp:483-497)
+    _, lo = oracle.init_mass_step_philox(t, pos, 5, 1e-4, mass_in=np.ones((4, D)))
+    _, hi = oracle.init_mass_step_philox(t, pos, 5, 100.0, mass_in=np.ones((4, D)))
+    assert np.all(lo / hi < 2.0 + 1e-12) and np.all(hi / lo < 2.0 + 1e-12)
+    # the accepted step brackets the energy-error window with that chain's own momentum
+    for c in range(4):
+        rho = oracle.philox_normals(5, c, 0, 3, D)       # sqrt(M) = 1
+        err = oracle.leapfrog_error(t, pos[c], rho, np.ones(D), lo[c])
+        assert err >= np.log(0.6)

@@ -250,6 +250,12 @@ session_warmup_sums = _sess("wb200_session_warmup_sums", [session_p, ctypes.c_vo
 session_warmup_deviation = _sess("wb200_session_warmup_deviation",
                                  [session_p, ctypes.c_void_p, double_array])
 session_lp_moments = _sess("wb200_session_lp_moments", [session_p, double_array])
+session_lp_moments_centered = _sess("wb200_session_lp_moments_centered",
+                                    [session_p, ctypes.c_double, double_array])
+_lib.wb200_session_logp_exceptions.restype = ctypes.c_int
+_lib.wb200_session_logp_exceptions.argtypes = [session_p,
+                                               ctypes.POINTER(ctypes.c_ulonglong)]
+session_logp_exceptions = _lib.wb200_session_logp_exceptions
 session_get_draws = _sess("wb200_session_get_draws", [
     session_p, ctypes.c_longlong, ctypes.c_longlong, double_array])
 session_get_trace = _sess("wb200_session_get_trace", [
@@ -341,6 +347,8 @@ EXPORTED_SYMBOLS = [
     "wb200_session_warmup_ticks",
     "wb200_session_chain_rows", "wb200_session_summary", "wb200_session_rhat_moments", "wb200_session_warmup_sums",
     "wb200_session_warmup_deviation", "wb200_session_lp_moments",
+    "wb200_session_lp_moments_centered", "wb200_session_logp_exceptions",
+    "walnutpie_sample_bridgestan",
     "wb200_session_get_draws", "wb200_session_get_trace", "wb200_session_get_state",
     "wb200_session_device_draws", "wb200_session_counters",
     "wb200_session_last_kernel_ms", "wb200_session_timer_record",

@@ -550,4 +550,21 @@ int walnutpie_sample_cfunc(
   });
 }
 
+// walnutpy.cpp:227-243.  BridgeStan models stay CPU-reference-only (BASELINE.json
+// north_star); the symbol exists so that the reference's _ffi.py, which binds it
+// unconditionally at import (_ffi.py:235), loads this library unchanged.
+int walnutpie_sample_bridgestan(
+    const char*, const char*, STREAM_CALLBACK, unsigned int, const char*, size_t,
+    unsigned int, unsigned int, double, const double*, int, int, int, int, int, int, int,
+    double, double, double, double, double, double, double, double, double, double,
+    double, double, double, double, bool, double*, size_t, int*, double*, double*, int,
+    PRINT_CALLBACK, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    throw std::runtime_error(
+        "walnuts_b200 runs device-resident models only: BridgeStan models are evaluated "
+        "by a host library and stay with the CPU reference (walnutpie). Describe the "
+        "model with WalnutModelDesc and call walnutpie_sample_device.");
+  });
+}
+
 }  // extern "C"

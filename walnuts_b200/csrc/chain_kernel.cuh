@@ -760,7 +760,12 @@ struct ChainRunner {
 
   __device__ __forceinline__ void run(int chain) {
     const uint32_t gchain = p.chain_offset + static_cast<uint32_t>(chain);
-    if (tid == 0) sc = p.sc[chain];
+    if (tid == 0) {
+      sc = p.sc[chain];
+      // the look-ahead cache is keyed by (iteration, index) only: a slot that takes a
+      // second chain in the same launch must not see the first chain's uniforms
+      if (dc != nullptr) dc->valid = 0;
+    }
     grp.sync();
     u_iter = sc.iter;
     evals = 0;

@@ -229,6 +229,44 @@ int wb200_session_lp_moments(wb200_session* s, double* moments_host4,
   });
 }
 
+// The same payload about a caller-chosen centre: {sum (mu - c), sum (mu - c)^2, sum var,
+// count}.  util.hpp:401-404 computes the variance of the chain means in two passes; with
+// |lp| ~ 1e5 (logistic N = 100k) the one-pass form sum mu^2 - (sum mu)^2 / M cancels
+// heavily, the centred one does not.  Multi-GPU callers all-reduce the plain sums first
+// and pass the global mean of the means as the centre.
+int wb200_session_lp_moments_centered(wb200_session* s, double center,
+                                      double* moments_host4, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    ChainParams p = s->params(0, 0, false);
+    DeviceBuffer<double> buf;
+    buf.alloc(3 * static_cast<size_t>(s->C));
+    lp_stats_kernel<<<(s->C + 255) / 256, 256, 0, s->stream>>>(
+        p, buf.ptr, buf.ptr + s->C, buf.ptr + 2 * s->C);
+    WB200_CUDA(cudaGetLastError());
+    std::vector<double> h(3 * static_cast<size_t>(s->C));
+    WB200_CUDA(cudaMemcpyAsync(h.data(), buf.ptr, h.size() * 8, cudaMemcpyDeviceToHost,
+                               s->stream));
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+    s->launches += 1;
+    double sm = 0, sm2 = 0, sv = 0;
+    for (int c = 0; c < s->C; ++c) {
+      const double d = h[c] - center;
+      sm += d;
+      sm2 += d * d;
+      sv += h[s->C + c];
+    }
+    moments_host4[0] = sm; moments_host4[1] = sm2; moments_host4[2] = sv;
+    moments_host4[3] = static_cast<double>(s->C);
+  });
+}
+
+int wb200_session_logp_exceptions(wb200_session* s, unsigned long long* count) {
+  if (!s || !count) return -1;
+  *count = s->logp_exceptions;
+  return 0;
+}
+
 int wb200_philox(const uint32_t* ctr_key6, size_t n, uint32_t* out4, WalnutpyError** err) {
   return catch_exceptions(err, [&] {
     DeviceBuffer<uint32_t> in, out;
@@ -365,6 +403,19 @@ int walnutpie_sample_device(
       }
     };
 
+    // handlers.hpp:30-36 (print_exception), for a batched density: one line per failed
+    // batch evaluation; the chains went on with logp = -inf (util.hpp:336-346)
+    size_t exceptions_reported = 0;
+    auto report_exceptions = [&] {
+      for (; exceptions_reported < s->exception_log.size(); ++exceptions_reported) {
+        const auto& ex = s->exception_log[exceptions_reported];
+        std::stringstream ss;
+        ss << "Chains [1-" << C << "]:Error evaluating the log density during tick "
+           << ex.first + 1 << ": logp failed with code " << ex.second << std::endl;
+        say(ss.str());
+      }
+    };
+
     // Draw read-back overlaps sampling: the rows a block of iterations stored are
     // copied on a second stream while the next block runs (one strided 3-D copy
     // per block: D doubles x rows x chains).  The copy of block k is issued
@@ -461,6 +512,7 @@ int walnutpie_sample_device(
         mark_block(warm_done + n);
       }
       progress(warm_done, warm_done + n, true);
+      report_exceptions();
       warm_done += n;
       interrupt.throw_if_interrupted();  // adapt.hpp:227
       if (warm_done >= min_warmup_iter && warm_done < max_warmup_iter) {
@@ -483,11 +535,15 @@ int walnutpie_sample_device(
       flush_pending();
       mark_block(saved_warm + samp_done + n);
       progress(warm_done + samp_done, warm_done + samp_done + n, false);
+      report_exceptions();
       samp_done += n;
       interrupt.throw_if_interrupted();  // sampler.hpp:154
       if (samp_done >= min_sampling_iter && samp_done < max_sampling_iter) {
-        double m[4];
-        check(wb200_session_lp_moments(s, m, &e), e);
+        // util.hpp:401-404 is a two-pass variance: first the mean of the chain means,
+        // then the squared deviations about it
+        double m0[4], m[4];
+        check(wb200_session_lp_moments(s, m0, &e), e);
+        check(wb200_session_lp_moments_centered(s, m0[0] / m0[3], m, &e), e);
         const double M = m[3];
         const double var_of_means = (m[1] - m[0] * m[0] / M) / (M - 1.0);
         const double mean_of_vars = m[2] / M;

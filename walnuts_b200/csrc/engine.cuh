@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/walnuts_b200.h"
@@ -154,6 +155,10 @@ struct wb200_session {
   bool trace = false;
   bool ragged = false;  // a free-running phase has stored draws: per-chain row counts
   unsigned long long launches = 0;
+  // kind 4: batched density evaluations that failed inside a transition and were
+  // replaced by logp = -inf, grad = 0 (util.hpp:336-346); {tick, return code} of the first
+  unsigned long long logp_exceptions = 0;
+  std::vector<std::pair<unsigned long long, int>> exception_log;
 
   wb200::DeviceBuffer<double> theta, inv_mass, est, tparam, scratch, draws,
       lp_out, step_out, im_out, red, adam_tab, sums;

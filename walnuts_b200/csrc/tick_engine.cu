@@ -337,7 +337,22 @@ __global__ void zero_padding_kernel(double* G, int C, int D, int ld) {
   }
 }
 
-static void tick_gradient(wb200_session& s, const TickParams& tp) {
+// NoExceptLogpGrad (util.hpp:336-346) for a whole batch: every chain of the tick sees
+// logp = -inf and a zero gradient
+__global__ void failed_batch_kernel(double* G, double* LP, int C, int ld) {
+  const long long n = static_cast<long long>(C) * ld;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    G[i] = 0.0;
+    if (i < C) LP[i] = -INFINITY;
+  }
+}
+
+// `sampling` = inside a transition, where the reference wraps the density in
+// NoExceptLogpGrad (adaptive_walnuts.hpp:205-215, walnuts.hpp:637-650); the
+// initialisation (config.hpp:360-382, :469-476) calls it bare, so a failure there ends
+// the run (walnutpy.cpp:162-170: "logp failed with code N").
+static void tick_gradient(wb200_session& s, const TickParams& tp, bool sampling) {
   TickEngine& e = *s.tick;
   if (s.kind == kLogistic) {
     e.logistic->evaluate(e.TH.ptr, e.G.ptr, e.LP.ptr, s.stream);
@@ -347,8 +362,15 @@ static void tick_gradient(wb200_session& s, const TickParams& tp) {
                               static_cast<size_t>(s.ld), e.TH.ptr, e.G.ptr, e.LP.ptr,
                               static_cast<void*>(s.stream), e.batch_data);
     if (rc != 0) {
-      throw std::runtime_error("the batched log density callback failed with code " +
-                               std::to_string(rc));
+      if (!sampling) {
+        throw std::runtime_error("logp failed with code " + std::to_string(rc));
+      }
+      const long long n = static_cast<long long>(s.C) * s.ld;
+      failed_batch_kernel<<<static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 8)),
+                            256, 0, s.stream>>>(e.G.ptr, e.LP.ptr, s.C, s.ld);
+      WB200_CUDA(cudaGetLastError());
+      s.logp_exceptions += 1;
+      if (s.exception_log.size() < 64) s.exception_log.push_back({e.ticks, rc});
     }
     if (s.ld != s.D) {
       zero_padding_kernel<<<(s.C + 255) / 256, 256, 0, s.stream>>>(e.G.ptr, s.C, s.D, s.ld);
@@ -433,7 +455,7 @@ void tick_init(wb200_session& s, bool have_mass, bool have_steps, bool have_posi
   const int grid = (s.C + s.shape.chains_per_cta - 1) / s.shape.chains_per_cta;
   WB200_TICK_SHAPE(s.shape, WB200_TICK_INIT_POS);
   WB200_CUDA(cudaGetLastError());
-  tick_gradient(s, ip.tp);
+  tick_gradient(s, ip.tp, false);
   WB200_TICK_SHAPE(s.shape, WB200_TICK_INIT_STATE);
   WB200_CUDA(cudaGetLastError());
   s.launches += 2;
@@ -441,7 +463,7 @@ void tick_init(wb200_session& s, bool have_mass, bool have_steps, bool have_posi
     for (int it = 0; it < 700; ++it) {
       WB200_CUDA(cudaMemsetAsync(e.active.ptr, 0, sizeof(int), s.stream));
       WB200_TICK_SHAPE(s.shape, WB200_TICK_SEARCH_POST);
-      tick_gradient(s, ip.tp);
+      tick_gradient(s, ip.tp, false);
       WB200_TICK_SHAPE(s.shape, WB200_TICK_SEARCH_UPDATE);
       WB200_CUDA(cudaGetLastError());
       s.launches += 2;
@@ -463,7 +485,7 @@ void tick_run(wb200_session& s, int n_iter, int adapt, bool store) {
     s.launches += 1;
     e.ticks += 1;
     if (read_active(s) == 0) break;
-    tick_gradient(s, tp);
+    tick_gradient(s, tp, true);
   }
   WB200_CUDA(cudaEventRecord(s.ev1, s.stream));
   if (store) s.rows_written += n_iter;
@@ -494,7 +516,7 @@ void tick_run_ticks(wb200_session& s, int n_ticks, int adapt, bool store) {
   for (int t = 0; t < n_ticks; ++t) {
     WB200_TICK_SHAPE(s.shape, WB200_TICK_RUN);
     WB200_CUDA(cudaGetLastError());
-    tick_gradient(s, tp);
+    tick_gradient(s, tp, true);
     s.launches += 1;
     e.ticks += 1;
   }

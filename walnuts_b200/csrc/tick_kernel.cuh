@@ -182,6 +182,9 @@ struct TickRunner {
     const uint32_t gchain = p.chain_offset + static_cast<uint32_t>(chain);
     ChainScalars sc = p.sc[chain];
     TickState st = tp.ts[chain];
+    // every warp of the group holds its copy of the records before thread 0 may write
+    // them back at the end of the tick (the mid-integration path has no other barrier)
+    grp.sync();
     if (st.pc == PC_DONE) return;
     vb = tp.vecs + static_cast<long long>(chain) * tp.vec_stride;
     double* th_row = tp.TH + static_cast<long long>(chain) * ld;

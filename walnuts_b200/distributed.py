@@ -32,7 +32,13 @@ def shard(total_chains: int, world: int, rank: int) -> Tuple[int, int]:
 
 def _all_reduce(t: torch.Tensor, op) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(t, op=op)
+        if t.is_cuda and dist.get_backend() == "gloo":
+            # CPU rendezvous over device sessions (tests on a single-GPU box)
+            h = t.cpu()
+            dist.all_reduce(h, op=op)
+            t.copy_(h)
+        else:
+            dist.all_reduce(t, op=op)
     return t
 
 
@@ -78,7 +84,13 @@ class DistributedController:
 
     # -- sampling -------------------------------------------------------------
     def lp_rhat(self) -> float:
-        m = self.s.local_lp_moments()                # tensor [4]
+        # util.hpp:401-404 is a two-pass variance: first the global mean of the chain
+        # means, then the squared deviations about it (no cancellation for large |lp|)
+        m0 = self.s.local_lp_moments()               # tensor [4]
+        _all_reduce(m0, dist.ReduceOp.SUM)
+        if float(m0[3]) < 2:
+            return float("nan")
+        m = self.s.local_lp_moments(float(m0[0]) / float(m0[3]))
         _all_reduce(m, dist.ReduceOp.SUM)
         return rhat_from_moments(m)
 
@@ -123,8 +135,9 @@ class SessionAdapter:
         out = self.sess.warmup_deviation(sums.data_ptr())
         return torch.tensor(out, dtype=torch.float64, device=self.device)
 
-    def local_lp_moments(self):
-        return torch.tensor(self.sess.lp_moments(), dtype=torch.float64, device=self.device)
+    def local_lp_moments(self, center=None):
+        return torch.tensor(self.sess.lp_moments(center), dtype=torch.float64,
+                            device=self.device)
 
 
 def combine_dimension_moments(mean_c: np.ndarray, var_c: np.ndarray,

@@ -97,7 +97,11 @@ def batch_callback(num_params: int, fn) -> DeviceModel:
     once per lock-step tick with raw device pointers (fp64; ``theta`` / ``grad`` are
     ``[num_chains][ld]`` row-major, ``lp`` is ``[num_chains]``) and the CUDA stream on which
     it must enqueue the work that fills ``grad`` and ``lp``.  An exception raised inside
-    ``fn`` aborts the run and is re-raised by the sampler call."""
+    ``fn`` is handled like the reference's trampoline handles one (pyfunc.py:32-42,
+    util.hpp:336-346): it is printed and the call returns 1; during initialisation that
+    ends the run (the sampler call re-raises the exception), inside a transition every
+    chain of the tick continues with ``logp = -inf`` and a zero gradient.  The last
+    exceptions are kept in ``model.errors``."""
     model = DeviceModel("batch_callback", int(num_params))
 
     def trampoline(C, D, ld, theta, grad, lp, stream, _data):
@@ -105,7 +109,9 @@ def batch_callback(num_params: int, fn) -> DeviceModel:
             fn(C, D, ld, theta, grad, lp, stream)
             return 0
         except BaseException as exc:  # must not propagate through the C frames
-            model.errors.append(exc)
+            print(exc)
+            if len(model.errors) < 16:
+                model.errors.append(exc)
             return 1
 
     model.callback = BATCH_LOGP_GRAD(trampoline)

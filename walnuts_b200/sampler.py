@@ -54,8 +54,10 @@ def _reraise_callback_errors(model):
     try:
         yield
     except RuntimeError as failure:
-        if errors:
-            exc = errors.pop(0)
+        # only a failure during initialisation ends a run (walnutpy.cpp:162-170); inside a
+        # transition the chains go on with logp = -inf and the exception is only printed
+        if errors and str(failure).startswith("logp failed with code"):
+            exc = errors[0]
             errors.clear()
             raise exc from failure
         raise
@@ -346,10 +348,23 @@ class Session:
     def warmup_sums(self, sums_device_ptr: int):
         _ffi.session_warmup_sums(self._h, sums_device_ptr)
 
-    def lp_moments(self):
+    def lp_moments(self, center: Optional[float] = None):
+        """{sum mu, sum mu^2, sum var, chains} of the per-chain Welford moments of lp
+        (sampler.hpp:132-151); with ``center`` the first two are taken about it (the
+        second pass of util.hpp:401-404)."""
         out = np.zeros(4)
-        _ffi.session_lp_moments(self._h, out)
+        if center is None:
+            _ffi.session_lp_moments(self._h, out)
+        else:
+            _ffi.session_lp_moments_centered(self._h, float(center), out)
         return out
+
+    def logp_exceptions(self) -> int:
+        """Batched density evaluations that failed inside a transition and were replaced
+        by logp = -inf, grad = 0 (util.hpp:336-346)."""
+        n = ctypes.c_ulonglong(0)
+        _ffi.session_logp_exceptions(self._h, ctypes.byref(n))
+        return n.value
 
 
 def orbit(model: DeviceModel, theta, rho, inv_mass, step: float, num_steps: int):
