@@ -271,9 +271,11 @@ template <int T, int K>
 struct FunnelTarget {
   double half_dm1;
   bool owner;  // owns element 0 (v)
+  int room;    // D - 2 * tid: element slot 2 * k * T + v of this thread is real iff < room
   __device__ __forceinline__ void init(const ChainParams& p, int tid) {
     half_dm1 = 0.5 * static_cast<double>(p.D - 1);
     owner = (tid == 0);
+    room = p.D - 2 * tid;
   }
   __device__ __forceinline__ void grad(const double (&th)[K][2], double (&g)[K][2],
                                        double& lp_part, Group<T>& grp) const {
@@ -294,7 +296,10 @@ struct FunnelTarget {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
-      for (int v = 0; v < 2; ++v) g[k][v] = -__dmul_rn(th[k][v], ev);
+      for (int v = 0; v < 2; ++v) {
+        // padding slots hold theta = 0: 0 * exp(-v0) must stay 0 when exp overflows
+        g[k][v] = (2 * k * T + v < room) ? -__dmul_rn(th[k][v], ev) : 0.0;
+      }
     }
     if (owner) {
       double lp = __dadd_rn(__dadd_rn(-__dmul_rn(v0, v0) / 18.0,

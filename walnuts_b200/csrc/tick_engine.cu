@@ -58,6 +58,19 @@ __device__ __forceinline__ int group_setup(Group<T>& grp, double* red_smem) {
   }
 }
 
+// register slots beyond D (V::load fills them with 0) carry a unit mass so that the
+// quotients of the step search stay finite
+template <int T, int K>
+__device__ __forceinline__ void unit_padding(double (&m)[K][2], int tid, int D) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      if (2 * (tid + k * T) + v >= D) m[k][v] = 1.0;
+    }
+  }
+}
+
 // gradient stage for element-wise targets: G, LP at the posted positions TH
 template <template <int, int> class TargetT, int T, int K, int CTA>
 __global__ void __launch_bounds__(CTA) elementwise_grad_kernel(const TickParams tp) {
@@ -233,6 +246,7 @@ __global__ void __launch_bounds__(CTA) tick_search_post_kernel(const TickInitPar
   V::load(vb + static_cast<long long>(TV_CUR_G) * ld, ld, tid, g);
   V::load(vb + static_cast<long long>(TV_RHO) * ld, ld, tid, rho);
   V::load(ip.mass + off, ld, tid, mass);
+  unit_padding<T, K>(mass, tid, p.D);
   const double s = st.step, hs = 0.5 * s;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -264,6 +278,7 @@ __global__ void __launch_bounds__(CTA) tick_search_update_kernel(const TickInitP
   V::load(ip.tp.G + off, ld, tid, g1);
   V::load(vb + static_cast<long long>(TV_RHO) * ld, ld, tid, rho);
   V::load(ip.mass + off, ld, tid, mass);
+  unit_padding<T, K>(mass, tid, p.D);
   const double hs = 0.5 * st.step;
   double kin = 0.0;
 #pragma unroll
