@@ -26,7 +26,7 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
                 int n_warmup, int n_sampling, double* draws, double* lp, int* depth,
                 double* step_trace, double* im_trace, double* inv_mass_out,
                 double* step_out, int* min_micro_out, unsigned long long* evals) {
-  const int ld = (D + 1) & ~1;
+  const int ld = 2 * kEmuK;  // rows padded to the group's element slots
   const int total = n_warmup + n_sampling;
   std::vector<double> theta(ld, 0.0), inv_mass(ld, 0.0), est(4 * ld, 0.0), tp(ld, 0.0);
   std::vector<double> scratch(static_cast<size_t>(scratch_doubles(t.max_depth, ld)), 0.0);
@@ -64,11 +64,13 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   ChainScalars sc_shared{};  // stands in for the per-chain record in shared memory
   DecisionCache decision_cache{};
   AdamQueue adam_queue{};
+  std::vector<double> chain_smem(static_cast<size_t>(chain_smem_doubles(ld)), 0.0);
   using Target = TargetT<1, kEmuK>;
   // warm-up launch
   p.n_iter = n_warmup; p.adapt = 1; p.draw_base = 0;
   {
-    ChainRunner<Target, 1, kEmuK, true> r(p, grp, scratch.data(), sc_shared);
+    ChainRunner<Target, 1, kEmuK, true> r(p, grp, scratch.data(), sc_shared,
+                                           chain_smem.data());
     r.dc = &decision_cache;
     r.aq = &adam_queue;
     if (n_warmup > 0) r.run(0);
@@ -84,7 +86,8 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   std::memcpy(inv_mass_out, inv_mass.data(), D * 8);
   p.n_iter = n_sampling; p.adapt = 0; p.draw_base = n_warmup; p.im_out = nullptr;
   {
-    ChainRunner<Target, 1, kEmuK, false> r(p, grp, scratch.data(), sc_shared);
+    ChainRunner<Target, 1, kEmuK, false> r(p, grp, scratch.data(), sc_shared,
+                                            chain_smem.data());
     r.dc = &decision_cache;
     if (n_sampling > 0) r.run(0);
   }
@@ -136,7 +139,7 @@ static void run_tick(const EmuTuning& t, int D, const double* tparam, uint32_t s
   // warm_ticks / samp_ticks >= 0: that phase runs free (exactly that many ticks, as
   // tick_run_ticks does) instead of an iteration quota; n_warmup + n_sampling is then
   // only the draw capacity and rows_out = {rows after warm-up, rows at the end}.
-  const int ld = (D + 1) & ~1;
+  const int ld = 2 * kEmuK;  // rows padded to the group's element slots
   const int total = n_warmup + n_sampling;
   const int nvec = tick_vectors(t.max_depth);
   std::vector<double> theta(ld, 0.0), inv_mass(ld, 0.0), est(4 * ld, 0.0), tp_(ld, 0.0);

@@ -9,6 +9,7 @@ CUDA library is missing the import fails.
 from __future__ import annotations
 
 import ctypes
+import os
 import functools
 import sys
 from pathlib import Path
@@ -17,7 +18,9 @@ import numpy as np
 from numpy.ctypeslib import ndpointer
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libwalnuts_b200.so"
+# WB200_LIB: a build variant of the same library (kernel experiments, csrc/Makefile VARIANT=)
+LIB_PATH = Path(os.environ["WB200_LIB"]) if os.environ.get("WB200_LIB") else \
+    _HERE / "libwalnuts_b200.so"
 
 if not LIB_PATH.exists():
     raise ImportError(

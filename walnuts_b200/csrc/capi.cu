@@ -10,6 +10,7 @@
 
 #include "../host/config.hpp"
 #include "engine.cuh"
+#include "stream.cuh"
 
 namespace wb200 {
 // walnutpy.cpp:36-62: the builders validate exactly like the reference
@@ -106,13 +107,15 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
     s->kind = model->kind;
     s->D = model->D;
     s->N = model->N;
-    s->ld = (model->D + 1) & ~1;  // even row stride: 16-byte aligned double2
     s->C = static_cast<int>(num_chains);
     s->seed = seed;
     s->chain_offset = chain_offset;
     s->tuning = *tuning;
     if (s->tuning.publish_stride <= 0) s->tuning.publish_stride = 5;
     s->shape = shape_for_dim(s->D);
+    // rows are padded to the 2*T*K element slots of a chain's group: vector loads and
+    // stores need no bounds checks (padding: theta = rho = grad = 0, unit metric)
+    s->ld = 2 * s->shape.T * s->shape.K;
     WB200_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     WB200_CUDA(cudaEventCreate(&s->ev0));
     WB200_CUDA(cudaEventCreate(&s->ev1));
@@ -160,7 +163,7 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
       return;
     }
     // slots: resident groups of the chain kernel
-    const int occ = occupancy_for(s->kind, s->shape);
+    const int occ = occupancy_for(s->kind, s->shape, s->ld);
     int sms = 0;
     WB200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const int max_grid = occ * sms;
@@ -181,6 +184,7 @@ void wb200_session_destroy(wb200_session* s) {
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->tick) tick_destroy(*s);
+  if (s->acc) stream_end(*s);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->tm0) cudaEventDestroy(s->tm0);
@@ -294,8 +298,23 @@ int wb200_session_freeze(wb200_session* s, WalnutpyError** err) {
 int wb200_session_sample(wb200_session* s, int n_iter, int store, WalnutpyError** err) {
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));
-    check_room(s, n_iter, store);
+    if (!s->initialised) throw std::runtime_error("session is not initialised");
     if (!s->frozen) throw std::runtime_error("sample before freeze");
+    if (s->acc && store) {
+      // streaming summaries: the draw buffer is a staging block that every launch
+      // refills from row 0 and stream_update folds into the running sums
+      if (n_iter < 0) throw std::invalid_argument("n_iter must be non-negative");
+      for (int done = 0; done < n_iter;) {
+        const int n = static_cast<int>(std::min<long long>(n_iter - done, s->draw_cap));
+        s->rows_written = 0;
+        if (s->tick) tick_run(*s, n, 0, true);
+        else launch_chains(*s, n, 0, true);
+        stream_update(*s, nullptr, n);
+        done += n;
+      }
+      return;
+    }
+    check_room(s, n_iter, store);
     if (n_iter > 0) {
       if (s->tick) tick_run(*s, n_iter, 0, store != 0);
       else launch_chains(*s, n_iter, 0, store != 0);
@@ -311,6 +330,15 @@ int wb200_session_sample_ticks(wb200_session* s, int n_ticks, int store,
     if (!s->frozen) throw std::runtime_error("sample before freeze");
     if (n_ticks < 0) throw std::invalid_argument("n_ticks must be non-negative");
     if (store && s->draw_cap == 0) throw std::runtime_error("reserve draws first");
+    if (s->acc && store) {
+      // streaming: chains restart their staging rows at 0; a chain that fills the block
+      // before the ticks are over idles until the next call (reserve generously)
+      s->rows_written = 0;
+      tick_run_ticks(*s, n_ticks, 0, true);
+      tick_take_rows(*s, s->acc_rows());
+      stream_update(*s, s->acc_rows(), 0);
+      return;
+    }
     tick_run_ticks(*s, n_ticks, 0, store != 0);
     if (store) s->ragged = true;
   });
@@ -508,7 +536,9 @@ int wb200_orbit(const WalnutModelDesc* model, size_t num_chains,
                 WalnutpyError** err) {
   return catch_exceptions(err, [&] {
     require_gpu();
-    const int D = model->D, ld = (D + 1) & ~1;
+    const int D = model->D;
+    const LaunchShape shape = shape_for_dim(D);
+    const int ld = 2 * shape.T * shape.K;
     const size_t C = num_chains, CL = C * ld;
     DeviceBuffer<double> th, rh, im, g, lp, jt, tp;
     th.alloc(CL); rh.alloc(CL); im.alloc(CL); g.alloc(CL); lp.alloc(C); jt.alloc(C);

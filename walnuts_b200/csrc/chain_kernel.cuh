@@ -115,6 +115,14 @@ __host__ __device__ inline long long scratch_doubles(int max_depth, int ld) {
   return static_cast<long long>(scratch_vectors(max_depth)) * ld + (1ll << max_depth);
 }
 
+// Shared memory of one resident chain: the macro-step start state (theta, rho, grad) --
+// the previous leaf, which the halving ladder restarts from and odd leaves take their
+// U-turn dots against -- and the (logW, lp) stack of finished sub-trees.  Parking the
+// start state here instead of in a second set of registers removes the register copies
+// between the two roles (a third of the executed instructions of the round-1 kernel
+// were MOVs) and a third of the register footprint.
+__host__ __device__ inline int chain_smem_doubles(int ld) { return 3 * ld + 2 * kMaxDepth; }
+
 // ---------------------------------------------------------------------------
 // T cooperating threads.  sum(): all-reduce, bitwise identical in every thread.
 // bcast(): values computed by the control warp reach every thread.
@@ -137,9 +145,53 @@ struct Group {
     }
   }
 
+  // All-reduce of N partial sums.  The warp stage halves the number of VALUES a lane
+  // carries at every butterfly step where it can (lanes with the xor bit set keep the upper
+  // half of the values, the others the lower half), so N = 4 costs 7 shuffled doubles
+  // instead of 20: after the steps, lane group l / (32 / N) holds the warp total of value
+  // l / (32 / N).  Warps then meet in shared memory (W > 1) or the group leaders'
+  // totals are broadcast by shuffle (one warp).
   template <int N>
   __device__ __forceinline__ void sum(double (&v)[N]) {
     static_assert(N <= kRedStride, "too many values");
+    if constexpr (T >= 32 && (N == 2 || N == 4)) {
+      double a = v[0], b = v[N > 2 ? 1 : 0];
+      if constexpr (N == 4) {
+        const bool hi16 = (lane & 16) != 0;
+        a = hi16 ? v[2] : v[0];
+        b = hi16 ? v[3] : v[1];
+        a += __shfl_xor_sync(0xffffffffu, hi16 ? v[0] : v[2], 16);
+        b += __shfl_xor_sync(0xffffffffu, hi16 ? v[1] : v[3], 16);
+        const bool hi8 = (lane & 8) != 0;
+        const double keep = hi8 ? b : a, give = hi8 ? a : b;
+        a = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+      } else {
+        const bool hi16 = (lane & 16) != 0;
+        a = (hi16 ? v[1] : v[0]) + __shfl_xor_sync(0xffffffffu, hi16 ? v[0] : v[1], 16);
+        a += __shfl_xor_sync(0xffffffffu, a, 8);
+      }
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      constexpr int kGroup = 32 / N;  // lanes holding the total of one value
+      if constexpr (W > 1) {
+        double* buf = red + parity * ((W + 1) * kRedStride);
+        if ((lane & (kGroup - 1)) == 0) buf[warp * kRedStride + lane / kGroup] = a;
+        __syncthreads();
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          double s = buf[n];
+#pragma unroll
+          for (int w = 1; w < W; ++w) s += buf[w * kRedStride + n];
+          v[n] = s;
+        }
+        parity ^= 1;
+      } else {
+#pragma unroll
+        for (int n = 0; n < N; ++n) v[n] = __shfl_sync(0xffffffffu, a, n * kGroup);
+      }
+      return;
+    }
     if constexpr (T >= 32) {
 #pragma unroll
       for (int n = 0; n < N; ++n) {
@@ -191,31 +243,25 @@ constexpr int group_smem_doubles() {
 }
 
 // ---------------------------------------------------------------------------
+// Rows are padded to the 2*T*K element slots of their group (row_stride()), so loads and
+// stores need no bounds checks; padding holds theta = rho = grad = 0 and a unit metric.
 template <int T, int K>
 struct Vec {
   // element pair owned by this thread in chunk k: 2*(tid + k*T), +1
-  __device__ __forceinline__ static void load(const double* row, int ld, int tid,
+  __device__ __forceinline__ static void load(const double* row, int, int tid,
                                               double (&x)[K][2]) {
+    const double2* r2 = reinterpret_cast<const double2*>(row) + tid;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      int e = 2 * (tid + k * T);
-      if (e < ld) {
-        double2 v = *reinterpret_cast<const double2*>(row + e);
-        x[k][0] = v.x; x[k][1] = v.y;
-      } else {
-        x[k][0] = 0.0; x[k][1] = 0.0;
-      }
+      const double2 v = r2[k * T];
+      x[k][0] = v.x; x[k][1] = v.y;
     }
   }
-  __device__ __forceinline__ static void store(double* row, int ld, int tid,
+  __device__ __forceinline__ static void store(double* row, int, int tid,
                                                const double (&x)[K][2]) {
+    double2* r2 = reinterpret_cast<double2*>(row) + tid;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      int e = 2 * (tid + k * T);
-      if (e < ld) {
-        *reinterpret_cast<double2*>(row + e) = make_double2(x[k][0], x[k][1]);
-      }
-    }
+    for (int k = 0; k < K; ++k) r2[k * T] = make_double2(x[k][0], x[k][1]);
   }
   __device__ __forceinline__ static void copy(double (&dst)[K][2],
                                               const double (&src)[K][2]) {
@@ -559,13 +605,15 @@ struct ChainRunner {
   Target tgt;
   double* scr;   // this slot's scratch
   int ld, tid;
-  // registers
-  double th[K][2], rho[K][2], g[K][2];       // live integrator state / newest leaf
-  double ths[K][2], rhos[K][2], gs[K][2];    // macro-step start = previous leaf
+  // registers: the live integrator state / newest leaf, and the metric
+  double th[K][2], rho[K][2], g[K][2];
   double im[K][2];
+  // shared memory of this chain (chain_smem_doubles): the macro-step start state =
+  // previous leaf, and the stack of finished sub-trees
+  double* s_ths; double* s_rhos; double* s_gs;
+  double* st_logW; double* st_lp;
   // per-chain scalars live in shared memory; read-modify-write only by thread 0,
-  // read by others only after a barrier.  The few values every thread needs for
-  // its own vector work are mirrored in registers (u_*), updated redundantly.
+  // read by others only after a barrier.
   ChainScalars& sc;
   DecisionCache* dc = nullptr;  // shared memory, control warp only (null: no look-ahead)
   AdamQueue* aq = nullptr;      // shared memory; the entries live behind the scratch vectors
@@ -577,11 +625,29 @@ struct ChainRunner {
   unsigned long long evals;
 
   __device__ ChainRunner(const ChainParams& p_, Group<T>& grp_, double* scr_,
-                         ChainScalars& sc_)
-      : p(p_), grp(grp_), scr(scr_), ld(p_.ld), tid(grp_.tid), sc(sc_) {}
+                         ChainScalars& sc_, double* chain_smem)
+      : p(p_), grp(grp_), scr(scr_), ld(p_.ld), tid(grp_.tid), sc(sc_) {
+    s_ths = chain_smem;
+    s_rhos = chain_smem + p_.ld;
+    s_gs = chain_smem + 2 * p_.ld;
+    st_logW = chain_smem + 3 * p_.ld;
+    st_lp = st_logW + kMaxDepth;
+  }
 
   __device__ __forceinline__ double* sv(int v) const {
     return scr + static_cast<long long>(v) * ld;
+  }
+
+  // the live state becomes / is restored from the macro-step start state
+  __device__ __forceinline__ void park_start() {
+    V::store(s_ths, ld, tid, th);
+    V::store(s_rhos, ld, tid, rho);
+    V::store(s_gs, ld, tid, g);
+  }
+  __device__ __forceinline__ void load_start() {
+    V::load(s_ths, ld, tid, th);
+    V::load(s_rhos, ld, tid, rho);
+    V::load(s_gs, ld, tid, g);
   }
 
   // one leapfrog micro-step, walnuts.hpp:329-332
@@ -607,7 +673,7 @@ struct ChainRunner {
 
   // n micro-steps from the live state; logp and joint (util.hpp:220-223).  With
   // `with_dots` the U-turn dots (:192-201) of the end state against the start
-  // state (ths, rhos) ride in the same reduction.
+  // state (shared memory) ride in the same reduction.
   __device__ __forceinline__ void integrate(int n, double h, double& lp, double& H,
                                             bool with_dots, double& dot_new,
                                             double& dot_old) {
@@ -625,6 +691,9 @@ struct ChainRunner {
     }
     if (with_dots) {
       double a = 0.0, b = 0.0;
+      double ths[K][2], rhos[K][2];
+      V::load(s_ths, ld, tid, ths);
+      V::load(s_rhos, ld, tid, rhos);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
 #pragma unroll
@@ -648,9 +717,9 @@ struct ChainRunner {
     }
   }
 
-  // macro_step (:307-345) + reversible (:254-279) from (ths, rhos, gs, Hs).
-  // On success the new leaf is in (th, rho, g) with (lpn, Hn); (ths, rhos, gs)
-  // still hold the start state.
+  // macro_step (:307-345) + reversible (:254-279).  On entry the live registers AND the
+  // parked start state hold the D-end of the span; on success the new leaf is in
+  // (th, rho, g) with (lpn, Hn) and the parked state still is the start.
   __device__ __forceinline__ bool macro_step(int dir, double step, int min_micro,
                                              double Hs, double& lpn, double& Hn,
                                              bool with_dots, double& dot_new,
@@ -664,7 +733,6 @@ struct ChainRunner {
     bool reversing = false, first_rev = true;
     int cur_n = n;
     double cur_h = h;
-    V::copy(th, ths); V::copy(rho, rhos); V::copy(g, gs);
     while (true) {
       double lp2, H2, d_new = 0.0, d_old = 0.0;
       integrate(cur_n, cur_h, lp2, H2, with_dots && !reversing, d_new, d_old);
@@ -678,7 +746,7 @@ struct ChainRunner {
           if (rung >= p.max_halvings) return false;
           n *= 2; h *= 0.5;
           cur_n = n; cur_h = h;
-          V::copy(th, ths); V::copy(rho, rhos); V::copy(g, gs);
+          load_start();
           continue;
         }
         if (tid == 0) sc.rung_sum += rung;
@@ -763,6 +831,13 @@ struct ChainRunner {
     logW = r[1];
   }
 
+  // copy one vector between rows (parked state / scratch), through registers
+  __device__ __forceinline__ void copy_row(double* dst, const double* src) {
+    double t[K][2];
+    V::load(src, ld, tid, t);
+    V::store(dst, ld, tid, t);
+  }
+
   __device__ __forceinline__ void run(int chain) {
     const uint32_t gchain = p.chain_offset + static_cast<uint32_t>(chain);
     if (tid == 0) {
@@ -777,13 +852,25 @@ struct ChainRunner {
     tgt.init(p, tid);
     double* theta_row = p.theta + static_cast<long long>(chain) * ld;
     // the adaptation scalars (estimator weight, min-micro controller, warm-up count) stay
-    // in shared memory and are read where they are used: mirrored in registers they
-    // stayed live through the macro-step loop and pushed whole state arrays out to
-    // local memory
+    // in shared memory and are read where they are used
     auto est_row = [&]() { return p.est + static_cast<long long>(chain) * 4 * ld; };
-    double cur[K][2];  // current position of the chain
-    V::load(theta_row, ld, tid, cur);
-    if (!ADAPT) V::load(p.inv_mass + static_cast<long long>(chain) * ld, ld, tid, im);
+    // the chain's current position lives in scratch row A_SEL between transitions
+    copy_row(sv(A_SEL), theta_row);
+    if (!ADAPT) {
+      V::load(p.inv_mass + static_cast<long long>(chain) * ld, ld, tid, im);
+      // Cholesky factor of the fixed metric, sqrt().inverse() (walnuts.hpp:647): constant
+      // over the launch, so its square roots and divisions are paid once per chain
+      double c[K][2];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const bool pad = 2 * (tid + k * T) + v >= p.D;
+          c[k][v] = div_noinline(1.0, sqrt_noinline(pad ? 1.0 : im[k][v]));
+        }
+      }
+      V::store(sv(A_IM), ld, tid, c);
+    }
 
     for (int it = 0; it < p.n_iter; ++it) {
       const uint32_t iter = u_iter;
@@ -812,24 +899,26 @@ struct ChainRunner {
                  ld, tid, im);
       }
       // ---- momentum refresh rho = chol_mass * z  (walnuts.hpp:528-529)
-      V::copy(th, cur);
+      V::load(sv(A_SEL), ld, tid, th);
+      {
+        double c[K][2];
+        if (!ADAPT) V::load(sv(A_IM), ld, tid, c);
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const int j = tid + k * T;
-        double z0 = 0.0, z1 = 0.0;
-        if (2 * j < p.D) {
-          const double2 z = momentum_normals(p.seed, gchain, iter, j);
-          z0 = z.x;
-          z1 = (2 * j + 1 >= p.D) ? 0.0 : z.y;
+        for (int k = 0; k < K; ++k) {
+          const int j = tid + k * T;
+          double z0 = 0.0, z1 = 0.0;
+          if (2 * j < p.D) {
+            const double2 z = momentum_normals(p.seed, gchain, iter, j);
+            z0 = z.x;
+            z1 = (2 * j + 1 >= p.D) ? 0.0 : z.y;
+          }
+          // adaptive: inverse().sqrt() (adaptive_walnuts.hpp:236);
+          // fixed:    sqrt().inverse() (walnuts.hpp:647), precomputed above
+          const double c0 = ADAPT ? sqrt_noinline(div_noinline(1.0, im[k][0])) : c[k][0];
+          const double c1 = ADAPT ? sqrt_noinline(div_noinline(1.0, im[k][1])) : c[k][1];
+          rho[k][0] = __dmul_rn(c0, z0);
+          rho[k][1] = __dmul_rn(c1, z1);
         }
-        // adaptive: inverse().sqrt() (adaptive_walnuts.hpp:236);
-        // fixed:    sqrt().inverse() (walnuts.hpp:647)
-        double c0 = ADAPT ? sqrt_noinline(div_noinline(1.0, im[k][0]))
-                          : div_noinline(1.0, sqrt_noinline(im[k][0]));
-        double c1 = ADAPT ? sqrt_noinline(div_noinline(1.0, im[k][1]))
-                          : div_noinline(1.0, sqrt_noinline(im[k][1]));
-        rho[k][0] = __dmul_rn(c0, z0);
-        rho[k][1] = __dmul_rn(c1, z1);
       }
       // ---- initial point (walnuts.hpp:532-535)
       double lp0, H0;
@@ -853,30 +942,28 @@ struct ChainRunner {
       V::store(sv(A_TH_BK), ld, tid, th);  V::store(sv(A_TH_FW), ld, tid, th);
       V::store(sv(A_RHO_BK), ld, tid, rho); V::store(sv(A_RHO_FW), ld, tid, rho);
       V::store(sv(A_G_BK), ld, tid, g);    V::store(sv(A_G_FW), ld, tid, g);
-      V::store(sv(A_SEL), ld, tid, th);
       double H_bk = H0, H_fw = H0, logW = H0, lp_sel = lp0;
-      V::copy(ths, th); V::copy(rhos, rho); V::copy(gs, g);
-      int regs_dir = 0;  // +-1: (ths, rhos, gs) equal that end of the span
+      park_start();
+      int regs_dir = 0;  // +-1: the live / parked state equals that end of the span
       bool first_ext = true;
 
-      // stack of finished sub-trees with >= 2 leaves
-      double st_logW[kMaxDepth], st_lp[kMaxDepth];
       int depth;
       for (depth = 1; depth <= p.max_depth; ++depth) {
         const bool fwd = direction_bit(p.seed, gchain, iter, sctr++);  // :552
         const int dir = fwd ? 1 : -1;
         if (!first_ext && regs_dir != dir) {
           const int b = fwd ? A_TH_FW : A_TH_BK;
-          V::load(sv(b), ld, tid, ths);
-          V::load(sv(b + 1), ld, tid, rhos);
-          V::load(sv(b + 2), ld, tid, gs);
+          V::load(sv(b), ld, tid, th);
+          V::load(sv(b + 1), ld, tid, rho);
+          V::load(sv(b + 2), ld, tid, g);
+          park_start();
         }
         first_ext = false;
         double Hs = fwd ? H_fw : H_bk;
         double lps = 0.0;  // logp of the previous leaf (the level-0 entry)
         // ---- build_span(depth-1): 2^(depth-1) leaves, binary-counter merges.
         // The level-0 entry (a single leaf) is never written out: it is the
-        // macro-step start state, still in (ths, rhos) when leaf i+1 arrives.
+        // macro-step start state, still parked when leaf i+1 arrives.
         const int nleaf = 1 << (depth - 1);
         int sp = 0;
         bool ok = true;
@@ -888,8 +975,8 @@ struct ChainRunner {
           ok = macro_step(dir, step, min_micro, Hs, lpn, Hn, odd, dot_new, dot_old);
           if (!ok) break;
           double cur_logW = Hn, cur_lp = lpn;
-          // selection of the span being assembled: -1 newest leaf (th),
-          // -2 previous leaf (ths), >= 0 already in that stack slot
+          // selection of the span being assembled: -1 newest leaf (live),
+          // -2 previous leaf (parked), >= 0 already in that stack slot
           int cur_sel = -1;
           const int nm = __ffs(~i) - 1;  // trailing one bits of i = merges
           if (odd) {
@@ -905,18 +992,18 @@ struct ChainRunner {
               const int s = sp - 1;
               const int sb = ST_BASE + 3 * s;
               if (uturn(sv(sb + ST_THF), sv(sb + ST_RHOF), dir)) { ok = false; break; }
-              merge_decision(false, st_logW[s], cur_logW, gchain, iter, sctr++,
-                             take_new, lw);
+              // entry s is read before the barrier inside merge_decision and rewritten
+              // (below) only after it
+              const double logW_s = st_logW[s], lp_s = st_lp[s];
+              merge_decision(false, logW_s, cur_logW, gchain, iter, sctr++, take_new, lw);
               if (take_new) {
                 if (cur_sel >= 0) {
-                  double t[K][2];
-                  V::load(sv(ST_BASE + 3 * cur_sel + ST_SEL), ld, tid, t);
-                  V::store(sv(sb + ST_SEL), ld, tid, t);
+                  copy_row(sv(sb + ST_SEL), sv(ST_BASE + 3 * cur_sel + ST_SEL));
                   cur_sel = s;
                 }
               } else {
                 cur_sel = s;
-                cur_lp = st_lp[s];
+                cur_lp = lp_s;
               }
               cur_logW = lw;
               sp = s;
@@ -924,11 +1011,14 @@ struct ChainRunner {
             if (!ok) break;
             const int sb = ST_BASE + 3 * sp;
             if (nm == 1) {  // new two-leaf entry: its first state is the previous leaf
-              V::store(sv(sb + ST_THF), ld, tid, ths);
-              V::store(sv(sb + ST_RHOF), ld, tid, rhos);
+              copy_row(sv(sb + ST_THF), s_ths);
+              copy_row(sv(sb + ST_RHOF), s_rhos);
             }
             if (cur_sel == -1) V::store(sv(sb + ST_SEL), ld, tid, th);
-            if (cur_sel == -2) V::store(sv(sb + ST_SEL), ld, tid, ths);
+            if (cur_sel == -2) copy_row(sv(sb + ST_SEL), s_ths);
+            // every thread stores the same pair (and later reads back a copy of it), so
+            // only a lane that has not yet read the old entry needs to be waited for
+            if constexpr (T <= 32) grp.sync();
             st_logW[sp] = cur_logW;
             st_lp[sp] = cur_lp;
             ++sp;
@@ -936,38 +1026,35 @@ struct ChainRunner {
           sub_logW = cur_logW;
           sub_lp = cur_lp;
           // the newest leaf becomes the start of the next macro step
-          V::copy(ths, th); V::copy(rhos, rho); V::copy(gs, g);
+          park_start();
           Hs = Hn;
           lps = lpn;
         }
         if (!ok) break;  // extension rejected, span unchanged (:543-545)
         // ---- top level: U-turn across the whole span, then Metropolis merge
         const int farb = fwd ? A_TH_BK : A_TH_FW;
-        const bool ut = uturn(sv(farb), sv(farb + 1), dir);  // :546 (th == ths here)
+        const bool ut = uturn(sv(farb), sv(farb + 1), dir);  // :546 (live == parked here)
         bool take;
         double lw;
         merge_decision(true, logW, sub_logW, gchain, iter, sctr++, take, lw);
         if (take) {
           if (nleaf == 1) {
-            V::store(sv(A_SEL), ld, tid, ths);
+            V::store(sv(A_SEL), ld, tid, th);
           } else {
-            double t[K][2];
-            V::load(sv(ST_BASE + ST_SEL), ld, tid, t);
-            V::store(sv(A_SEL), ld, tid, t);
+            copy_row(sv(A_SEL), sv(ST_BASE + ST_SEL));
           }
           lp_sel = sub_lp;
         }
         const int nb = fwd ? A_TH_FW : A_TH_BK;
-        V::store(sv(nb), ld, tid, ths);
-        V::store(sv(nb + 1), ld, tid, rhos);
-        V::store(sv(nb + 2), ld, tid, gs);
+        V::store(sv(nb), ld, tid, th);
+        V::store(sv(nb + 1), ld, tid, rho);
+        V::store(sv(nb + 2), ld, tid, g);
         if (fwd) H_fw = Hs; else H_bk = Hs;
         logW = lw;
         regs_dir = dir;
         if (ut) break;  // :556-558
       }
-      // ---- the draw
-      V::load(sv(A_SEL), ld, tid, cur);
+      // ---- the draw (scratch row A_SEL)
       if (ADAPT) {
         grp.parity = adapt_end<Target, T, K>(p, grp, sc, est_row(), sv(A_SEL), depth);
       } else if (tid == 0) {
@@ -984,8 +1071,8 @@ struct ChainRunner {
         sc.last_lp = lp_sel;
       }
       if (p.draws) {
-        V::store(p.draws + (static_cast<long long>(chain) * p.draw_cap + row) * ld,
-                 ld, tid, cur);
+        copy_row(p.draws + (static_cast<long long>(chain) * p.draw_cap + row) * ld,
+                 sv(A_SEL));
       }
       if (tid == 0) {
         const long long o = static_cast<long long>(chain) * p.draw_cap + row;
@@ -994,7 +1081,7 @@ struct ChainRunner {
         if (p.step_out) p.step_out[o] = ADAPT ? exp_noinline(sc.adam_x) : sc.step;
       }
     }
-    V::store(theta_row, ld, tid, cur);
+    copy_row(theta_row, sv(A_SEL));
     if (tid == 0) {
       sc.grad_evals += evals;
       sc.iter = u_iter;
@@ -1009,6 +1096,7 @@ struct ChainRunner {
 template <class Target, int T, int K, int CTA, int MINB, bool ADAPT>
 __global__ void __launch_bounds__(CTA, MINB)
 walnuts_chain_kernel(const ChainParams p) {
+  extern __shared__ double chain_smem[];  // [CTA / T][chain_smem_doubles(ld)]
   __shared__ double red_smem[group_smem_doubles<T>()];
   __shared__ ChainScalars sc_smem[CTA / T];
   __shared__ DecisionCache dc_smem[CTA / T];
@@ -1030,7 +1118,9 @@ walnuts_chain_kernel(const ChainParams p) {
     slot = blockIdx.x;
   }
   double* scr = p.scratch + static_cast<long long>(slot) * p.scratch_stride;
-  ChainRunner<Target, T, K, ADAPT> runner(p, grp, scr, sc_smem[threadIdx.x / T]);
+  ChainRunner<Target, T, K, ADAPT> runner(
+      p, grp, scr, sc_smem[threadIdx.x / T],
+      chain_smem + static_cast<int>(threadIdx.x / T) * chain_smem_doubles(p.ld));
   if (grp.tid == 0) {
     dc_smem[threadIdx.x / T].valid = 0;
     if (ADAPT) aq_smem[threadIdx.x / T].n = 0;

@@ -28,13 +28,19 @@ LaunchShape shape_for_dim(int D) {
 }
 
 // (TARGET, T, K, CTA, min resident CTAs per SM -> register cap)
+#ifndef WB200_MINB_32X2
+#define WB200_MINB_32X2 3
+#endif
+#ifndef WB200_MINB_128X4
+#define WB200_MINB_128X4 3
+#endif
 #define WB200_FOR_SHAPE(S, MACRO, TARGET)                                      \
   do {                                                                         \
     if ((S).T == 32 && (S).K == 1) { MACRO(TARGET, 32, 1, 128, 4); }           \
-    else if ((S).T == 32 && (S).K == 2) { MACRO(TARGET, 32, 2, 128, 3); }      \
+    else if ((S).T == 32 && (S).K == 2) { MACRO(TARGET, 32, 2, 128, WB200_MINB_32X2); }      \
     else if ((S).T == 64) { MACRO(TARGET, 64, 2, 64, 6); }                     \
     else if ((S).T == 128 && (S).K == 2) { MACRO(TARGET, 128, 2, 128, 3); }    \
-    else if ((S).T == 128 && (S).K == 4) { MACRO(TARGET, 128, 4, 128, 3); }    \
+    else if ((S).T == 128 && (S).K == 4) { MACRO(TARGET, 128, 4, 128, WB200_MINB_128X4); }    \
     else if ((S).T == 256 && (S).K == 2) { MACRO(TARGET, 256, 2, 256, 2); }    \
     else if ((S).T == 256 && (S).K == 4) { MACRO(TARGET, 256, 4, 256, 1); }    \
     else { MACRO(TARGET, 512, 4, 512, 1); }                                    \
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(CTA) orbit_kernel(const OrbitParams op) {
   }
   if (chain >= p.C) return;
   ChainScalars unused_sc{};
-  ChainRunner<Target, T, K, false> r(p, grp, nullptr, unused_sc);
+  ChainRunner<Target, T, K, false> r(p, grp, nullptr, unused_sc, nullptr);
   r.tgt.init(p, grp.tid);
   const long long off = static_cast<long long>(chain) * p.ld;
   V::load(p.theta + off, p.ld, grp.tid, r.th);
@@ -280,10 +286,20 @@ __global__ void __launch_bounds__(CTA) orbit_kernel(const OrbitParams op) {
 }
 
 // ---------------------------------------------------------------------------
+// dynamic shared memory of a chain-kernel CTA: the parked start states and sub-tree
+// stacks of its resident chains
+static size_t chain_dyn_smem(const LaunchShape& shape, int ld) {
+  return static_cast<size_t>(shape.chains_per_cta) * chain_smem_doubles(ld) * sizeof(double);
+}
+
 template <class Kernel>
-static int blocks_per_sm(Kernel k, int cta) {
+static int blocks_per_sm(Kernel k, int cta, size_t dyn_smem) {
   int n = 0;
-  WB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, cta, 0));
+  if (dyn_smem > 48 * 1024) {
+    WB200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(dyn_smem)));
+  }
+  WB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, cta, dyn_smem));
   return std::max(n, 1);
 }
 
@@ -293,16 +309,22 @@ static int sm_count(int device) {
   return n;
 }
 
+// both instances get the opt-in for > 48 KB of dynamic shared memory; the grid is sized
+// by the one with fewer resident CTAs
 #define WB200_OCC(TARGET, T_, K_, CTA_, MINB_)                                 \
-  occ = blocks_per_sm(walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, false>, CTA_)
+  occ = std::min(                                                              \
+      blocks_per_sm(walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, false>, CTA_, \
+                    dyn_smem),                                                 \
+      blocks_per_sm(walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, true>, CTA_,  \
+                    dyn_smem))
 #define WB200_LAUNCH_CHAIN(TARGET, T_, K_, CTA_, MINB_)                        \
   do {                                                                         \
     if (p.adapt) {                                                             \
       walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, true>          \
-          <<<s.grid, CTA_, 0, s.stream>>>(p);                                  \
+          <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
     } else {                                                                   \
       walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, false>         \
-          <<<s.grid, CTA_, 0, s.stream>>>(p);                                  \
+          <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
     }                                                                          \
   } while (0)
 #define WB200_LAUNCH_INIT(TARGET, T_, K_, CTA_, MINB_)                         \
@@ -310,14 +332,16 @@ static int sm_count(int device) {
 #define WB200_LAUNCH_ORBIT(TARGET, T_, K_, CTA_, MINB_)                        \
   orbit_kernel<TARGET, T_, K_, CTA_><<<grid, CTA_, 0, stream>>>(op)
 
-int occupancy_for(int kind, const LaunchShape& shape) {
+int occupancy_for(int kind, const LaunchShape& shape, int ld) {
   int occ = 1;
+  const size_t dyn_smem = chain_dyn_smem(shape, ld);
   WB200_FOR_TARGET(kind, shape, WB200_OCC);
   return occ;
 }
 
 void launch_chains(wb200_session& s, int n_iter, int adapt, bool store) {
   ChainParams p = s.params(n_iter, adapt, store);
+  const size_t dyn_smem = chain_dyn_smem(s.shape, s.ld);
   WB200_CUDA(cudaMemsetAsync(s.ticket.ptr, 0, sizeof(unsigned int), s.stream));
   WB200_CUDA(cudaEventRecord(s.ev0, s.stream));
   WB200_FOR_TARGET(s.kind, s.shape, WB200_LAUNCH_CHAIN);

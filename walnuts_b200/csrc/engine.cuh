@@ -91,7 +91,7 @@ struct LaunchShape {
   int T, K, cta, chains_per_cta;
 };
 LaunchShape shape_for_dim(int D);
-int occupancy_for(int kind, const LaunchShape& shape);
+int occupancy_for(int kind, const LaunchShape& shape, int ld);
 
 // errors.hpp:30-33: the user pressed Ctrl+C (interrupts.hpp)
 struct InterruptException {};
@@ -137,7 +137,7 @@ inline void download_rows(double* dst, int D, const double* src, int ld, size_t 
 
 }  // namespace wb200
 
-namespace wb200 { struct TickEngine; }
+namespace wb200 { struct TickEngine; struct StreamState; }
 
 struct wb200_session {
   int device = 0;
@@ -166,8 +166,10 @@ struct wb200_session {
   wb200::DeviceBuffer<wb200::ChainScalars> sc;
   wb200::DeviceBuffer<unsigned int> ticket;
   wb200::TickEngine* tick = nullptr;  // lock-step engine (logistic; WB200_ENGINE=tick)
+  wb200::StreamState* acc = nullptr;  // streaming summary accumulators (stream.cu)
 
   wb200::ChainParams params(int n_iter, int adapt, bool store);
+  long long* acc_rows();  // device [C]: staged rows per chain of the streaming block
 };
 
 namespace wb200 {
@@ -183,6 +185,10 @@ void tick_init(wb200_session& s, bool have_mass, bool have_steps, bool have_posi
 void tick_run(wb200_session& s, int n_iter, int adapt, bool store);
 void tick_run_ticks(wb200_session& s, int n_ticks, int adapt, bool store);
 void tick_chain_rows(wb200_session& s, long long* rows_host);
+// free-running + streaming: per-chain staged row counts -> rows_dev, then reset to 0
+void tick_take_rows(wb200_session& s, long long* rows_dev);
+void stream_end(wb200_session& s);
+void stream_update(wb200_session& s, const long long* rows_c, long long rows_uniform);
 void tick_abort_inflight(wb200_session& s);
 unsigned long long tick_count(const wb200_session& s);
 void launch_orbit(int kind, int D, int ld, int C, const double* tparam,

@@ -562,6 +562,20 @@ void tick_chain_rows(wb200_session& s, long long* rows_host) {
   WB200_CUDA(cudaStreamSynchronize(s.stream));
 }
 
+// rows[c] = draws chain c has staged since the last call; its counter restarts at 0
+__global__ void tick_take_rows_kernel(TickState* ts, int C, long long* rows) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    rows[c] = ts[c].rows;
+    ts[c].rows = 0;
+  }
+}
+
+void tick_take_rows(wb200_session& s, long long* rows_dev) {
+  tick_take_rows_kernel<<<(s.C + 255) / 256, 256, 0, s.stream>>>(s.tick->ts.ptr, s.C, rows_dev);
+  WB200_CUDA(cudaGetLastError());
+}
+
 unsigned long long tick_count(const wb200_session& s) { return s.tick ? s.tick->ticks : 0; }
 
 }  // namespace wb200
