@@ -111,6 +111,32 @@ int walnutpie_sample_device(
     double* inv_metric_out, int refresh, PRINT_CALLBACK print,
     WalnutpyError** err);
 
+/* The one-shot call for runs whose draws are too many to keep or ship (65 536 chains x
+ * 1000 draws x 512 parameters are 268 GB): the arguments of walnutpie_sample_device up to
+ * step_learn_rate_decay, then, instead of save_warmup and the draw buffer, the number of
+ * autocovariance lags to keep (8, 16 or 32) and HOST arrays of num_params (any may be
+ * NULL) that receive the posterior summaries of summary.hpp:371-405,594-769 -- pooled
+ * mean and variance, R-hat, ESS, MCSE and a flag per dimension whose Geyer sequence
+ * was cut at max_lags -- computed on the device by the streaming accumulators (see
+ * "streaming summaries" below).  Nothing but these 5 x num_params doubles, the lengths,
+ * step sizes and metrics crosses PCIe. */
+int walnutpie_sample_device_summary(
+    const WalnutModelDesc* model, int num_params, const double* inits,
+    size_t num_chains, unsigned int seed, unsigned int id, double init_radius,
+    const double* init_inv_metric, int min_warmup_iter, int max_warmup_iter,
+    int min_sampling_iter, int max_sampling_iter, int max_trajectory_doublings,
+    int max_step_halvings, int min_micro_steps, double max_hamiltonian_error,
+    double step_size_converge_tol, double mass_converge_tol,
+    double rhat_converge_tol, double mass_init_count,
+    double mass_additive_smoothing, double max_macro_steps_target,
+    double step_size_init, double step_accept_rate_target,
+    double step_learning_rate, double step_gradient_decay,
+    double step_sq_gradient_decay, double step_stabilization,
+    double step_learn_rate_decay, int max_lags, double* mean_out, double* var_out,
+    double* rhat_out, double* ess_out, double* mcse_out, int* truncated_out,
+    int* final_lengths, double* stepsize_out, double* inv_metric_out, int refresh,
+    PRINT_CALLBACK print, WalnutpyError** err);
+
 /* walnutpie_sample_cfunc (walnutpy.cpp:134): exported for link compatibility; a
  * host callback cannot feed a device batch, so it fails with a `generic` error that
  * names walnutpie_sample_device and the batched device callback (WalnutModelDesc
@@ -251,6 +277,41 @@ int wb200_session_lp_moments_centered(wb200_session* s, double center,
  * on with logp = -inf and a zero gradient.  (A failure during initialisation ends the
  * run with "logp failed with code N", walnutpy.cpp:162-170.) */
 int wb200_session_logp_exceptions(wb200_session* s, unsigned long long* count);
+
+/* ---- streaming summaries (summary.hpp:594-769 without keeping the draws) ---------
+ * After wb200_session_stream_begin the draw buffer reserved with
+ * wb200_session_reserve_draws is a STAGING block: every storing wb200_session_sample /
+ * _sample_ticks call refills it from row 0 and folds its rows into per-chain running
+ * sums -- count, sum, lag products sum_i y_i y_{i+t} for t < max_lags (8, 16 or 32) and
+ * the first / last max_lags values, all about the chain's first streamed draw.  From
+ * those the reference's R-hat, ESS, MCSE, pooled mean and variance follow exactly,
+ * provided the Geyer sequence of a dimension ends before lag max_lags (else that
+ * dimension is flagged in `truncated` and its ESS is an upper bound).  Chains with
+ * fewer than 3 streamed draws are left out (summary.hpp:595-603).
+ *
+ * Multi-GPU (chains sharded over ranks): the cross-chain part is two reductions a
+ * caller performs with NCCL (or any all-reduce) between the calls:
+ *   phase1 -> out1 [2D + 3] = {sum_k mu_k [D], sum_k n_k mu_k [D], K, N, min_len}
+ *             all-reduce: SUM over [0, 2D + 2), MIN over element 2D + 2;
+ *   phase2(reduced1) -> out2 [(3 + max_lags) D] = {sum_k (mu_k - mbar)^2, sum_k s_k^2,
+ *             pooled sum of squares, sum_k acov_k(t) for t < max_lags}, centred on the
+ *             GLOBAL means of phase 1;  all-reduce: SUM;
+ *   wb200_stream_finish(reduced1, reduced2) -> the summaries, identical on every rank
+ *             and equal to those of one session holding all the chains.
+ * wb200_session_stream_summary runs the three steps for a single session.
+ * Outputs are HOST arrays of num_params (any may be NULL). */
+int wb200_session_stream_begin(wb200_session* s, int max_lags, WalnutpyError** err);
+int wb200_session_stream_phase1(wb200_session* s, double* out1, WalnutpyError** err);
+int wb200_session_stream_phase2(wb200_session* s, const double* reduced1, double* out2,
+                                WalnutpyError** err);
+int wb200_stream_finish(int num_params, int max_lags, const double* reduced1,
+                        const double* reduced2, double* rhat, double* ess, double* mcse,
+                        double* mean, double* var, int* truncated, WalnutpyError** err);
+int wb200_session_stream_summary(wb200_session* s, double* rhat, double* ess, double* mcse,
+                                 double* mean, double* var, int* truncated,
+                                 WalnutpyError** err);
+/* draws folded in so far, per chain (host [C]) */
+int wb200_session_stream_counts(wb200_session* s, long long* counts, WalnutpyError** err);
 
 /* Read-back (host buffers).  draws: [C][count][D] from row `first`. */
 int wb200_session_get_draws(wb200_session* s, long long first, long long count,

@@ -12,6 +12,7 @@ Only tests/, ``__graft_entry__.smoke()`` and bench.py's cpu_baseline /
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import subprocess
@@ -233,6 +234,19 @@ class Checker:
             _dp(positions), _dp(mass_in), C.c_double(smoothing), C.c_double(step_init),
             _dp(mass), _dp(steps)))
         return mass, steps
+
+    def set_fused_arith(self, fused: bool) -> bool:
+        """Arithmetic policy of the accumulate sites (oracle/targets.hpp); oracle only.
+        Returns the previous setting."""
+        return bool(self.lib.oracle_set_fused_arith(C.c_int(int(fused))))
+
+    @contextlib.contextmanager
+    def fused_arith(self, fused: bool = True):
+        before = self.set_fused_arith(fused)
+        try:
+            yield self
+        finally:
+            self.set_fused_arith(before)
 
     def warmup_controller(self, log_step, log_mass):
         """(max_m ||(M_m - gm)/gm||_2, max(0, max_m (eps_m - gs)/gs)) of adapt.hpp:186-224

@@ -354,6 +354,12 @@ int oracle_sampling_rhat(size_t num_chains, const double* mean, const double* va
   });
 }
 
+int oracle_set_fused_arith(int fused) {
+  const int before = oracle::fused_arith() ? 1 : 0;
+  oracle::fused_arith() = fused != 0;
+  return before;
+}
+
 double oracle_leapfrog_error(const OracleTarget* target, const double* theta,
                              const double* rho, const double* inv_mass,
                              double step) {

@@ -121,6 +121,10 @@ int oracle_warmup_controller(size_t num_chains, size_t D, const double* log_step
                              double* max_rel_step);
 int oracle_sampling_rhat(size_t num_chains, const double* mean, const double* var,
                          double* r_hat);
+/* Arithmetic policy of the accumulate sites (oracle/targets.hpp): 0 = the reference's
+ * baseline build, separate roundings (default; the policy pinned to the reference);
+ * 1 = fused multiply-add, what the device kernels ship.  Returns the previous value. */
+int oracle_set_fused_arith(int fused);
 int oracle_logp_grad(const OracleTarget* target, const double* theta,
                      double* logp, double* grad);
 void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

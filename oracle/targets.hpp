@@ -19,6 +19,21 @@ namespace oracle {
 
 using Vec = std::vector<double>;
 
+// Arithmetic policy of the accumulate sites a*b + c of the hot loops (leapfrog kicks and
+// drift, the targets' sums of squares, kinetic energy, U-turn dots, the discounted sum
+// of squares of OnlineMoments).  Default = the reference's baseline x86-64 build: product
+// and sum round separately (this file is compiled with -ffp-contract=off).  "Fused" = one
+// rounding, what the device kernels ship (walnuts_b200/csrc/chain_kernel.cuh, kFusedArith)
+// and what a contracting build of the reference would do.  Process-wide switch; the
+// reference-policy oracle is the one pinned bit for bit to the reference's headers.
+inline bool& fused_arith() {
+  static bool fused = false;
+  return fused;
+}
+inline double madd(double a, double b, double c) {
+  return fused_arith() ? std::fma(a, b, c) : a * b + c;
+}
+
 enum TargetKind : int { kStdNormal = 0, kDiagGaussian = 1, kFunnel = 2,
                         kLogistic = 3 };
 
@@ -26,7 +41,7 @@ struct StdNormal {
   void eval(const double* x, std::size_t n, double& lp, double* g) const {
     double s = 0.0;
     for (std::size_t i = 0; i < n; ++i) {
-      s += x[i] * x[i];
+      s = madd(x[i], x[i], s);
       g[i] = -x[i];
     }
     lp = -0.5 * s;
@@ -44,7 +59,7 @@ struct DiagGaussian {
     double s = 0.0;
     for (std::size_t i = 0; i < n; ++i) {
       double t = x[i] * prec[i];
-      s += x[i] * t;
+      s = madd(x[i], t, s);
       g[i] = -t;
     }
     lp = -0.5 * s;
@@ -67,7 +82,7 @@ struct Funnel {
     const double ev = std::exp(-v);
     double ss = 0.0;
     for (std::size_t i = 1; i < D; ++i) {
-      ss += x[i] * x[i];
+      ss = madd(x[i], x[i], ss);
       g[i] = -(x[i] * ev);
     }
     const double half_dm1 = 0.5 * static_cast<double>(D - 1);

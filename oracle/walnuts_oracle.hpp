@@ -92,7 +92,7 @@ inline double log_sum_exp(const Vec& x) {
 inline double logp_momentum(const Vec& rho, const Vec& inv_mass) {
   double s = 0.0;
   for (std::size_t i = 0; i < rho.size(); ++i) {
-    s += inv_mass[i] * (rho[i] * rho[i]);
+    s = madd(inv_mass[i], rho[i] * rho[i], s);
   }
   return -0.5 * s;
 }
@@ -291,7 +291,7 @@ class OnlineMoments {
     }
     for (std::size_t i = 0; i < y.size(); ++i) {
       double d = y[i] - mean_[i];
-      ssd_[i] = gamma * ssd_[i] + d * d;
+      ssd_[i] = madd(gamma, ssd_[i], d * d);
     }
   }
   const Vec& mean() const { return mean_; }
@@ -393,8 +393,8 @@ bool uturn(const SpanW& span1, const SpanW& span2, const Vec& inv_mass) {
   double dot_fw = 0.0, dot_bk = 0.0;
   for (std::size_t i = 0; i < n; ++i) {
     double sd = inv_mass[i] * (span_fw.theta_fw[i] - span_bk.theta_bk[i]);
-    dot_fw += span_fw.rho_fw[i] * sd;
-    dot_bk += span_bk.rho_bk[i] * sd;
+    dot_fw = madd(span_fw.rho_fw[i], sd, dot_fw);
+    dot_bk = madd(span_bk.rho_bk[i], sd, dot_bk);
   }
   return dot_fw < 0 || dot_bk < 0;
 }
@@ -405,10 +405,10 @@ inline void leapfrog(const F& logp_grad, const Vec& inv_mass, double step,
                      double half_step, Vec& theta, Vec& rho, Vec& grad,
                      double& logp_pos) {
   const std::size_t D = theta.size();
-  for (std::size_t i = 0; i < D; ++i) rho[i] += half_step * grad[i];
-  for (std::size_t i = 0; i < D; ++i) theta[i] += step * inv_mass[i] * rho[i];
+  for (std::size_t i = 0; i < D; ++i) rho[i] = madd(half_step, grad[i], rho[i]);
+  for (std::size_t i = 0; i < D; ++i) theta[i] = madd(step * inv_mass[i], rho[i], theta[i]);
   logp_grad(theta, logp_pos, grad);
-  for (std::size_t i = 0; i < D; ++i) rho[i] += half_step * grad[i];
+  for (std::size_t i = 0; i < D; ++i) rho[i] = madd(half_step, grad[i], rho[i]);
 }
 
 // walnuts.hpp:218-235

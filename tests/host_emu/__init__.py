@@ -19,13 +19,18 @@ class EmuTuning(C.Structure):
                                   "adam_eps", "adam_decay")]
 
 
-def build():
+def build(exact_arith: bool = False):
+    """exact_arith: -DWB200_EXACT_ARITH, every rounding separate (the reference's baseline
+    build); default: the fused policy the shipped kernels use."""
+    so = HERE / ("libemu_exact.so" if exact_arith else "libemu.so")
     deps = [SRC, CSRC / "chain_kernel.cuh", CSRC / "tick_kernel.cuh", CSRC / "philox.cuh",
             CSRC / "host_shims.hpp"]
-    if not SO.exists() or any(d.stat().st_mtime > SO.stat().st_mtime for d in deps):
+    if not so.exists() or any(d.stat().st_mtime > so.stat().st_mtime for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-shared",
-                        "-I/usr/local/cuda/include", "-o", str(SO), str(SRC)], check=True)
-    return C.CDLL(str(SO))
+                        "-I/usr/local/cuda/include"] +
+                       (["-DWB200_EXACT_ARITH"] if exact_arith else []) +
+                       ["-o", str(so), str(SRC)], check=True)
+    return C.CDLL(str(so))
 
 
 def run_chain(lib, kind, D, tparam, cfg, seed, chain, th0, m0, step0, nw, ns, engine="chain",

@@ -18,6 +18,14 @@ import pytest
 from oracle.binding import Target, default_config
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _device_arithmetic_policy(oracle):
+    """The shipped kernels use the fused arithmetic policy (chain_kernel.cuh, kFusedArith);
+    the oracle is switched to the same policy for every comparison in this module."""
+    with oracle.fused_arith(True):
+        yield
 ROOT = Path(__file__).resolve().parent.parent
 
 

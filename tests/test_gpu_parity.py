@@ -16,6 +16,14 @@ from oracle.binding import Target, default_config
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, scope="module")
+def _device_arithmetic_policy(oracle):
+    """The shipped kernels use the fused arithmetic policy (chain_kernel.cuh, kFusedArith);
+    the oracle is switched to the same policy for every comparison in this module."""
+    with oracle.fused_arith(True):
+        yield
+
 ORBIT_RTOL = 1e-12
 
 

@@ -1,12 +1,15 @@
 """The DEVICE transition state machine (walnuts_b200/csrc/chain_kernel.cuh) compiled
 with g++ for one emulated thread per chain, against the oracle's Philox policy.
 
-Same source as the CUDA build, same non-contracted fp64 arithmetic, sums in
-element order — so whole warm-up + sampling runs must equal the oracle's bit
-for bit: iterative doubling vs the reference's recursion (walnuts.hpp:464-495),
-the halving and reversibility ladders (:254-345), Barker / Metropolis selection
-(:368-387), Adam, the discounted Welford estimators and the min-micro controller
-(adaptive_walnuts.hpp:234-251).  Runs without a GPU.
+Same source as the CUDA build, same fp64 arithmetic, sums in element order — so
+whole warm-up + sampling runs must equal the oracle's bit for bit: iterative doubling
+vs the reference's recursion (walnuts.hpp:464-495), the halving and reversibility
+ladders (:254-345), Barker / Metropolis selection (:368-387), Adam, the discounted
+Welford estimators and the min-micro controller (adaptive_walnuts.hpp:234-251).
+Both arithmetic policies are pinned: "exact" (-DWB200_EXACT_ARITH, every rounding
+separate) against the oracle's reference policy -- the one that reproduces the
+unmodified reference headers bit for bit -- and "fused" (what ships: fused multiply-add
+at the accumulate sites) against the oracle's fused policy.  Runs without a GPU.
 """
 import numpy as np
 import pytest
@@ -27,9 +30,12 @@ CASES = [
 ]
 
 
-@pytest.fixture(scope="module")
-def emu():
-    return host_emu.build()
+@pytest.fixture(scope="module", params=["fused", "exact"])
+def emu(request, oracle):
+    exact = request.param == "exact"
+    lib = host_emu.build(exact_arith=exact)
+    with oracle.fused_arith(not exact):
+        yield lib
 
 
 @pytest.mark.parametrize("engine", ["chain", "tick"])

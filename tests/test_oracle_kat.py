@@ -8,7 +8,7 @@ import math
 import numpy as np
 import pytest
 
-from oracle.binding import Target
+from oracle.binding import Target, default_config
 
 INF = float("inf")
 NAN = float("nan")
@@ -199,3 +199,49 @@ def test_philox_init_mass_and_step_follow_the_reference_rules(oracle):
         rho = oracle.philox_normals(5, c, 0, 3, D)       # sqrt(M) = 1
         err = oracle.leapfrog_error(t, pos[c], rho, np.ones(D), lo[c])
         assert err >= np.log(0.6)
+
+
+# ---- the two arithmetic policies -----------------------------------------------------
+@pytest.mark.parametrize("kind,D,step,nsteps", [("std_normal", 100, 0.37, 64),
+                                                ("diag_gaussian", 1000, 0.2, 50),
+                                                ("funnel", 100, 0.05, 40)])
+def test_fused_policy_orbits_agree_with_the_reference_policy_to_1e12(oracle, kind, D, step,
+                                                                     nsteps):
+    """BASELINE.json north_star: fixed-step leapfrog orbits within 1e-12 relative of the
+    reference's integrator.  The fused policy (one rounding per a*b + c at the accumulate
+    sites, what the kernels ship) differs from the reference policy (separate roundings,
+    pinned bit for bit to the reference's headers) by rounding only."""
+    rng = np.random.default_rng(D + nsteps)
+    prec = 1.0 / (10.0 ** (4 * np.arange(D) / (D - 1))) if kind == "diag_gaussian" else None
+    t = Target(kind, D, prec=prec)
+    inv_mass = rng.uniform(0.5, 2.0, D) * (1.0 / prec if prec is not None else 1.0)
+    theta = rng.normal(size=D) * (0.3 if kind == "funnel" else 1.0)
+    rho = rng.normal(size=D) / np.sqrt(inv_mass)
+    ref = oracle.orbit(t, theta, rho, inv_mass, step, nsteps)
+    with oracle.fused_arith(True):
+        fused = oracle.orbit(t, theta, rho, inv_mass, step, nsteps)
+    assert any(np.any(a != b) for a, b in zip(ref[:3], fused[:3])), "policies must differ"
+    for a, b in zip(ref[:3], fused[:3]):
+        assert np.max(np.abs(a - b)) / np.max(np.abs(a)) <= 1e-12
+    assert abs(ref[3] - fused[3]) <= 1e-12 * max(abs(ref[3]), 1.0)
+    assert abs(ref[4] - fused[4]) <= 1e-12 * max(abs(ref[4]), 1.0)
+    assert oracle.set_fused_arith(False) is False      # the context manager restored it
+
+
+def test_fused_policy_trajectories_follow_the_reference_policy_until_a_branch_flips(oracle):
+    """Identically seeded chains under the two policies agree to rounding until the first
+    rounding-induced accept / U-turn flip (north_star); the prefix is reported."""
+    D = 20
+    t = Target("diag_gaussian", D, prec=np.linspace(0.5, 3.0, D))
+    cfg = default_config()
+    rng = np.random.default_rng(3)
+    th0, m0 = rng.normal(size=D), rng.uniform(0.5, 2.0, D)
+    ref = oracle.run_chain(t, cfg, 7, 0, th0, m0, 0.4, 40, 40, rng_policy=1)
+    with oracle.fused_arith(True):
+        fused = oracle.run_chain(t, cfg, 7, 0, th0, m0, 0.4, 40, 40, rng_policy=1)
+    a = np.concatenate([ref["warmup_draws"], ref["draws"]])
+    b = np.concatenate([fused["warmup_draws"], fused["draws"]])
+    bad = np.flatnonzero(np.max(np.abs(a - b), axis=1) > 1e-9 * np.max(np.abs(a), axis=1))
+    first = int(bad[0]) if bad.size else len(a)
+    print(f"\nfirst divergence between the arithmetic policies: iteration {first} of {len(a)}")
+    assert first >= 10

@@ -8,12 +8,13 @@ not been built — there is no CPU path.
 from . import models
 from ._ffi import logp_cfunc_type
 from .models import DeviceModel
-from .sampler import Session, WalnutsOutputArray, orbit, walnuts_device
+from .sampler import (Session, WalnutsOutputArray, orbit, walnuts_device,
+                      walnuts_device_summary)
 from .summary import (Summarizer, ess, mcse, mean, r_hat, standard_deviation,
                       variance)
 
 __all__ = [
-    "walnuts_device", "Session", "DeviceModel", "models", "orbit",
+    "walnuts_device", "walnuts_device_summary", "Session", "DeviceModel", "models", "orbit",
     "WalnutsOutputArray", "logp_cfunc_type", "r_hat", "ess", "mcse", "mean",
     "variance", "standard_deviation", "Summarizer",
 ]

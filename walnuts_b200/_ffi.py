@@ -192,6 +192,17 @@ _ffi_sample_device.argtypes = [
     nullable_double_array,  # inits
 ] + _common_sampling_argtypes
 
+# the same call without the draw buffer: save_warmup, out, out_size -> max_lags and the
+# five summary arrays + truncation flags (include/walnuts_b200.h)
+_ffi_sample_device_summary = erroring(_lib.walnutpie_sample_device_summary)
+_ffi_sample_device_summary.argtypes = [
+    ctypes.POINTER(WalnutModelDesc), ctypes.c_int, nullable_double_array,
+] + _common_sampling_argtypes[:26] + [
+    ctypes.c_int,  # max_lags
+    nullable_double_array, nullable_double_array, nullable_double_array,
+    nullable_double_array, nullable_double_array, nullable_int_array,
+] + _common_sampling_argtypes[29:]
+
 _ffi_sample_cfunc = erroring(_lib.walnutpie_sample_cfunc)
 _ffi_sample_cfunc.argtypes = [
     logp_cfunc_type, ctypes.c_void_p, ctypes.c_int, nullable_double_array,
@@ -259,6 +270,19 @@ _lib.wb200_session_logp_exceptions.restype = ctypes.c_int
 _lib.wb200_session_logp_exceptions.argtypes = [session_p,
                                                ctypes.POINTER(ctypes.c_ulonglong)]
 session_logp_exceptions = _lib.wb200_session_logp_exceptions
+session_stream_begin = _sess("wb200_session_stream_begin", [session_p, ctypes.c_int])
+session_stream_phase1 = _sess("wb200_session_stream_phase1", [session_p, double_array])
+session_stream_phase2 = _sess("wb200_session_stream_phase2",
+                              [session_p, double_array, double_array])
+stream_finish = _sess("wb200_stream_finish", [
+    ctypes.c_int, ctypes.c_int, double_array, double_array, nullable_double_array,
+    nullable_double_array, nullable_double_array, nullable_double_array,
+    nullable_double_array, nullable_int_array])
+session_stream_summary = _sess("wb200_session_stream_summary", [
+    session_p, nullable_double_array, nullable_double_array, nullable_double_array,
+    nullable_double_array, nullable_double_array, nullable_int_array])
+session_stream_counts = _sess("wb200_session_stream_counts", [
+    session_p, ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")])
 session_get_draws = _sess("wb200_session_get_draws", [
     session_p, ctypes.c_longlong, ctypes.c_longlong, double_array])
 session_get_trace = _sess("wb200_session_get_trace", [
@@ -351,7 +375,10 @@ EXPORTED_SYMBOLS = [
     "wb200_session_chain_rows", "wb200_session_summary", "wb200_session_rhat_moments", "wb200_session_warmup_sums",
     "wb200_session_warmup_deviation", "wb200_session_lp_moments",
     "wb200_session_lp_moments_centered", "wb200_session_logp_exceptions",
-    "walnutpie_sample_bridgestan",
+    "walnutpie_sample_bridgestan", "walnutpie_sample_device_summary",
+    "wb200_session_stream_begin",
+    "wb200_session_stream_phase1", "wb200_session_stream_phase2", "wb200_stream_finish",
+    "wb200_session_stream_summary", "wb200_session_stream_counts",
     "wb200_session_get_draws", "wb200_session_get_trace", "wb200_session_get_state",
     "wb200_session_device_draws", "wb200_session_counters",
     "wb200_session_last_kernel_ms", "wb200_session_timer_record",

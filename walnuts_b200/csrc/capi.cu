@@ -163,13 +163,14 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
       return;
     }
     // slots: resident groups of the chain kernel
-    const int occ = occupancy_for(s->kind, s->shape, s->ld);
+    int occ_adapt = 1, occ_sample = 1;
+    occupancy_for(s->kind, s->shape, s->ld, &occ_adapt, &occ_sample);
     int sms = 0;
     WB200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    const int max_grid = occ * sms;
     const int need = (s->C + s->shape.chains_per_cta - 1) / s->shape.chains_per_cta;
-    s->grid = std::min(max_grid, need);
-    s->slots = s->grid * s->shape.chains_per_cta;
+    s->grid = std::min(occ_sample * sms, need);
+    s->grid_adapt = std::min(occ_adapt * sms, need);
+    s->slots = std::max(s->grid, s->grid_adapt) * s->shape.chains_per_cta;
     const size_t stride =
         static_cast<size_t>(scratch_doubles(s->tuning.max_trajectory_doublings, s->ld));
     s->scratch.alloc(stride * s->slots);
@@ -306,10 +307,9 @@ int wb200_session_sample(wb200_session* s, int n_iter, int store, WalnutpyError*
       if (n_iter < 0) throw std::invalid_argument("n_iter must be non-negative");
       for (int done = 0; done < n_iter;) {
         const int n = static_cast<int>(std::min<long long>(n_iter - done, s->draw_cap));
-        s->rows_written = 0;
+        if (s->rows_written + n > s->draw_cap) stream_flush(*s);  // block full: fold it in
         if (s->tick) tick_run(*s, n, 0, true);
         else launch_chains(*s, n, 0, true);
-        stream_update(*s, nullptr, n);
         done += n;
       }
       return;
@@ -333,7 +333,7 @@ int wb200_session_sample_ticks(wb200_session* s, int n_ticks, int store,
     if (s->acc && store) {
       // streaming: chains restart their staging rows at 0; a chain that fills the block
       // before the ticks are over idles until the next call (reserve generously)
-      s->rows_written = 0;
+      stream_flush(*s);
       tick_run_ticks(*s, n_ticks, 0, true);
       tick_take_rows(*s, s->acc_rows());
       stream_update(*s, s->acc_rows(), 0);

@@ -294,7 +294,19 @@ int wb200_philox_normals(unsigned int seed, unsigned int chain, unsigned int ite
 // ---------------------------------------------------------------------------
 // walnutpie_sample_device: the whole of walnutpy.cpp:134-222 + run_sampler
 // (:20-84) + walnutpie::walnuts (api.hpp:33-69) for a device model.
-int walnutpie_sample_device(
+namespace {
+// outputs of the summaries-only form of the one-shot call (any pointer may be null)
+struct StreamOutputs {
+  int max_lags;
+  double *mean, *var, *rhat, *ess, *mcse;
+  int* truncated;
+};
+}  // namespace
+
+// so == nullptr: the reference-shaped call, every draw copied to `out`;
+// so != nullptr: no draw leaves the device, streaming summaries are returned instead
+static int sample_device_impl(
+    const StreamOutputs* so,
     const WalnutModelDesc* model, int num_params, const double* inits,
     size_t num_chains, unsigned int seed, unsigned int id, double init_radius,
     const double* init_inv_metric, int min_warmup_iter, int max_warmup_iter,
@@ -327,7 +339,11 @@ int walnutpie_sample_device(
         static_cast<size_t>(max_sampling_iter) +
         (save_warmup ? static_cast<size_t>(max_warmup_iter) : 0);
     const size_t draws_offset = static_cast<size_t>(num_params) * rows_per_chain;
-    if (out_size < C * draws_offset) {  // walnutpy.cpp:153-160
+    if (so && save_warmup) {
+      throw std::invalid_argument("save_warmup needs the draw buffer of "
+                                  "walnutpie_sample_device");
+    }
+    if (!so && out_size < C * draws_offset) {  // walnutpy.cpp:153-160
       std::stringstream ss;
       ss << "Output buffer too small. Expected at least " << C << " chains of "
          << draws_offset << " doubles, got " << out_size;
@@ -384,7 +400,10 @@ int walnutpie_sample_device(
     if (cudaGetDevice(&device) != cudaSuccess) device = 0;
     check(wb200_session_create(model, C, run_seed, 0, &t, device, &s, &e), e);
     check(wb200_session_init(s, inits, init_radius, init_inv_metric, nullptr, &e), e);
-    check(wb200_session_reserve_draws(s, static_cast<long long>(rows_per_chain), 0, &e), e);
+    // summaries-only: the draw buffer is a staging block folded into running sums
+    const long long stage_rows = std::min<long long>(std::max(max_sampling_iter, 1), 50);
+    check(wb200_session_reserve_draws(
+              s, so ? stage_rows : static_cast<long long>(rows_per_chain), 0, &e), e);
 
     phase("setup+init");
     auto say = [&](const std::string& m) {
@@ -498,8 +517,11 @@ int walnutpie_sample_device(
     sums.alloc(static_cast<size_t>(num_params) + 2);
     // The lock-step engine idles finished chains until the slowest one has done its
     // quota, so it gets the longest block that needs no controller decision.
+    // With min == max there is no controller decision to take: longer launches (less tail
+    // imbalance per iteration), still short enough for progress lines and Ctrl+C.
     auto block = [&](int done, int min_iter, int max_iter) {
       if (s->tick && done < min_iter) return min_iter - done;
+      if (min_iter == max_iter) return std::min(std::max(stride, 20), max_iter - done);
       return std::min(stride, max_iter - done);
     };
     while (warm_done < max_warmup_iter) {
@@ -523,6 +545,7 @@ int walnutpie_sample_device(
       }
     }
     check(wb200_session_freeze(s, &e), e);
+    if (so) check(wb200_session_stream_begin(s, so->max_lags, &e), e);
     phase("warmup");
     const int saved_warm = save_warmup ? warm_done : 0;
     // ---- sampling: R-hat of lp between blocks (sampler.hpp:132-151)
@@ -532,8 +555,10 @@ int walnutpie_sample_device(
       throttle();
       check(wb200_session_sample(s, n, 1, &e), e);
       launched();
-      flush_pending();
-      mark_block(saved_warm + samp_done + n);
+      if (!so) {
+        flush_pending();
+        mark_block(saved_warm + samp_done + n);
+      }
       progress(warm_done + samp_done, warm_done + samp_done + n, false);
       report_exceptions();
       samp_done += n;
@@ -557,9 +582,14 @@ int walnutpie_sample_device(
         if (r_hat <= rhat_converge_tol) break;
       }
     }
-    flush_pending();
+    if (!so) flush_pending();
     check(wb200_session_sync(s, &e), e);
     phase("sampling");
+    if (so) {
+      check(wb200_session_stream_summary(s, C > 1 ? so->rhat : nullptr, so->ess, so->mcse,
+                                         so->mean, so->var, so->truncated, &e), e);
+      phase("summaries");
+    }
     WB200_CUDA(cudaStreamSynchronize(copy_stream));
     phase("copy tail");
     // ---- outputs (walnutpy.cpp:196-221; handlers.hpp:73-100)
@@ -582,6 +612,67 @@ int walnutpie_sample_device(
                      std::chrono::steady_clock::now() - t_destroy).count());
   }
   return rc;
+}
+
+int walnutpie_sample_device(
+    const WalnutModelDesc* model, int num_params, const double* inits,
+    size_t num_chains, unsigned int seed, unsigned int id, double init_radius,
+    const double* init_inv_metric, int min_warmup_iter, int max_warmup_iter,
+    int min_sampling_iter, int max_sampling_iter, int max_trajectory_doublings,
+    int max_step_halvings, int min_micro_steps, double max_hamiltonian_error,
+    double step_size_converge_tol, double mass_converge_tol,
+    double rhat_converge_tol, double mass_init_count,
+    double mass_additive_smoothing, double max_macro_steps_target,
+    double step_size_init, double step_accept_rate_target,
+    double step_learning_rate, double step_gradient_decay,
+    double step_sq_gradient_decay, double step_stabilization,
+    double step_learn_rate_decay, bool save_warmup, double* out,
+    size_t out_size, int* final_lengths, double* stepsize_out,
+    double* inv_metric_out, int refresh, PRINT_CALLBACK print,
+    WalnutpyError** err) {
+  return sample_device_impl(
+      nullptr, model, num_params, inits, num_chains, seed, id, init_radius, init_inv_metric,
+      min_warmup_iter, max_warmup_iter, min_sampling_iter, max_sampling_iter,
+      max_trajectory_doublings, max_step_halvings, min_micro_steps, max_hamiltonian_error,
+      step_size_converge_tol, mass_converge_tol, rhat_converge_tol, mass_init_count,
+      mass_additive_smoothing, max_macro_steps_target, step_size_init,
+      step_accept_rate_target, step_learning_rate, step_gradient_decay,
+      step_sq_gradient_decay, step_stabilization, step_learn_rate_decay, save_warmup, out,
+      out_size, final_lengths, stepsize_out, inv_metric_out, refresh, print, err);
+}
+
+// The same call for runs whose draws are too many to keep or ship (SURVEY.md section
+// 8(f)-1: 65 536 chains x 1000 draws x 512 parameters are 268 GB): every argument of
+// walnutpie_sample_device up to save_warmup, then instead of the draw buffer the posterior
+// summaries of summary.hpp:371-405,594-769 computed by the streaming accumulators
+// (stream.cu).  Host arrays of num_params, any may be NULL.
+int walnutpie_sample_device_summary(
+    const WalnutModelDesc* model, int num_params, const double* inits,
+    size_t num_chains, unsigned int seed, unsigned int id, double init_radius,
+    const double* init_inv_metric, int min_warmup_iter, int max_warmup_iter,
+    int min_sampling_iter, int max_sampling_iter, int max_trajectory_doublings,
+    int max_step_halvings, int min_micro_steps, double max_hamiltonian_error,
+    double step_size_converge_tol, double mass_converge_tol,
+    double rhat_converge_tol, double mass_init_count,
+    double mass_additive_smoothing, double max_macro_steps_target,
+    double step_size_init, double step_accept_rate_target,
+    double step_learning_rate, double step_gradient_decay,
+    double step_sq_gradient_decay, double step_stabilization,
+    double step_learn_rate_decay, int max_lags, double* mean_out, double* var_out,
+    double* rhat_out, double* ess_out, double* mcse_out, int* truncated_out,
+    int* final_lengths, double* stepsize_out, double* inv_metric_out, int refresh,
+    PRINT_CALLBACK print, WalnutpyError** err) {
+  const StreamOutputs so{max_lags, mean_out, var_out, rhat_out, ess_out, mcse_out,
+                         truncated_out};
+  return sample_device_impl(
+      &so, model, num_params, inits, num_chains, seed, id, init_radius, init_inv_metric,
+      min_warmup_iter, max_warmup_iter, min_sampling_iter, max_sampling_iter,
+      max_trajectory_doublings, max_step_halvings, min_micro_steps, max_hamiltonian_error,
+      step_size_converge_tol, mass_converge_tol, rhat_converge_tol, mass_init_count,
+      mass_additive_smoothing, max_macro_steps_target, step_size_init,
+      step_accept_rate_target, step_learning_rate, step_gradient_decay,
+      step_sq_gradient_decay, step_stabilization, step_learn_rate_decay, false, nullptr, 0,
+      final_lengths, stepsize_out, inv_metric_out, refresh, print, err);
 }
 
 // Page-locked host memory for `out` / `inits`: makes the read-back of

@@ -28,22 +28,28 @@ LaunchShape shape_for_dim(int D) {
 }
 
 // (TARGET, T, K, CTA, min resident CTAs per SM -> register cap)
+// (TARGET, T, K, CTA, resident CTAs per SM asked of the adaptive / the sampling instance ->
+// register cap).  The sampling instance of the wide shapes fits 128 registers without
+// spilling since the start state moved to shared memory; the adaptive one needs 168.
 #ifndef WB200_MINB_32X2
-#define WB200_MINB_32X2 3
+#define WB200_MINB_32X2 4
 #endif
 #ifndef WB200_MINB_128X4
-#define WB200_MINB_128X4 3
+#define WB200_MINB_128X4 4
+#endif
+#ifndef WB200_MINB_128X4_ADAPT
+#define WB200_MINB_128X4_ADAPT 3
 #endif
 #define WB200_FOR_SHAPE(S, MACRO, TARGET)                                      \
   do {                                                                         \
-    if ((S).T == 32 && (S).K == 1) { MACRO(TARGET, 32, 1, 128, 4); }           \
-    else if ((S).T == 32 && (S).K == 2) { MACRO(TARGET, 32, 2, 128, WB200_MINB_32X2); }      \
-    else if ((S).T == 64) { MACRO(TARGET, 64, 2, 64, 6); }                     \
-    else if ((S).T == 128 && (S).K == 2) { MACRO(TARGET, 128, 2, 128, 3); }    \
-    else if ((S).T == 128 && (S).K == 4) { MACRO(TARGET, 128, 4, 128, WB200_MINB_128X4); }    \
-    else if ((S).T == 256 && (S).K == 2) { MACRO(TARGET, 256, 2, 256, 2); }    \
-    else if ((S).T == 256 && (S).K == 4) { MACRO(TARGET, 256, 4, 256, 1); }    \
-    else { MACRO(TARGET, 512, 4, 512, 1); }                                    \
+    if ((S).T == 32 && (S).K == 1) { MACRO(TARGET, 32, 1, 128, 4, 4); }        \
+    else if ((S).T == 32 && (S).K == 2) { MACRO(TARGET, 32, 2, 128, WB200_MINB_32X2, WB200_MINB_32X2); } \
+    else if ((S).T == 64) { MACRO(TARGET, 64, 2, 64, 6, 6); }                  \
+    else if ((S).T == 128 && (S).K == 2) { MACRO(TARGET, 128, 2, 128, 3, 3); } \
+    else if ((S).T == 128 && (S).K == 4) { MACRO(TARGET, 128, 4, 128, WB200_MINB_128X4_ADAPT, WB200_MINB_128X4); } \
+    else if ((S).T == 256 && (S).K == 2) { MACRO(TARGET, 256, 2, 256, 2, 2); } \
+    else if ((S).T == 256 && (S).K == 4) { MACRO(TARGET, 256, 4, 256, 1, 1); } \
+    else { MACRO(TARGET, 512, 4, 512, 1, 1); }                                 \
   } while (0)
 
 #define WB200_FOR_TARGET(KIND, S, MACRO)                                       \
@@ -167,8 +173,8 @@ __global__ void __launch_bounds__(CTA) init_kernel(const InitParams ip) {
       }
       invM[k][0] = 1.0 / mass[k][0]; invM[k][1] = 1.0 / mass[k][1];
       rho[k][0] = z0 * sqrt(mass[k][0]); rho[k][1] = z1 * sqrt(mass[k][1]);
-      kin0 += invM[k][0] * (rho[k][0] * rho[k][0]);
-      kin0 += invM[k][1] * (rho[k][1] * rho[k][1]);
+      kin0 = madd(invM[k][0], rho[k][0] * rho[k][0], kin0);
+      kin0 = madd(invM[k][1], rho[k][1] * rho[k][1], kin0);
     }
     double r0[2] = {lp_part, kin0};
     grp.sum(r0);
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(CTA) init_kernel(const InitParams ip) {
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           rs[k][v] = rs[k][v] + hs * g2[k][v];
-          kin += invM[k][v] * (rs[k][v] * rs[k][v]);
+          kin = madd(invM[k][v], rs[k][v] * rs[k][v], kin);
         }
       }
       double r[2] = {lp2, kin};
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(CTA) orbit_kernel(const OrbitParams op) {
   } else {
     double kin = 0.0;
     for (int k = 0; k < K; ++k)
-      for (int v = 0; v < 2; ++v) kin += r.im[k][v] * (r.rho[k][v] * r.rho[k][v]);
+      for (int v = 0; v < 2; ++v) kin = madd(r.im[k][v], r.rho[k][v] * r.rho[k][v], kin);
     double s[2] = {lp_part, kin};
     grp.sum(s);
     lp = s[0]; H = s[0] + (-0.5 * s[1]);
@@ -309,34 +315,35 @@ static int sm_count(int device) {
   return n;
 }
 
-// both instances get the opt-in for > 48 KB of dynamic shared memory; the grid is sized
-// by the one with fewer resident CTAs
-#define WB200_OCC(TARGET, T_, K_, CTA_, MINB_)                                 \
-  occ = std::min(                                                              \
-      blocks_per_sm(walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, false>, CTA_, \
-                    dyn_smem),                                                 \
-      blocks_per_sm(walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, true>, CTA_,  \
-                    dyn_smem))
-#define WB200_LAUNCH_CHAIN(TARGET, T_, K_, CTA_, MINB_)                        \
+#define WB200_OCC(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)                      \
+  do {                                                                         \
+    occ_adapt = blocks_per_sm(                                                 \
+        walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true>, CTA_, dyn_smem); \
+    occ_sample = blocks_per_sm(                                                \
+        walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false>, CTA_, dyn_smem); \
+  } while (0)
+#define WB200_LAUNCH_CHAIN(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)             \
   do {                                                                         \
     if (p.adapt) {                                                             \
-      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, true>          \
-          <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
+      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true>        \
+          <<<s.grid_adapt, CTA_, dyn_smem, s.stream>>>(p);                     \
     } else {                                                                   \
-      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_, false>         \
+      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false>       \
           <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
     }                                                                          \
   } while (0)
-#define WB200_LAUNCH_INIT(TARGET, T_, K_, CTA_, MINB_)                         \
+#define WB200_LAUNCH_INIT(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)              \
   init_kernel<TARGET, T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(ip)
-#define WB200_LAUNCH_ORBIT(TARGET, T_, K_, CTA_, MINB_)                        \
+#define WB200_LAUNCH_ORBIT(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)             \
   orbit_kernel<TARGET, T_, K_, CTA_><<<grid, CTA_, 0, stream>>>(op)
 
-int occupancy_for(int kind, const LaunchShape& shape, int ld) {
-  int occ = 1;
+// resident CTAs per SM of the adaptive and of the sampling instance
+void occupancy_for(int kind, const LaunchShape& shape, int ld, int* adapt, int* sample) {
+  int occ_adapt = 1, occ_sample = 1;
   const size_t dyn_smem = chain_dyn_smem(shape, ld);
   WB200_FOR_TARGET(kind, shape, WB200_OCC);
-  return occ;
+  *adapt = occ_adapt;
+  *sample = occ_sample;
 }
 
 void launch_chains(wb200_session& s, int n_iter, int adapt, bool store) {

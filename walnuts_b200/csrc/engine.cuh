@@ -91,7 +91,7 @@ struct LaunchShape {
   int T, K, cta, chains_per_cta;
 };
 LaunchShape shape_for_dim(int D);
-int occupancy_for(int kind, const LaunchShape& shape, int ld);
+void occupancy_for(int kind, const LaunchShape& shape, int ld, int* adapt, int* sample);
 
 // errors.hpp:30-33: the user pressed Ctrl+C (interrupts.hpp)
 struct InterruptException {};
@@ -149,7 +149,7 @@ struct wb200_session {
   uint32_t seed = 0, chain_offset = 0;
   WalnutTuning tuning{};
   wb200::LaunchShape shape{};
-  int slots = 0, grid = 0;
+  int slots = 0, grid = 0, grid_adapt = 0;  // sampling / adaptive instance grids
   bool frozen = false, initialised = false;
   long long draw_cap = 0, rows_written = 0;
   bool trace = false;
@@ -189,6 +189,7 @@ void tick_chain_rows(wb200_session& s, long long* rows_host);
 void tick_take_rows(wb200_session& s, long long* rows_dev);
 void stream_end(wb200_session& s);
 void stream_update(wb200_session& s, const long long* rows_c, long long rows_uniform);
+void stream_flush(wb200_session& s);
 void tick_abort_inflight(wb200_session& s);
 unsigned long long tick_count(const wb200_session& s);
 void launch_orbit(int kind, int D, int ld, int C, const double* tparam,

@@ -294,6 +294,12 @@ void stream_update(wb200_session& s, const long long* rows_c, long long rows_uni
   st.blocks += 1;
 }
 
+// fold the rows staged by iteration-quota launches (the same count for every chain)
+void stream_flush(wb200_session& s) {
+  if (s.rows_written > 0) stream_update(s, nullptr, s.rows_written);
+  s.rows_written = 0;
+}
+
 // host copy of the per-chain counts -> {K, N, min_len} over chains with >= 3 draws
 static void stream_counts(wb200_session& s, double* K, double* N, double* min_len) {
   StreamState& st = *s.acc;
@@ -327,6 +333,7 @@ static void stream_chain_stats(wb200_session& s) {
 void stream_phase1(wb200_session& s, double* out_host) {
   StreamState& st = *s.acc;
   const int D = s.D;
+  stream_flush(s);
   stream_chain_stats(s);
   DeviceBuffer<double> out;
   out.alloc(2 * static_cast<size_t>(D));
@@ -471,6 +478,7 @@ int wb200_session_stream_counts(wb200_session* s, long long* counts, WalnutpyErr
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));
     if (!s->acc) throw std::runtime_error("streaming summaries have not been started");
+    stream_flush(*s);
     WB200_CUDA(cudaMemcpyAsync(counts, s->acc->n.ptr, s->C * sizeof(long long),
                                cudaMemcpyDeviceToHost, s->stream));
     WB200_CUDA(cudaStreamSynchronize(s->stream));

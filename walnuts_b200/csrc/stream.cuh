@@ -16,6 +16,7 @@ struct StreamState {
 void stream_begin(wb200_session& s, int max_lags);
 void stream_end(wb200_session& s);
 void stream_update(wb200_session& s, const long long* rows_c, long long rows_uniform);
+void stream_flush(wb200_session& s);
 void stream_phase1(wb200_session& s, double* out_host);
 void stream_phase2(wb200_session& s, const double* reduced1, double* out_host);
 void stream_finish(int D, int T, const double* reduced1, const double* reduced2, double* rhat,

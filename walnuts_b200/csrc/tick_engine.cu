@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(CTA) tick_init_state_kernel(const TickInitPara
       sd[k][v] = p.mass_init_count * (1.0 / mass[k][v]);
       ss[k][v] = p.mass_init_count * mass[k][v];
       rho[k][v] = z[v] * sqrt(mass[k][v]);
-      kin += (1.0 / mass[k][v]) * (rho[k][v] * rho[k][v]);
+      kin = madd(1.0 / mass[k][v], rho[k][v] * rho[k][v], kin);
     }
   }
   V::store(est_row + 0 * ld, ld, tid, zero);
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(CTA) tick_search_update_kernel(const TickInitP
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       const double rs = (rho[k][v] + hs * g0[k][v]) + hs * g1[k][v];
-      kin += (1.0 / mass[k][v]) * (rs * rs);
+      kin = madd(1.0 / mass[k][v], rs * rs, kin);
     }
   }
   double r[1] = {kin};

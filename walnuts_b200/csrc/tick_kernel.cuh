@@ -92,7 +92,7 @@ struct TickRunner {
     for (int k = 0; k < K; ++k) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        kin = __dadd_rn(kin, __dmul_rn(im[k][v], __dmul_rn(rho[k][v], rho[k][v])));
+        kin = madd(im[k][v], __dmul_rn(rho[k][v], rho[k][v]), kin);
       }
     }
     return kin;
@@ -108,8 +108,8 @@ struct TickRunner {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
         double sd = __dmul_rn(im[k][v], __dadd_rn(th[k][v], -thF[k][v]));
-        a = __dadd_rn(a, __dmul_rn(rho[k][v], sd));
-        b = __dadd_rn(b, __dmul_rn(rhoF[k][v], sd));
+        a = madd(rho[k][v], sd, a);
+        b = madd(rhoF[k][v], sd, b);
       }
     }
   }
@@ -143,8 +143,8 @@ struct TickRunner {
     for (int k = 0; k < K; ++k) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        rho[k][v] = __dadd_rn(rho[k][v], __dmul_rn(hh, g[k][v]));
-        th[k][v] = __dadd_rn(th[k][v], __dmul_rn(__dmul_rn(h, im[k][v]), rho[k][v]));
+        rho[k][v] = madd(hh, g[k][v], rho[k][v]);
+        th[k][v] = madd(__dmul_rn(h, im[k][v]), rho[k][v], th[k][v]);
       }
     }
     V::store(th_row, ld, tid, th);
@@ -265,7 +265,7 @@ struct TickRunner {
         for (int k = 0; k < K; ++k) {
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
-            rho[k][v] = __dadd_rn(rho[k][v], __dmul_rn(hh, g[k][v]));
+            rho[k][v] = madd(hh, g[k][v], rho[k][v]);
           }
         }
         evals += 1;
@@ -528,7 +528,7 @@ struct TickRunner {
                 const double y = e == 0 ? cur[k][v] : gsel[k][v];
                 mu[k][v] = __dadd_rn(mu[k][v], __dadd_rn(y, -mu[k][v]) / sc.est_w);
                 const double d = __dadd_rn(y, -mu[k][v]);
-                S[k][v] = __dadd_rn(__dmul_rn(gamma, S[k][v]), __dmul_rn(d, d));
+                S[k][v] = madd(gamma, S[k][v], __dmul_rn(d, d));
               }
             }
             V::store(est_row + (2 * e) * ld, ld, tid, mu);

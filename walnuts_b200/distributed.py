@@ -166,3 +166,25 @@ def rhat_from_dimension_moments(m) -> np.ndarray:
     M = m[3 * D]
     between = (m[D:2 * D] - m[:D] ** 2 / M) / (M - 1.0)
     return np.sqrt(1.0 + between / (m[2 * D:3 * D] / M))
+
+
+def stream_summary_all_ranks(session, device: Optional[torch.device] = None):
+    """R-hat / ESS / MCSE / mean / variance over the streamed draws of ALL ranks' chains
+    (summary.hpp:594-769): the two small all-reduces of the streaming summaries
+    (include/walnuts_b200.h) -- phase 1 {sum mu, sum n mu}[D] + {K, N} (SUM) and min_len
+    (MIN); phase 2, centred on the global means, {between, within, pooled SS,
+    sum_k acov_k(t)}[D] (SUM) -- then the Geyer loop on the combined sums.  The result is
+    identical on every rank and equal to that of one session holding all the chains."""
+    from .sampler import stream_finish
+    device = device or torch.device("cpu")
+    D = session.num_params
+    r1 = torch.as_tensor(session.stream_phase1(), device=device)
+    mn = r1[2 * D + 2:].clone()
+    _all_reduce(r1, dist.ReduceOp.SUM)
+    _all_reduce(mn, dist.ReduceOp.MIN)
+    r1[2 * D + 2] = mn[0]
+    r1h = r1.cpu().numpy()
+    r2 = torch.as_tensor(session.stream_phase2(r1h), device=device)
+    _all_reduce(r2, dist.ReduceOp.SUM)
+    return stream_finish(D, session._stream_lags, r1h, r2.cpu().numpy(),
+                         want_rhat=r1h[2 * D] >= 2)

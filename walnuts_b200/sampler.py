@@ -169,6 +169,55 @@ def walnuts_device(
     return outputs
 
 
+def walnuts_device_summary(logp: DeviceModel, *, num_chains: int = 4, seed: Optional[int] = None,
+                           id: int = 1, inits: Optional[np.ndarray] = None,
+                           init_radius: float = 2.0,
+                           init_inv_metric: Optional[np.ndarray] = None, max_lags: int = 32,
+                           refresh: int = 0, **tuning):
+    """``walnuts_device`` for runs whose draws are too many to keep: the same sampler run
+    (``walnutpie_sample_device_summary``), returning the posterior summaries computed on
+    the device by streaming accumulators -- ``mean``, ``variance``, ``r_hat``, ``ess``,
+    ``mcse`` per parameter (summary.hpp:371-405,594-769), ``truncated`` flags, per-chain
+    ``stepsize`` / ``inv_metric`` and the iteration counts.  ``tuning`` takes the tuning
+    keywords of ``walnuts_device`` (reference defaults)."""
+    if not isinstance(logp, DeviceModel):
+        raise TypeError("walnuts_b200 samples device models only")
+    D = logp.num_params
+    t = make_tuning(**tuning)
+    seed = prepare_seed(seed)
+    if inits is not None:
+        inits = np.ascontiguousarray(inits, dtype=np.float64)
+        if inits.shape == (D,):
+            inits = np.ascontiguousarray(np.repeat(inits[np.newaxis], num_chains, axis=0))
+        elif inits.shape != (num_chains, D):
+            raise ValueError(f"Invalid inits size. Expected a {(D,)} or "
+                             f"{(num_chains, D)} matrix.")
+    init_inv_metric = prepare_inv_metric(init_inv_metric, (D,), num_chains)
+    out = {k: np.zeros(D) for k in ("mean", "variance", "r_hat", "ess", "mcse")}
+    cut = np.zeros(D, np.int32)
+    lengths = np.zeros(2 * num_chains, np.int32)
+    stepsize = np.zeros(num_chains)
+    inv_metric = np.zeros((num_chains, D))
+    desc = logp.desc()
+    with _reraise_callback_errors(logp):
+        _ffi._ffi_sample_device_summary(
+            ctypes.byref(desc), D, inits, num_chains, seed, id, init_radius, init_inv_metric,
+            t.min_warmup_iter, t.max_warmup_iter, t.min_sampling_iter, t.max_sampling_iter,
+            t.max_trajectory_doublings, t.max_step_halvings, t.min_micro_steps,
+            t.max_hamiltonian_error, t.step_size_converge_tol, t.mass_converge_tol,
+            t.rhat_converge_tol, t.mass_init_count, t.mass_additive_smoothing,
+            t.max_macro_steps_target, t.step_size_init, t.step_accept_rate_target,
+            t.step_learning_rate, t.step_gradient_decay, t.step_sq_gradient_decay,
+            t.step_stabilization, t.step_learn_rate_decay, int(max_lags), out["mean"],
+            out["variance"], out["r_hat"] if num_chains > 1 else None, out["ess"],
+            out["mcse"], cut, lengths, stepsize, inv_metric, refresh, _ffi.print_callback)
+    # final_lengths reports SAVED warm-up draws (0 here); the iterations run are in the stats
+    out.update(truncated=cut, stepsize=stepsize, inv_metric=inv_metric,
+               warmup_iters=_ffi.last_run_stats()["warmup_iters"],
+               sampling_iters=int(lengths[num_chains]))
+    return out
+
+
 class Session:
     """A device-resident batch of chains (include/walnuts_b200.h, session API).
 
@@ -340,6 +389,41 @@ class Session:
                             out["ess"], out["mcse"], out["mean"], out["variance"])
         return out
 
+    # -- streaming summaries (include/walnuts_b200.h) ---------------------------------
+    def stream_begin(self, max_lags: int = 32):
+        """From now on storing ``sample`` / ``sample_ticks`` calls fold their draws into
+        per-chain running sums instead of keeping them: the reserved draw buffer becomes
+        a staging block (``reserve(block)`` first)."""
+        _ffi.session_stream_begin(self._h, int(max_lags))
+        self._stream_lags = int(max_lags)
+        return self
+
+    def stream_counts(self) -> np.ndarray:
+        n = np.zeros(self.num_chains, np.int64)
+        _ffi.session_stream_counts(self._h, n)
+        return n
+
+    def stream_phase1(self) -> np.ndarray:
+        out = np.zeros(2 * self.num_params + 3)
+        _ffi.session_stream_phase1(self._h, out)
+        return out
+
+    def stream_phase2(self, reduced1: np.ndarray) -> np.ndarray:
+        out = np.zeros((3 + self._stream_lags) * self.num_params)
+        _ffi.session_stream_phase2(self._h, np.ascontiguousarray(reduced1, np.float64), out)
+        return out
+
+    def stream_summary(self):
+        """R-hat, ESS, MCSE, pooled mean and variance of everything streamed so far
+        (summary.hpp:594-769), plus ``truncated`` flags per dimension."""
+        D = self.num_params
+        out = {k: np.zeros(D) for k in ("r_hat", "ess", "mcse", "mean", "variance")}
+        cut = np.zeros(D, np.int32)
+        _ffi.session_stream_summary(self._h, out["r_hat"] if self.num_chains > 1 else None,
+                                    out["ess"], out["mcse"], out["mean"], out["variance"], cut)
+        out["truncated"] = cut
+        return out
+
     def warmup_deviation(self, sums_device_ptr: int):
         out = np.zeros(2)
         _ffi.session_warmup_deviation(self._h, sums_device_ptr, out)
@@ -365,6 +449,20 @@ class Session:
         n = ctypes.c_ulonglong(0)
         _ffi.session_logp_exceptions(self._h, ctypes.byref(n))
         return n.value
+
+
+def stream_finish(num_params: int, max_lags: int, reduced1, reduced2, want_rhat: bool = True):
+    """The summaries from the (all-reduced) payloads of ``Session.stream_phase1`` /
+    ``stream_phase2``; identical on every rank."""
+    D = int(num_params)
+    out = {k: np.zeros(D) for k in ("r_hat", "ess", "mcse", "mean", "variance")}
+    cut = np.zeros(D, np.int32)
+    _ffi.stream_finish(D, int(max_lags), np.ascontiguousarray(reduced1, np.float64),
+                       np.ascontiguousarray(reduced2, np.float64),
+                       out["r_hat"] if want_rhat else None, out["ess"], out["mcse"],
+                       out["mean"], out["variance"], cut)
+    out["truncated"] = cut
+    return out
 
 
 def orbit(model: DeviceModel, theta, rho, inv_mass, step: float, num_steps: int):
