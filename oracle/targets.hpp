@@ -24,8 +24,12 @@ using Vec = std::vector<double>;
 // of squares of OnlineMoments).  Default = the reference's baseline x86-64 build: product
 // and sum round separately (this file is compiled with -ffp-contract=off).  "Fused" = one
 // rounding, what the device kernels ship (walnuts_b200/csrc/chain_kernel.cuh, kFusedArith)
-// and what a contracting build of the reference would do.  Process-wide switch; the
-// reference-policy oracle is the one pinned bit for bit to the reference's headers.
+// and what a contracting build of the reference would do.  The fused policy also takes
+// the two algebraic short cuts of the device estimators: the common weight of the two
+// discounted Welford estimators cancels in var_draws / var_scores
+// (adaptive_walnuts.hpp:89-94 -> sqrt(S_draw / S_score)) and the mean update multiplies
+// by one reciprocal of that scalar weight (online_moments.hpp:187).  Process-wide switch;
+// the reference-policy oracle is the one pinned bit for bit to the reference's headers.
 inline bool& fused_arith() {
   static bool fused = false;
   return fused;

@@ -286,8 +286,15 @@ class OnlineMoments {
       throw std::invalid_argument("discount_factor must be in [0, 1]");
     }
     weight_ = gamma * weight_ + 1;
-    for (std::size_t i = 0; i < y.size(); ++i) {
-      mean_[i] += (y[i] - mean_[i]) / weight_;
+    if (fused_arith()) {  // one reciprocal of the scalar weight, then multiply-adds
+      const double r_w = 1.0 / weight_;
+      for (std::size_t i = 0; i < y.size(); ++i) {
+        mean_[i] = std::fma(y[i] - mean_[i], r_w, mean_[i]);
+      }
+    } else {
+      for (std::size_t i = 0; i < y.size(); ++i) {
+        mean_[i] += (y[i] - mean_[i]) / weight_;
+      }
     }
     for (std::size_t i = 0; i < y.size(); ++i) {
       double d = y[i] - mean_[i];
@@ -295,6 +302,8 @@ class OnlineMoments {
     }
   }
   const Vec& mean() const { return mean_; }
+  const Vec& sum_sq_dev() const { return ssd_; }
+  double weight() const { return weight_; }
   Vec variance() const {  // :225-230
     Vec v(mean_.size());
     if (!(weight_ > 0)) {
@@ -692,6 +701,14 @@ class MassEstimator {
     score_.discount_observe(gamma, grad);
   }
   Vec inv_mass_estimate() const {  // :89-94
+    if (fused_arith() && draw_.weight() > 0) {
+      // both estimators carry the same weight (:54-80): it cancels in the ratio
+      const Vec& ds = draw_.sum_sq_dev();
+      const Vec& ss = score_.sum_sq_dev();
+      Vec r(ds.size());
+      for (std::size_t i = 0; i < r.size(); ++i) r[i] = std::sqrt(ds[i] / ss[i]);
+      return r;
+    }
     Vec dv = draw_.variance(), sv = score_.variance();
     Vec r(dv.size());
     for (std::size_t i = 0; i < r.size(); ++i) r[i] = std::sqrt(dv[i] / sv[i]);

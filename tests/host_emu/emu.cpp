@@ -77,7 +77,7 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   }
   // freeze_kernel
   for (int i = 0; i < ld; ++i) {
-    inv_mass[i] = std::sqrt((est[1 * ld + i] / sc.est_w) / (est[3 * ld + i] / sc.est_w));
+    inv_mass[i] = metric_from_sums(est[1 * ld + i], est[3 * ld + i], sc.est_w);
   }
   sc.step = std::exp(sc.adam_x);
   sc.min_micro = min_micro_steps(sc, p);
@@ -225,7 +225,7 @@ static void run_tick(const EmuTuning& t, int D, const double* tparam, uint32_t s
   }
   if (rows_out) rows_out[0] = warm_ticks >= 0 ? ts.rows : n_warmup;
   for (int i = 0; i < ld; ++i) {
-    inv_mass[i] = std::sqrt((est[1 * ld + i] / sc.est_w) / (est[3 * ld + i] / sc.est_w));
+    inv_mass[i] = metric_from_sums(est[1 * ld + i], est[3 * ld + i], sc.est_w);
   }
   sc.step = std::exp(sc.adam_x);
   sc.min_micro = min_micro_steps(sc, p);

@@ -65,6 +65,15 @@ __device__ __forceinline__ double madd(double a, double b, double c) {
   if constexpr (kFusedArith) return __fma_rn(a, b, c);
   return __dadd_rn(__dmul_rn(a, b), c);
 }
+// The fused policy also spares the estimators two of their fp64 divisions per element
+// (35-60 instructions each): the two discounted Welford estimators of MassEstimator share
+// one weight (adaptive_walnuts.hpp:54-80), so it cancels in var_draws / var_scores
+// (:89-94), and the mean update divides by that scalar weight (online_moments.hpp:187),
+// i.e. multiplies by a reciprocal taken once per transition.
+__device__ __forceinline__ double metric_from_sums(double S_draw, double S_score, double w) {
+  if constexpr (kFusedArith) return sqrt(S_draw / S_score);
+  return sqrt((S_draw / w) / (S_score / w));
+}
 
 enum TargetKind : int { kStdNormal = 0, kDiagGaussian = 1, kFunnel = 2,
                         kLogistic = 3, kBatchCallback = 4 };
@@ -560,8 +569,10 @@ __device__ __noinline__ int adapt_begin(const ChainParams& p, Group<T> grp, Chai
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       // MassEstimator::inv_mass_estimate, adaptive_walnuts.hpp:89-94
-      im[k][v] = sqrt_noinline(div_noinline(div_noinline(Sd[k][v], est_w),
-                                            div_noinline(Ss[k][v], est_w)));
+      im[k][v] = kFusedArith
+                     ? sqrt_noinline(div_noinline(Sd[k][v], Ss[k][v]))
+                     : sqrt_noinline(div_noinline(div_noinline(Sd[k][v], est_w),
+                                                  div_noinline(Ss[k][v], est_w)));
     }
   }
   V::store(im_row, ld, tid, im);
@@ -587,6 +598,7 @@ __device__ __noinline__ int adapt_end(const ChainParams& p, Group<T> grp, ChainS
   tgt.grad(cur, gsel, lp_dummy, grp);  // grad_select (cached by the reference)
   const double gamma = 1.0 - 1.0 / (p.mass_init_count + static_cast<double>(sc.warm_iter));
   const double est_w = gamma * sc.est_w + 1.0;
+  const double r_w = 1.0 / est_w;
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     double mu[K][2], S[K][2];
@@ -598,7 +610,9 @@ __device__ __noinline__ int adapt_end(const ChainParams& p, Group<T> grp, ChainS
       for (int v = 0; v < 2; ++v) {
         const double y = e == 0 ? cur[k][v] : gsel[k][v];
         // online_moments.hpp:185-191 (both factors see the updated mean)
-        mu[k][v] = __dadd_rn(mu[k][v], div_noinline(__dadd_rn(y, -mu[k][v]), est_w));
+        mu[k][v] = kFusedArith
+                       ? madd(__dadd_rn(y, -mu[k][v]), r_w, mu[k][v])
+                       : __dadd_rn(mu[k][v], div_noinline(__dadd_rn(y, -mu[k][v]), est_w));
         const double d = __dadd_rn(y, -mu[k][v]);
         S[k][v] = madd(gamma, S[k][v], __dmul_rn(d, d));
       }

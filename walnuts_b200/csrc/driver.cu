@@ -32,7 +32,7 @@ __global__ void warmup_sums_kernel(ChainParams p, double* sums) {
     for (int c = 0; c < p.C; ++c) {
       const double* est_row = p.est + static_cast<long long>(c) * 4 * p.ld;
       const double w = p.sc[c].est_w;
-      const double im = sqrt((est_row[1 * p.ld + d] / w) / (est_row[3 * p.ld + d] / w));
+      const double im = metric_from_sums(est_row[1 * p.ld + d], est_row[3 * p.ld + d], w);
       acc += -log(im);  // AdaptiveWalnuts::log_mass, adaptive_walnuts.hpp:320-323
     }
     sums[d] = acc;
@@ -65,7 +65,7 @@ __global__ void warmup_deviation_kernel(ChainParams p, const double* sums,
   double acc = 0.0;
   for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
     const double gm = exp(sums[d] / count);
-    const double im = sqrt((est_row[1 * p.ld + d] / w) / (est_row[3 * p.ld + d] / w));
+    const double im = metric_from_sums(est_row[1 * p.ld + d], est_row[3 * p.ld + d], w);
     const double mass = exp(-log(im));  // snap.mass = exp(log_mass), adapt.hpp:137
     const double r = (mass - gm) / gm;
     acc += r * r;

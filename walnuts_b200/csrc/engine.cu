@@ -230,7 +230,7 @@ __global__ void freeze_kernel(ChainParams p) {
     const int c = static_cast<int>(i / p.ld), e = static_cast<int>(i % p.ld);
     const double* est_row = p.est + static_cast<long long>(c) * 4 * p.ld;
     const double w = p.sc[c].est_w;
-    p.inv_mass[i] = sqrt((est_row[1 * p.ld + e] / w) / (est_row[3 * p.ld + e] / w));
+    p.inv_mass[i] = metric_from_sums(est_row[1 * p.ld + e], est_row[3 * p.ld + e], w);
     if (e == 0) {
       ChainScalars& sc = p.sc[c];
       sc.step = exp(sc.adam_x);

@@ -161,7 +161,7 @@ struct TickRunner {
       for (int k = 0; k < K; ++k) {
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
-          im[k][v] = sqrt((Sd[k][v] / sc.est_w) / (Ss[k][v] / sc.est_w));
+          im[k][v] = metric_from_sums(Sd[k][v], Ss[k][v], sc.est_w);
         }
       }
     } else {
@@ -516,6 +516,7 @@ struct TickRunner {
           const double gamma =
               1.0 - 1.0 / (p.mass_init_count + static_cast<double>(sc.warm_iter));
           sc.est_w = gamma * sc.est_w + 1.0;
+          const double r_w = 1.0 / sc.est_w;
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             double mu[K][2], S[K][2];
@@ -526,7 +527,9 @@ struct TickRunner {
 #pragma unroll
               for (int v = 0; v < 2; ++v) {
                 const double y = e == 0 ? cur[k][v] : gsel[k][v];
-                mu[k][v] = __dadd_rn(mu[k][v], __dadd_rn(y, -mu[k][v]) / sc.est_w);
+                mu[k][v] = kFusedArith
+                               ? madd(__dadd_rn(y, -mu[k][v]), r_w, mu[k][v])
+                               : __dadd_rn(mu[k][v], __dadd_rn(y, -mu[k][v]) / sc.est_w);
                 const double d = __dadd_rn(y, -mu[k][v]);
                 S[k][v] = madd(gamma, S[k][v], __dmul_rn(d, d));
               }
