@@ -3,32 +3,38 @@
 per second and min-ESS per second vs the CPU reference sampler).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c2|c3|c4|c5]
+                    [--workload c2|c3|c4|c5] [--no-extra-workloads]
 
-Workload (config.workload "c2"): BASELINE.json configs[1] — 1000-dimensional
-ill-conditioned diagonal Gaussian (condition number 1e4), 4096 chains per GPU,
-fp64, max_trajectory_doublings 10, max_step_halvings 5, 300 adaptive warm-up
-iterations (untimed set-up) then sampling.  One STEP = `--iters-per-step` (10)
-WALNUTS transitions of every chain on the GPU, draws stored in HBM.
+The line the driver reads (config.workload "c2"): BASELINE.json configs[1] -- the
+1000-dimensional ill-conditioned diagonal Gaussian (condition number 1e4), 4096 chains per
+GPU, fp64, max_trajectory_doublings 10, max_step_halvings 5, 300 adaptive warm-up
+iterations (untimed set-up) then sampling.  One STEP = `--iters-per-step` (10) WALNUTS
+transitions of every chain on the GPU.
 
  * value      gradient evaluations / s over exactly K steps, state resident in HBM,
               timed with CUDA events on the launching stream (max over ranks)
- * e2e        the same metric through the reference-facing C-ABI call
-              walnutpie_sample_device with (pinned) HOST buffers: session set-up, initial
-              positions uploaded, adaptive warm-up + K steps of sampling, every draw copied
-              back to the host (overlapped with sampling), all inside the timed call
- * roofline   7*D*8 algorithmic bytes per gradient evaluation (SURVEY.md §8(d))
-              against the measured HBM copy bandwidth
+ * e2e        the same metric through the reference-facing C-ABI call with pinned HOST
+              buffers: walnutpie_sample_device_summary -- session set-up, initial positions
+              uploaded, adaptive warm-up + K steps of sampling, and the posterior summaries
+              (mean, variance, R-hat, ESS, MCSE per parameter, computed on the device by the
+              streaming accumulators) read back; `e2e_all_draws` is the same run through
+              walnutpie_sample_device, every draw copied back to the host as the reference
+              returns them (PCIe-bound: 3.3 GB per step at c2)
+ * roofline   7*D*8 algorithmic bytes per gradient evaluation (SURVEY.md section 8(d))
+              against the measured HBM copy bandwidth; the chain-resident kernel keeps the
+              state on chip, so `roofline_binding` restates the kernel against what does
+              bind it -- fp64 instruction issue (per-evaluation instruction counts from the
+              committed ncu capture x the live evaluation rate)
  * cpu_baseline  the reference's own sampler (oracle/_ref: unmodified headers on the
               Eigen shim; falls back to the oracle port) one chain per host core
+ * workloads  short runs of the other BASELINE.json configs in the same process, each with
+              its own roofline, clocks and posterior / R-hat check: c3 (Neal's funnel D=100,
+              16384 chains), c4 (Bayesian logistic regression N=100k, D=512, 8192 chains:
+              lock-step engine + tcgen05 gradient) and c5 (65,536 logistic chains sharded
+              over the ranks -- strong scaling -- with the R-hat AND ESS moments combined by
+              NCCL all-reduce inside a timed summary phase)
 With --impl reference the reference arm alone is timed (rank 0 only).
-
-Other workloads (not the driver's default line): c3 = Neal's funnel D=100, 16384 chains
-(same code path as c2); c4 = Bayesian logistic regression N=100k, D=512, 8192 chains on the
-lock-step engine with the tcgen05 gradient -- a step is 100 ticks (one batched gradient each),
-the roofline is 4*N*D flops per chain-gradient against the measured sustained bf16 peak, e2e
-goes through the C-ABI session calls from host X / y to host draws; c5 = c4 with 65,536
-chains in total sharded over the ranks (strong scaling, NCCL all-reduce of R-hat moments).
+--workload c3|c4|c5 runs that workload alone as the main line (full length, CPU leg).
 stdout carries exactly one JSON line.
 """
 from __future__ import annotations
@@ -62,19 +68,24 @@ ELEMENTWISE = {
     "c2": dict(label="c2: 1000-dim ill-conditioned diagonal Gaussian (cond 1e4), "
                      "4096 chains per GPU, fp64",
                kind="diag_gaussian", D=D, chains=CHAINS_PER_GPU, init_radius=2.0,
-               warmup_iters=WARMUP_ITERS, max_doublings=MAX_DOUBLINGS,
+               warmup_iters=WARMUP_ITERS, burn_iters=0, max_doublings=MAX_DOUBLINGS,
                max_halvings=MAX_HALVINGS, cpu_warm=300, cpu_samp=1000,
                kernel="walnuts_chain_kernel<DiagGaussianTarget<128,4>, ADAPT=false>"),
+    # the funnel's v relaxes with a time constant of ~1200 iterations after the adaptive
+    # phase (tests/test_gpu_c3.py): 6000 unstored sampling iterations precede the timed
+    # steps so that the posterior check is against the true moments
     "c3": dict(label="c3: Neal's funnel D=100, 16384 chains per GPU, fp64",
                kind="funnel", D=100, chains=16384, init_radius=1.0, warmup_iters=300,
-               max_doublings=10, max_halvings=8, cpu_warm=300, cpu_samp=300,
+               burn_iters=6000, max_doublings=10, max_halvings=8, cpu_warm=300, cpu_samp=300,
                kernel="walnuts_chain_kernel<FunnelTarget<32,2>, ADAPT=false>"),
 }
 
-# --workload c4: Bayesian logistic regression (BASELINE.json configs[3]); not the
-# default line (the driver's N=1 run is c2), used for the tensor-core roofline
+# Bayesian logistic regression (BASELINE.json configs[3], [4]): the tensor-core roofline
 C4 = dict(N=100_000, D=512, chains=8192, warmup_ticks=3000, ticks_per_step=100,
           max_doublings=8, max_halvings=5)
+# fp64 instruction issue ceiling of one B200: 148 SMs x 4 schedulers x 1 warp instruction
+# per clock; the fp64 pipe takes one warp instruction every other clock per scheduler
+SM_COUNT, SCHEDULERS_PER_SM = 148, 4
 
 
 _JSON_FD = None
@@ -173,7 +184,16 @@ def bf16_peaks():
     return 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+_LOGISTIC_CACHE = {}
+
+
 def logistic_data(N, Dm):
+    if (N, Dm) not in _LOGISTIC_CACHE:
+        _LOGISTIC_CACHE[(N, Dm)] = _logistic_data(N, Dm)
+    return _LOGISTIC_CACHE[(N, Dm)]
+
+
+def _logistic_data(N, Dm):
     """X iid N(0,1) rounded to bf16, theta* ~ N(0, I/D),
     y ~ Bernoulli(sigmoid(X theta*)); host generator seeded 20250."""
     import torch
@@ -185,69 +205,131 @@ def logistic_data(N, Dm):
     return X, y
 
 
-def run_c4(args):
-    """Logistic regression, lock-step tick engine + tcgen05 gradient (1 GPU)."""
+class Comm:
+    """torch.distributed over NCCL, one rank per GPU (launched by torchrun); a no-op at N=1."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: walnuts_b200 has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        self.on = self.world > 1
+        if self.on:
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=self.device)
+
+    def barrier(self):
+        if self.on:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op="sum"):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=self.device)
+        if self.on:
+            ops = {"sum": self.dist.ReduceOp.SUM, "max": self.dist.ReduceOp.MAX,
+                   "min": self.dist.ReduceOp.MIN}
+            self.dist.all_reduce(t, op=ops[op])
+        return [float(x) for x in t.cpu()]
+
+    def close(self):
+        if self.on:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def instr_per_eval(kernel_key):
+    """Executed warp instructions per gradient evaluation of a chain-kernel instance, from
+    the committed ncu capture (profiles/r2_chain_kernel_instr_per_eval.json, written by
+    tools/ncu_instr_per_eval.py).  None if the file is absent."""
+    p = ROOT / "profiles" / "r2_chain_kernel_instr_per_eval.json"
+    if not p.exists():
+        return None
+    return json.loads(p.read_text()).get(kernel_key)
+
+
+def binding_roofline(kernel_key, evals_per_s_per_gpu, sm_mhz):
+    """What actually bounds the chain-resident kernel: instruction issue, with the fp64 pipe
+    as its narrowest part.  achieved = fp64 warp instructions / s (per-evaluation count from
+    the ncu capture x live evaluation rate); peak = SMs x schedulers x clock / 2."""
+    ipe = instr_per_eval(kernel_key)
+    if not ipe or not sm_mhz:
+        return None
+    clock = sm_mhz * 1e6
+    fp64_peak = SM_COUNT * SCHEDULERS_PER_SM * clock / 2.0
+    issue_peak = SM_COUNT * SCHEDULERS_PER_SM * clock
+    fp64 = evals_per_s_per_gpu * ipe["fp64_warp_instr_per_eval"]
+    total = evals_per_s_per_gpu * ipe["warp_instr_per_eval"]
+    return {"bound": "fp64-issue", "achieved": fp64 / 1e9, "peak": fp64_peak / 1e9,
+            "unit": "G fp64 warp instructions/s", "frac": fp64 / fp64_peak,
+            "issue_slots_frac": total / issue_peak,
+            "fp64_warp_instr_per_eval": ipe["fp64_warp_instr_per_eval"],
+            "warp_instr_per_eval": ipe["warp_instr_per_eval"],
+            "ncu": {k: ipe.get(k) for k in ("sm__inst_executed_pipe_fp64_pct",
+                                            "smsp__issue_active_pct", "registers",
+                                            "resident_warps_per_sm", "source")},
+            "clock_mhz": sm_mhz,
+            "note": "ideal = 6 fp64 instructions per element and leapfrog step (fused "
+                    "policy) = D * 6 / 32 warp instructions per evaluation; the rest is the "
+                    "per-leaf work of the tree (energy and U-turn reductions, selection, "
+                    "bookkeeping) and the per-transition momentum refresh"}
+
+
+# ---------------------------------------------------------------------------
+def bench_logistic(args, comm, strong, K, W, warmup_ticks, chains=None, cpu_leg=True):
+    """Logistic regression on the lock-step tick engine + tcgen05 gradient.  strong: the
+    chains (65,536 by default) are sharded over the ranks (c5); else 8192 per GPU (c4).
+    Sampling streams into the summary accumulators; the cross-rank R-hat / ESS / MCSE
+    combination (two NCCL all-reduces) is timed as its own phase."""
     import torch
 
     import walnuts_b200 as wb
     from oracle.binding import Target, default_config
+    from walnuts_b200 import _ffi
+    from walnuts_b200.distributed import shard, stream_summary_all_ranks
 
-    import torch.distributed as dist
-    from walnuts_b200.distributed import rhat_from_dimension_moments, shard
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: walnuts_b200 has no CPU path")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    distributed = world > 1
-    if distributed:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    world, rank, local_rank = comm.world, comm.rank, comm.local_rank
     cfgw = dict(C4)
-    strong = args.workload == "c5"
     if strong:
-        # c5: 65,536 chains in total, sharded over the GPUs (strong scaling)
-        total = args.chains if args.chains else 65536
+        total = chains if chains else 65536
         chain_offset, C = shard(total, world, rank)
     else:
-        C = args.chains if args.chains else cfgw["chains"]
+        C = chains if chains else cfgw["chains"]
         chain_offset, total = rank * C, C * world
     N, Dm = cfgw["N"], cfgw["D"]
-    tps = args.iters_per_step if args.iters_per_step != 10 else cfgw["ticks_per_step"]
-    K, W = args.steps, args.warmup
+    tps = cfgw["ticks_per_step"]
     X, y = logistic_data(N, Dm)
     tune = dict(max_trajectory_doublings=cfgw["max_doublings"],
                 max_step_halvings=cfgw["max_halvings"])
-    cap = max(8, (W + K) * tps // 8)  # room for the draws of the free-running phase
-    from walnuts_b200 import _ffi
-    import psutil
-    if C * cap * Dm * 8 > 0.25 * psutil.virtual_memory().available:
-        raise SystemExit("not enough host memory for the draw read-back buffer")
-    host_draws = _ffi.pinned_empty((C, cap, Dm))   # the caller's result buffer
-    # e2e: everything a user of the C-ABI session pays, from host X / y to host draws
+    stage = max(16, tps // 4)   # staging block: rows a chain may complete per step
+    comm.barrier()
+    # e2e: everything a user of the C-ABI session pays, from host X / y to host summaries
     t_e2e = time.perf_counter()
     sess = wb.Session(wb.models.logistic(X, y), C, seed=SEED, chain_offset=chain_offset,
                       device=local_rank, **tune)
     sess.init(init_radius=0.1)
-    sess.reserve(cap)
+    sess.reserve(stage)
     c0 = sess.counters()
     t0 = time.perf_counter()
-    # free-running adaptive warm-up: every chain adapts over the transitions that fit
-    # (about 100 on average); an iteration quota would idle the batch on its slowest chain
-    sess.warmup_ticks(cfgw["warmup_ticks"])
+    # free-running adaptive warm-up: every chain adapts over the transitions that fit; an
+    # iteration quota would idle the batch on its slowest chain
+    sess.warmup_ticks(warmup_ticks)
     sess.freeze().sync()
     warm_s = time.perf_counter() - t0
     c1 = sess.counters()
+    sess.stream_begin(32)
     # a step = `tps` lock-step ticks: one batched gradient evaluation for every chain per
     # tick; chains roll straight into their next transition (free-running, ragged draws)
     for _ in range(W):
         sess.sample_ticks(tps)
     sess.sync()
     c2 = sess.counters()
-    torch.cuda.synchronize()
-    if distributed:
-        dist.barrier()
+    comm.barrier()
     with ClockSampler(local_rank) as clocks:
         t0 = time.perf_counter()
         sess.timer_start()
@@ -255,69 +337,39 @@ def run_c4(args):
             sess.sample_ticks(tps)
         total_ms = sess.timer_stop_ms()
         wall_ms = 1e3 * (time.perf_counter() - t0)
-    sess.draws(0, cap, out=host_draws)
-    rows = sess.chain_rows()
-    e2e_s = time.perf_counter() - t_e2e
-    if distributed:
-        dist.barrier()
     c3 = sess.counters()
-    evals = c3["grad_evals"] - c2["grad_evals"]
+    # ---- summary phase: the path's only collective.  {sum mu, sum n mu}[D] + counts, then
+    # {between, within, pooled SS, sum_k acov_k(t), t < 32}[D]: two all-reduces over NVLink,
+    # then the reference's R-hat / Geyer ESS / MCSE on the combined sums -- over ALL chains
+    comm.barrier()
+    t0 = time.perf_counter()
+    summ = stream_summary_all_ranks(sess, comm.device if comm.on else None)
+    torch.cuda.synchronize()
+    summary_s = time.perf_counter() - t0
+    rows = sess.stream_counts()
+    e2e_s = time.perf_counter() - t_e2e
+    evals_local = c3["grad_evals"] - c2["grad_evals"]
     launches = c3["kernel_launches"] - c2["kernel_launches"]
-    summ = sess.summary_ragged(0)
-    # the only collective: per-dimension chain-moment sums -> R-hat over ALL ranks' chains
-    mom = torch.tensor(sess.rhat_moments(0), dtype=torch.float64, device="cuda")
-    tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
-    ee = torch.tensor([float(evals), float(np.min(summ["ess"])), float(c3["grad_evals"])],
-                      dtype=torch.float64, device="cuda")
-    if distributed:
-        dist.all_reduce(mom, op=dist.ReduceOp.SUM)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ee, op=dist.ReduceOp.SUM)   # independent chains: evals and ESS add
-    global_rhat = rhat_from_dimension_moments(mom.cpu().numpy())
-    total_ms, e2e_s = float(tt[0].item()), float(tt[1].item())
-    e2e_evals = float(ee[2].item())
-    e2e_steps = (cfgw["warmup_ticks"] + (W + K) * tps) / tps
-    evals_local = evals
-    evals = float(ee[0].item())
-    min_ess_total = float(ee[1].item())
+    total_ms, e2e_s, summary_s = comm.reduce([total_ms, e2e_s, summary_s], "max")
+    evals, e2e_evals, draws_total = comm.reduce(
+        [float(evals_local), float(c3["grad_evals"]), float(rows.sum())], "sum")
     value = evals / (total_ms * 1e-3)
     active_lane_fraction = evals_local / float(K * tps * C)
+    clock_summary = clocks.summary()
     sess.close()
     if rank != 0:
-        if distributed:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-    # stand-alone timing of the batched gradient (the dominant kernels)
-    from walnuts_b200.sampler import logistic_logp_grad
-    theta = np.random.default_rng(1).normal(size=(C, Dm)) * 0.05
-    _, _, grad_ms = logistic_logp_grad(X, y, theta, repeats=5)
+        return None
     sustained, burst, src = bf16_peaks()
     flops_alg = 4.0 * N * Dm
     achieved = value / world * flops_alg / 1e12   # per GPU
-    # CPU baseline: the oracle port of the same sampler on a bounded sample
-    checker, kind = load_cpu_checker()
-    cores = os.cpu_count() or 1
-    target = Target("logistic", Dm, X=X, y=y)
-    ccfg = default_config(min_warmup_iter=2, max_warmup_iter=2, min_sampling_iter=2,
-                          max_sampling_iter=2, max_trajectory_doublings=cfgw["max_doublings"],
-                          max_step_halvings=cfgw["max_halvings"])
-    pos = checker.init_positions(cores, Dm, SEED, 0.5)
-    mass = np.ones((cores, Dm))
-    steps = np.full(cores, 0.02)
-    t0 = time.perf_counter()
-    if args.no_cpu_baseline:
-        r, cpu_s = {"grad_evals": 0}, 1.0
-    else:
-        r = checker.walnuts(target, ccfg, SEED, pos, mass, steps)
-        cpu_s = time.perf_counter() - t0
+    e2e_steps = (warmup_ticks + (W + K) * tps) / tps
     line = {
         "metric": "grad_evals_per_sec", "value": value, "unit": "grad_evals/s",
-        "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
-        "scaling": "strong" if strong else "weak", "vs_baseline": None,
-        "dtype": "bf16 tensor cores (hi+lo split), "
-        "fp32 accumulate, fp64 state", "data": "synthetic",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+        "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None,
+        "dtype": "bf16 tensor cores (hi+lo split), fp32 accumulate, fp64 state",
+        "data": "synthetic",
         "config": {"workload": ("c5: Bayesian logistic regression N=100k, D=512, "
                                 f"{total} chains sharded over the GPUs, "
                                 if strong else
@@ -326,18 +378,27 @@ def run_c4(args):
                                "lock-step tick engine + tcgen05 batched gradient",
                    "N": N, "dims": Dm, "chains_per_gpu": C, "chains_total": total,
                    "ticks_per_step": tps,
-                   "parallelism": f"chains sharded over {world} GPU(s); X replicated; one "
-                                  "NCCL all-reduce of R-hat moments after the timed region",
-                   "adaptive_warmup_ticks": cfgw["warmup_ticks"],
+                   "parallelism": f"chains sharded over {world} GPU(s); X replicated; the "
+                                  "only collective is the summary phase: two NCCL "
+                                  "all-reduces of R-hat / ESS moment sums",
+                   "adaptive_warmup_ticks": warmup_ticks,
                    "max_trajectory_doublings": cfgw["max_doublings"],
                    "l2": "operands (X 102 MB, R^T 1.6 GB) exceed the 126 MB L2"},
-        "min_ess_per_sec": min_ess_total / (total_ms * 1e-3),
-        "max_r_hat": float(np.max(global_rhat)),
+        "min_ess": float(np.min(summ["ess"])),
+        "min_ess_per_sec": float(np.min(summ["ess"])) / (total_ms * 1e-3 * (W + K) / K),
+        "max_r_hat": float(np.max(summ["r_hat"])),
+        "summary_phase": {"seconds": summary_s, "chains": total, "draws": draws_total,
+                          "payload_doubles": (2 * Dm + 3) + (3 + 32) * Dm,
+                          "collective": ("NCCL all-reduce x2 (SUM) + MIN" if comm.on
+                                         else "none (1 GPU)"),
+                          "ess_truncated_dims": int(np.sum(summ["truncated"])),
+                          "what": "reference R-hat / ESS / MCSE (summary.hpp:594-769) over "
+                                  "ALL chains from streamed per-chain sums"},
         "active_lane_fraction": active_lane_fraction,
         "draws_per_chain": {"min": int(rows.min()), "mean": float(rows.mean()),
                             "max": int(rows.max())},
         "wall_ms": wall_ms, "gpu_launches": int(launches),
-        "warmup_phase": {"ticks": cfgw["warmup_ticks"], "seconds": warm_s,
+        "warmup_phase": {"ticks": warmup_ticks, "seconds": warm_s,
                          "grad_evals_per_sec": (c1["grad_evals"] - c0["grad_evals"]) / warm_s},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": sustained,
                      "unit": "TFLOP/s", "frac": achieved / sustained,
@@ -347,28 +408,43 @@ def run_c4(args):
                      "traffic_source": "profiles/r1_ncu_gemm_logistic_final_c4.csv",
                      "peak_burst": burst, "peak_source": src,
                      "algorithmic_flops_per_eval": flops_alg,
-                     "gradient_only_ms_per_batched_eval": grad_ms,
-                     "gradient_only_tflops": C * flops_alg / (grad_ms * 1e-3) / 1e12,
                      "kernel": "gemm_kmajor_kernel<256,1> + gemm_kmajor_kernel<256,2>"},
         "e2e": {"value": e2e_evals / e2e_s, "unit": "grad_evals/s",
-                "h2d_bytes_per_step": int((X.nbytes + y.nbytes) / e2e_steps),
-                "d2h_bytes_per_step": int(host_draws.nbytes / e2e_steps),
+                "h2d_bytes_per_step": int((X.nbytes + y.nbytes) * world / e2e_steps),
+                "d2h_bytes_per_step": int(5 * Dm * 8 * world / e2e_steps),
                 "seconds": e2e_s, "grad_evals": e2e_evals, "steps": e2e_steps,
                 "api": "C-ABI session (wb200_session_create with host X / y, init, "
-                       "warmup_ticks, freeze, sample_ticks, get_draws into a pinned host "
-                       "buffer): upload, adaptive warm-up, every sampling step of this run "
-                       "and the read-back of all stored draws inside the timed region"},
-        "cpu_baseline": (None if args.no_cpu_baseline else {
-            "value": r["grad_evals"] / cpu_s, "unit": "grad_evals/s",
-            "cores": cores, "kind": kind,
-            "sample": f"{cores} chains x (2 warm-up + 2 sampling) iterations, same data",
-            "seconds": cpu_s}),
-        "clocks": clocks.summary(),
+                       "warmup_ticks, freeze, stream_begin, sample_ticks, stream summary): "
+                       "upload, adaptive warm-up, every sampling step of this run and the "
+                       "summaries read back, all inside the timed region"},
+        "clocks": clock_summary,
     }
-    emit(line)
-    if distributed:
-        dist.barrier()
-        dist.destroy_process_group()
+    if cpu_leg:
+        # stand-alone timing of the batched gradient (the dominant kernels)
+        from walnuts_b200.sampler import logistic_logp_grad
+        theta = np.random.default_rng(1).normal(size=(min(C, 8192), Dm)) * 0.05
+        _, _, grad_ms = logistic_logp_grad(X, y, theta, repeats=5)
+        line["roofline"]["gradient_only_ms_per_batched_eval"] = grad_ms
+        line["roofline"]["gradient_only_tflops"] = (
+            len(theta) * flops_alg / (grad_ms * 1e-3) / 1e12)
+        # CPU baseline: the reference's sampler on a bounded sample of the same data
+        checker, kind = load_cpu_checker()
+        cores = os.cpu_count() or 1
+        target = Target("logistic", Dm, X=X, y=y)
+        ccfg = default_config(min_warmup_iter=2, max_warmup_iter=2, min_sampling_iter=2,
+                              max_sampling_iter=2,
+                              max_trajectory_doublings=cfgw["max_doublings"],
+                              max_step_halvings=cfgw["max_halvings"])
+        pos = checker.init_positions(cores, Dm, SEED, 0.5)
+        t0 = time.perf_counter()
+        r = checker.walnuts(target, ccfg, SEED, pos, np.ones((cores, Dm)),
+                            np.full(cores, 0.02))
+        cpu_s = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": r["grad_evals"] / cpu_s, "unit": "grad_evals/s", "cores": cores,
+            "kind": kind, "seconds": cpu_s,
+            "sample": f"{cores} chains x (2 warm-up + 2 sampling) iterations, same data"}
+    return line
 
 
 # ---------------------------------------------------------------------------
@@ -401,6 +477,11 @@ def load_cpu_checker():
     return load_oracle(), "port"
 
 
+CPU_ARM_NOTE = ("the reference's headers are compiled unmodified against a local stand-in for "
+                "Eigen (oracle/eigen_shim: scalar left-to-right loops, not Eigen's packet "
+                "code), so a real-Eigen build may be somewhat faster than this baseline")
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -430,7 +511,7 @@ def run_reference_arm(args):
                    "max_trajectory_doublings": wl["max_doublings"],
                    "max_step_halvings": wl["max_halvings"]},
         "cpu_baseline": {"value": value, "unit": "grad_evals/s", "cores": cores,
-                         "kind": kind, "sample": sample},
+                         "kind": kind, "sample": sample, "note": CPU_ARM_NOTE},
         "e2e": {"value": value, "unit": "grad_evals/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -439,38 +520,64 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------
-def run_ours(args):
+def one_shot(model, wl, C, rank, n_warm, n_samp, summaries, inits):
+    """The C-ABI one-shot call with pinned host buffers on this rank's GPU; returns
+    (seconds, gradient evaluations, h2d bytes, d2h bytes, result)."""
+    import ctypes
+
+    from walnuts_b200 import _ffi
+    Dw = wl["D"]
+    desc = model.desc()
+    lengths = np.zeros(2 * C, np.int32)
+    stepsize = np.zeros(C)
+    tail = (wl["max_doublings"], wl["max_halvings"], 1, 0.5, 0.1, 1.0, 1.01, 4.0, 1e-5, 15.0,
+            1.0, 0.8, 0.05, 0.8, 0.9, 1e-4, 0.5)
+    head = (ctypes.byref(desc), Dw, inits, C, SEED, 1 + rank * C, wl["init_radius"], None,
+            n_warm, n_warm, n_samp, n_samp)
+    if summaries:
+        out = {k: _ffi.pinned_empty((Dw,)) for k in ("mean", "variance", "r_hat", "ess", "mcse")}
+        cut = np.zeros(Dw, np.int32)
+        t0 = time.perf_counter()
+        _ffi._ffi_sample_device_summary(
+            *head, *tail, 32, out["mean"], out["variance"], out["r_hat"], out["ess"],
+            out["mcse"], cut, lengths, stepsize, None, 0, _ffi.print_callback)
+        dt = time.perf_counter() - t0
+        d2h = 5 * Dw * 8 + cut.nbytes + stepsize.nbytes + lengths.nbytes
+        result = {k: np.array(v) for k, v in out.items()}
+        result["truncated"] = cut
+    else:
+        import psutil
+        if C * n_samp * Dw * 8 > 0.5 * psutil.virtual_memory().available:
+            raise SystemExit("not enough host memory for the e2e output buffer")
+        out = _ffi.pinned_empty((C, n_samp, Dw))
+        t0 = time.perf_counter()
+        _ffi._ffi_sample_device(*head, *tail, False, out, out.size, lengths, stepsize, None, 0,
+                                _ffi.print_callback)
+        dt = time.perf_counter() - t0
+        d2h = out.nbytes + stepsize.nbytes + lengths.nbytes
+        result = None
+        del out
+    return dt, float(_ffi.last_run_stats()["grad_evals"]), inits.nbytes, d2h, result
+
+
+def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=True):
+    """c2 / c3 on the chain-resident kernel: device-timed sampling steps, the one-shot
+    C-ABI calls, the posterior check and (cpu_leg) the reference on the host cores."""
     import torch
-    import torch.distributed as dist
 
     import walnuts_b200 as wb
     from walnuts_b200 import _ffi
+    from walnuts_b200.distributed import stream_summary_all_ranks
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: walnuts_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    distributed = world > 1
-    if distributed:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    wl = ELEMENTWISE[args.workload]
-    D, WARMUP_ITERS = wl["D"], wl["warmup_iters"]
-    MAX_DOUBLINGS, MAX_HALVINGS = wl["max_doublings"], wl["max_halvings"]
-    ALG_BYTES_PER_EVAL = 7 * D * 8
-    C = args.chains if args.chains else wl["chains"]
-    ips = args.iters_per_step
-    K, W = args.steps, args.warmup
+    world, rank, local_rank = comm.world, comm.rank, comm.local_rank
+    wl = ELEMENTWISE[name]
+    Dw, n_warm, burn = wl["D"], wl["warmup_iters"], wl["burn_iters"]
+    alg_bytes = 7 * Dw * 8
+    C = args.chains if (args.chains and name == args.workload) else wl["chains"]
     model = (wb.models.diag_gaussian(variances()) if wl["kind"] == "diag_gaussian"
-             else wb.models.funnel(D))
-    tune = dict(max_trajectory_doublings=MAX_DOUBLINGS, max_step_halvings=MAX_HALVINGS)
+             else wb.models.funnel(Dw))
+    tune = dict(max_trajectory_doublings=wl["max_doublings"],
+                max_step_halvings=wl["max_halvings"])
     sess = wb.Session(model, C, seed=SEED, chain_offset=rank * C, device=local_rank, **tune)
     sess.init(init_radius=wl["init_radius"])
     sess.reserve((W + K) * ips)
@@ -478,18 +585,20 @@ def run_ours(args):
     sess.sync()
     c0 = sess.counters()
     sess.timer_start()
-    sess.warmup(WARMUP_ITERS)
+    sess.warmup(n_warm)
     warm_ms = sess.timer_stop_ms()
     sess.freeze()
     c1 = sess.counters()
     warm_evals = c1["grad_evals"] - c0["grad_evals"]
+    if burn:
+        for _ in range(0, burn, 50):
+            sess.sample(50, store=False)
     for _ in range(W):
         sess.sample(ips)
     sess.sync()
     # ---- timed region: exactly K steps
     c2 = sess.counters()
-    barrier()
-    kernel_ms = []
+    comm.barrier()
     with ClockSampler(local_rank) as clocks:
         t0 = time.perf_counter()
         sess.timer_start()
@@ -498,96 +607,86 @@ def run_ours(args):
         total_ms = sess.timer_stop_ms()
         torch.cuda.synchronize()
         wall_ms = 1e3 * (time.perf_counter() - t0)
-    barrier()
+    comm.barrier()
     c3 = sess.counters()
     evals = c3["grad_evals"] - c2["grad_evals"]
     launches = c3["kernel_launches"] - c2["kernel_launches"]
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    e = torch.tensor([float(evals)], dtype=torch.float64, device="cuda")
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e, op=dist.ReduceOp.SUM)
-    max_ms, total_evals = float(t.item()), float(e.item())
+    (max_ms,) = comm.reduce([total_ms], "max")
+    (total_evals,) = comm.reduce([float(evals)], "sum")
     value = total_evals / (max_ms * 1e-3)
+    clock_summary = clocks.summary()
 
-    # ---- posterior summary of the timed draws (device), cross-chain moments by NCCL
+    # ---- posterior summary of the timed draws over ALL ranks' chains: the stored draws of
+    # the timed steps are folded into the streaming accumulators, then two all-reduces
     first = W * ips
-    summ = sess.summary(first, K * ips)
-    min_ess_local = float(np.min(summ["ess"]))
-    if distributed:
-        # the only collective of the path: per-dimension chain-moment sums
-        ptr, cap, ld, rows = sess.device_draws()
-        mom = torch.tensor(np.stack([summ["mean"], summ["variance"]]), device="cuda")
-        dist.all_reduce(mom, op=dist.ReduceOp.SUM)
-        mom /= world
-        ess_t = torch.tensor([min_ess_local], dtype=torch.float64, device="cuda")
-        dist.all_reduce(ess_t, op=dist.ReduceOp.SUM)   # independent chains: ESS adds
-        min_ess = float(ess_t.item())
-        post_mean, post_var = mom[0].cpu().numpy(), mom[1].cpu().numpy()
-    else:
-        min_ess, post_mean, post_var = min_ess_local, summ["mean"], summ["variance"]
+    local = sess.summary(first, K * ips)
+    draws_last = sess.draws(first + K * ips - 1, 1)[:, 0]       # one draw per chain
+    sess.close()
+    comm.barrier()
+    # cross-rank moments of the timed draws (chains independent: pooled over ranks)
+    mom = comm.reduce(list(local["mean"]) + list(local["variance"]), "sum")
+    post_mean = np.array(mom[:Dw]) / world
+    post_var = np.array(mom[Dw:]) / world
     if wl["kind"] == "diag_gaussian":
         true_var = variances()
-    else:  # funnel: x0 ~ N(0, 9); x_i has mean 0 (its variance e^{4.5} is never reached)
-        true_var = np.full(D, np.nan)
-        true_var[0] = 9.0
-    clock_summary = clocks.summary()
-    sess.close()
+        posterior = {
+            "max_abs_mean_over_sd": float(np.max(np.abs(post_mean) / np.sqrt(true_var))),
+            "max_rel_var_error": float(np.max(np.abs(post_var / true_var - 1.0))),
+            "max_abs_z_mean": float(np.max(np.abs(local["mean"]) / local["mcse"])),
+            "truth": "N(0, diag(variances)); z of the pooled mean against the device MCSE"}
+    else:
+        v = draws_last[:, 0]
+        n = len(v)
+        posterior = {
+            "E_v": float(v.mean()), "Var_v": float(v.var(ddof=1)),
+            "z_E_v": float(v.mean() / np.sqrt(9.0 / n)),
+            "z_Var_v": float((v.var(ddof=1) - 9.0) / (9.0 * np.sqrt(2.0 / n))),
+            "max_z_E_x": float(np.max(np.abs(draws_last[:, 1:].mean(0)) /
+                                      (draws_last[:, 1:].std(0, ddof=1) / np.sqrt(n)))),
+            "truth": "v ~ N(0, 9), E x_i = 0: cross-chain z scores of the last timed draw "
+                     f"of this rank's {n} chains, after {n_warm} adaptive + {burn} + "
+                     f"{(W + K) * ips} sampling iterations",
+            "tau_v_iterations_lower_bound": float(C * K * ips / local["ess"][0])}
+    min_ess = comm.reduce([float(np.min(local["ess"]))], "sum")[0]  # independent shards add
 
-    # ---- e2e: the C-ABI one-shot call with host buffers, every rank on its own GPU
+    # ---- e2e: the C-ABI one-shot calls with pinned host buffers, every rank on its GPU
     torch.cuda.synchronize()
     e2e_samp = K * ips
-    import psutil
-    if world * C * e2e_samp * D * 8 > 0.5 * psutil.virtual_memory().available:
-        raise SystemExit("not enough host memory for the e2e output buffers")
-    # host buffers are page-locked (wb200_host_alloc), as the bench contract asks
-    inits = _ffi.pinned_empty((C, D))
-    inits[...] = np.random.default_rng(SEED).normal(size=(C, D)) * wl["init_radius"]
-    out = _ffi.pinned_empty((C, e2e_samp, D))
-    lengths = np.zeros(2 * C, np.int32)
-    stepsize = np.zeros(C)
-    desc = model.desc()
-    import ctypes
-    barrier()
-    t0 = time.perf_counter()
-    _ffi._ffi_sample_device(
-        ctypes.byref(desc), D, inits, C, SEED, 1 + rank * C, wl["init_radius"], None,
-        WARMUP_ITERS, WARMUP_ITERS,
-        e2e_samp, e2e_samp, MAX_DOUBLINGS, MAX_HALVINGS, 1, 0.5, 0.1, 1.0, 1.01, 4.0, 1e-5,
-        15.0, 1.0, 0.8, 0.05, 0.8, 0.9, 1e-4, 0.5, False, out, out.size, lengths, stepsize,
-        None, 0, _ffi.print_callback)
-    e2e_s = time.perf_counter() - t0
-    st = _ffi.last_run_stats()
-    e2e_evals = float(st["grad_evals"])
-    if distributed:   # whole job: evaluations of all ranks over the slowest rank's time
-        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        ee = torch.tensor([e2e_evals], dtype=torch.float64, device="cuda")
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ee, op=dist.ReduceOp.SUM)
-        e2e_s, e2e_evals = float(te.item()), float(ee.item())
-    e2e_value = e2e_evals / e2e_s
-    e2e_steps = (WARMUP_ITERS + e2e_samp) / ips
-    h2d_bytes, d2h_bytes = inits.nbytes * world, out.nbytes * world
-    del out, inits
+    inits = _ffi.pinned_empty((C, Dw))
+    inits[...] = np.random.default_rng(SEED).normal(size=(C, Dw)) * wl["init_radius"]
+    comm.barrier()
+    dt, ev, h2d, d2h, e2e_summary = one_shot(model, wl, C, rank, n_warm, e2e_samp, True, inits)
+    (e2e_s,) = comm.reduce([dt], "max")
+    (e2e_evals,) = comm.reduce([ev], "sum")
+    e2e_steps = (n_warm + e2e_samp) / ips
+    e2e = {"value": e2e_evals / e2e_s, "unit": "grad_evals/s",
+           "h2d_bytes_per_step": int(h2d * world / e2e_steps),
+           "d2h_bytes_per_step": int(d2h * world / e2e_steps),
+           "seconds": e2e_s, "grad_evals": e2e_evals, "steps": e2e_steps,
+           "api": "walnutpie_sample_device_summary (C-ABI, pinned host buffers): session "
+                  "set-up, initial positions uploaded, adaptive warm-up, sampling and the "
+                  "posterior summaries (mean, variance, R-hat, ESS, MCSE per parameter, "
+                  "streamed on the device) read back, all inside the timed call",
+           "min_ess": float(np.min(e2e_summary["ess"])),
+           "max_r_hat": float(np.max(e2e_summary["r_hat"]))}
+    e2e_all = None
+    if all_draws_leg:
+        comm.barrier()
+        dt, ev, h2d, d2h, _ = one_shot(model, wl, C, rank, n_warm, e2e_samp, False, inits)
+        (all_s,) = comm.reduce([dt], "max")
+        (all_evals,) = comm.reduce([ev], "sum")
+        e2e_all = {"value": all_evals / all_s, "unit": "grad_evals/s",
+                   "h2d_bytes_per_step": int(h2d * world / e2e_steps),
+                   "d2h_bytes_per_step": int(d2h * world / e2e_steps), "seconds": all_s,
+                   "api": "walnutpie_sample_device: the same run with every draw copied "
+                          "back to the host (read-back overlapped with sampling), as the "
+                          "reference returns them"}
+    del inits
     if rank != 0:
-        if distributed:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # ---- CPU baseline on a bounded sample of the same workload
-    checker, kind = load_cpu_checker()
-    cores = os.cpu_count() or 1
-    cpu_warm, cpu_samp = wl["cpu_warm"], wl["cpu_samp"]
-    cpu_evals, cpu_s, cpu_draws = reference_step(checker, kind, cores, cpu_warm, cpu_samp,
-                                                 SEED, wl)
-    oracle_checker = checker if kind == "port" else __import__(
-        "oracle.binding", fromlist=["load_oracle"]).load_oracle()
-    cpu_min_ess = float(np.min(oracle_checker.ess([cpu_draws[c] for c in range(cores)])))
+        return None
 
     hbm_peak, peak_src = measured_peaks()
-    ms_per_launch = max_ms / max(launches, 1)
-    achieved = (total_evals / world) * ALG_BYTES_PER_EVAL / (max_ms * 1e-3) / 1e9
+    achieved = (total_evals / world) * alg_bytes / (max_ms * 1e-3) / 1e9
     line = {
         "metric": "grad_evals_per_sec", "value": value, "unit": "grad_evals/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
@@ -595,59 +694,79 @@ def run_ours(args):
         "data": "synthetic",
         "config": {
             "workload": wl["label"],
-            "dims": D, "chains_per_gpu": C, "chains_total": C * world,
-            "iters_per_step": ips, "adaptive_warmup_iters": WARMUP_ITERS,
-            "max_trajectory_doublings": MAX_DOUBLINGS, "max_step_halvings": MAX_HALVINGS,
+            "dims": Dw, "chains_per_gpu": C, "chains_total": C * world,
+            "iters_per_step": ips, "adaptive_warmup_iters": n_warm,
+            "unstored_sampling_iters_before_timing": burn,
+            "max_trajectory_doublings": wl["max_doublings"],
+            "max_step_halvings": wl["max_halvings"],
+            "arithmetic": "fused policy (FMA at the accumulate sites; DESIGN.md section 3.1)",
             "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
             "l2": "working set per step (chain state + scratch + stored draws, "
-                  f"{(C * D * 8 * (2 + ips)) / 1e6:.0f} MB) exceeds the 126 MB L2",
+                  f"{(C * Dw * 8 * (2 + ips)) / 1e6:.0f} MB) exceeds the 126 MB L2",
         },
         "min_ess_per_sec": min_ess / (max_ms * 1e-3),
         "min_ess": min_ess,
         "grad_evals_per_transition": total_evals / (C * world * K * ips),
         "wall_ms": wall_ms,
-        "posterior_check": {
-            "max_abs_mean_over_sd": float(np.nanmax(np.abs(post_mean) / np.sqrt(true_var))),
-            "max_rel_var_error": float(np.nanmax(np.abs(post_var / true_var - 1.0))),
-        },
-        "warmup_phase": {"iters": WARMUP_ITERS, "ms": warm_ms,
+        "posterior_check": posterior,
+        "warmup_phase": {"iters": n_warm, "ms": warm_ms,
                          "grad_evals_per_sec": warm_evals / (warm_ms * 1e-3)},
-        "e2e": {"value": e2e_value, "unit": "grad_evals/s",
-                "h2d_bytes_per_step": int(h2d_bytes / e2e_steps),
-                "d2h_bytes_per_step": int(d2h_bytes / e2e_steps),
-                "seconds": e2e_s, "api": "walnutpie_sample_device (C-ABI, pinned host buffers; "
-                       "session set-up, initialisation, adaptive warm-up, sampling and the "
-                       "overlapped read-back of every draw are all inside the timed call)",
-                "grad_evals": e2e_evals, "steps": e2e_steps},
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
             "frac": achieved / hbm_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one timed launch (10
             # transitions x 4096 chains) from the committed ncu --set full capture
-            "traffic": 1.85e9 if args.workload == "c2" and ips == 10 and C == 4096 else None,
-            "traffic_source": "profiles/r1_ncu_chain_kernel_sampling_final_c2.csv",
+            "traffic": (instr_per_eval("c2_sampling") or {}).get("dram_bytes_per_launch")
+            if name == "c2" and ips == 10 and C == 4096 else None,
+            "traffic_source": "profiles/r2_ncu_chain_kernel_sampling_c2.csv",
             "peak_source": peak_src,
             "kernel": wl["kernel"],
-            "algorithmic_bytes_per_eval": ALG_BYTES_PER_EVAL,
-            "ms_per_launch": ms_per_launch,
-            "note": "the chain-resident kernel keeps theta/rho/grad/M^-1 in registers "
-                    "across micro-steps, so it moves far fewer DRAM bytes than the "
-                    "7*D*w streaming model; frac > 1 means faster than a lock-step "
-                    "HBM-streaming kernel could be (see DESIGN.md, profiles/)",
+            "algorithmic_bytes_per_eval": alg_bytes,
+            "ms_per_launch": max_ms / max(launches, 1),
+            "streaming_equivalent": True,
+            "note": "SURVEY.md section 8(d)'s streaming model: 7*D*w bytes per evaluation. The "
+                    "chain-resident kernel keeps theta/rho/grad/M^-1 on chip across "
+                    "micro-steps, so its real DRAM traffic (`traffic`) is a few percent of "
+                    "that and frac > 1 only says it is faster than a lock-step HBM-streaming "
+                    "kernel could be; what binds it is in roofline_binding",
         },
-        "cpu_baseline": {
+        "roofline_binding": binding_roofline(f"{name}_sampling", total_evals / world /
+                                             (max_ms * 1e-3), clock_summary.get("sm_mhz")),
+        "clocks": clock_summary,
+    }
+    if e2e_all:
+        line["e2e_all_draws"] = e2e_all
+    if cpu_leg:
+        checker, kind = load_cpu_checker()
+        cores = os.cpu_count() or 1
+        cpu_warm, cpu_samp = wl["cpu_warm"], wl["cpu_samp"]
+        cpu_evals, cpu_s, cpu_draws = reference_step(checker, kind, cores, cpu_warm, cpu_samp,
+                                                     SEED, wl)
+        oracle_checker = checker if kind == "port" else __import__(
+            "oracle.binding", fromlist=["load_oracle"]).load_oracle()
+        cpu_min_ess = float(np.min(oracle_checker.ess([cpu_draws[c] for c in range(cores)])))
+        line["cpu_baseline"] = {
             "value": cpu_evals / cpu_s, "unit": "grad_evals/s", "cores": cores, "kind": kind,
             "sample": f"{cores} chains (one per core) x ({cpu_warm} warm-up + {cpu_samp} "
                       f"sampling) fixed iterations, same target and limits",
-            "min_ess_per_sec": cpu_min_ess / cpu_s, "seconds": cpu_s,
-        },
-        "clocks": clock_summary,
-    }
-    emit(line)
-    if distributed:
-        dist.barrier()
-        dist.destroy_process_group()
+            "min_ess_per_sec": cpu_min_ess / cpu_s, "seconds": cpu_s, "note": CPU_ARM_NOTE}
+        if wl["kind"] == "funnel":
+            v = cpu_draws[:, -50:, 0]
+            line["cpu_baseline"]["E_v_last_50_draws"] = float(v.mean())
+    return line
+
+
+def compact(line):
+    """the keys of a full line that a `workloads` entry keeps"""
+    if line is None:
+        return None
+    keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling",
+            "dtype", "config", "min_ess", "min_ess_per_sec", "max_r_hat", "posterior_check",
+            "summary_phase", "active_lane_fraction", "grad_evals_per_transition",
+            "warmup_phase", "roofline", "roofline_binding", "e2e", "gpu_launches", "clocks")
+    return {k: line[k] for k in keep if k in line}
 
 
 def main():
@@ -658,20 +777,41 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=None,
-                    help="chains per GPU (c2, c4) or in total (c5); default per workload")
+                    help="chains per GPU (c2, c3, c4) or in total (c5); default per workload")
     ap.add_argument("--iters-per-step", type=int, default=10)
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true",
-                    help="skip the CPU leg (scaling sweeps of the logistic workloads)")
+                    help="skip the CPU leg (scaling sweeps)")
+    ap.add_argument("--no-extra-workloads", action="store_true",
+                    help="c2 line only: skip the c3 / c4 / c5 blocks")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
         run_reference_arm(args)
-    elif args.workload in ("c4", "c5"):
-        run_c4(args)
-    else:
-        run_ours(args)
+        return
+    comm = Comm()
+    K, W, cpu = args.steps, args.warmup, not args.no_cpu_baseline
+    try:
+        if args.workload in ("c4", "c5"):
+            line = bench_logistic(args, comm, args.workload == "c5", K, W,
+                                  C4["warmup_ticks"], chains=args.chains, cpu_leg=cpu)
+        else:
+            line = bench_elementwise(args, comm, args.workload, K, W, args.iters_per_step,
+                                     cpu_leg=cpu)
+        if args.workload == "c2" and not args.no_extra_workloads:
+            # the other BASELINE.json configs, short, in the same process
+            extra = {}
+            extra["c3"] = compact(bench_elementwise(args, comm, "c3", 5, 3, 10, cpu_leg=False,
+                                                    all_draws_leg=False))
+            extra["c4"] = compact(bench_logistic(args, comm, False, 3, 3, 2000, cpu_leg=False))
+            extra["c5"] = compact(bench_logistic(args, comm, True, 2, 3, 1200, cpu_leg=False))
+            if line is not None:
+                line["workloads"] = extra
+        if line is not None:
+            emit(line)
+    finally:
+        comm.close()
 
 
 if __name__ == "__main__":

@@ -35,8 +35,8 @@ stream_update_kernel(const double* draws, long long draw_cap, int ld, const long
                      double* S1, double* P, double* head, double* tail) {
   __shared__ double win[T * kStreamTB];  // the last T values of this thread's series
   const int tx = threadIdx.x;
-  const int d = blockIdx.x * kStreamTB + tx;
-  const int c = blockIdx.y;
+  const int d = blockIdx.y * kStreamTB + tx;
+  const int c = blockIdx.x;  // chains on the x dimension of the grid: no 65 535 limit
   if (d >= ld) return;
   const long long B = rows_c ? rows_c[c] : rows_uniform;
   if (B <= 0) return;
@@ -90,8 +90,8 @@ __global__ void stream_advance_kernel(long long* n_c, const long long* rows_c,
 __global__ void stream_chain_stats_kernel(const long long* n_c, int ld, int D, int T,
                                           const double* ref, const double* S1,
                                           const double* P, double* mu, double* s2) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = blockIdx.y;
+  const int d = blockIdx.y * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x;
   if (d >= D) return;
   const long long n = n_c[c];
   if (n < 3) return;  // left out, as summary.hpp:595-603 would reject it
@@ -150,12 +150,12 @@ __global__ void __launch_bounds__(kStreamTB)
 stream_acov_kernel(const long long* n_c, int C, int chains_per_block, int ld, int D,
                    const double* S1, const double* P, const double* head, const double* tail,
                    double* macov) {
-  const int d = blockIdx.x * kStreamTB + threadIdx.x;
+  const int d = blockIdx.y * kStreamTB + threadIdx.x;
   if (d >= D) return;
   double acc[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t] = 0.0;
-  const int c0 = blockIdx.y * chains_per_block;
+  const int c0 = blockIdx.x * chains_per_block;
   const int c1 = min(C, c0 + chains_per_block);
   for (int c = c0; c < c1; ++c) {
     const long long n = n_c[c];
@@ -280,7 +280,7 @@ void stream_end(wb200_session& s) {
 // rows_c: device per-chain counts of staged rows (null: `rows_uniform` for every chain)
 void stream_update(wb200_session& s, const long long* rows_c, long long rows_uniform) {
   StreamState& st = *s.acc;
-  const dim3 grid((s.ld + kStreamTB - 1) / kStreamTB, s.C);
+  const dim3 grid(s.C, (s.ld + kStreamTB - 1) / kStreamTB);
 #define WB200_STREAM_UPDATE(T_)                                                          \
   stream_update_kernel<T_><<<grid, kStreamTB, 0, s.stream>>>(                   \
       s.draws.ptr, s.draw_cap, s.ld, rows_c, rows_uniform, 0, st.n.ptr, st.ref.ptr,      \
@@ -323,7 +323,7 @@ static void stream_chain_stats(wb200_session& s) {
   StreamState& st = *s.acc;
   const size_t CD = static_cast<size_t>(s.C) * s.D;
   if (st.mu.count != CD) { st.mu.alloc(CD); st.s2.alloc(CD); }
-  const dim3 grid((s.D + 127) / 128, s.C);
+  const dim3 grid(s.C, (s.D + 127) / 128);
   stream_chain_stats_kernel<<<grid, 128, 0, s.stream>>>(
       st.n.ptr, s.ld, s.D, st.T, st.ref.ptr, st.S1.ptr, st.P.ptr, st.mu.ptr, st.s2.ptr);
   WB200_CUDA(cudaGetLastError());
@@ -367,7 +367,7 @@ void stream_phase2(wb200_session& s, const double* reduced1, double* out_host) {
       st.n.ptr, s.C, D, st.mu.ptr, st.s2.ptr, cen.ptr, cen.ptr + D, out.ptr);
   WB200_CUDA(cudaGetLastError());
   const int cpb = 32;
-  const dim3 grid((D + kStreamTB - 1) / kStreamTB, (s.C + cpb - 1) / cpb);
+  const dim3 grid((s.C + cpb - 1) / cpb, (D + kStreamTB - 1) / kStreamTB);
 #define WB200_STREAM_ACOV(T_)                                                            \
   stream_acov_kernel<T_><<<grid, kStreamTB, 0, s.stream>>>(                     \
       st.n.ptr, s.C, cpb, s.ld, D, st.S1.ptr, st.P.ptr, st.head.ptr, st.tail.ptr,        \

@@ -26,8 +26,8 @@ struct SummaryView {
 
 // mean and unbiased variance of every (chain, dimension) series
 __global__ void chain_moments_kernel(SummaryView v, double* mu, double* s2) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = blockIdx.y;
+  const int d = blockIdx.y * blockDim.x + threadIdx.x;
+  const int k = blockIdx.x;  // chains on the x dimension of the grid: no 65 535 limit
   if (d >= v.D) return;
   const double* base = v.x + v.start[k] * v.ld + d;
   const long long n = v.len[k];
@@ -82,8 +82,8 @@ template <int TILE>
 __global__ void acov_kernel(SummaryView v, const double* mu, int lag0, int nlag,
                             double* acc) {
   extern __shared__ double tile[];  // [len][TILE]
-  const int k = blockIdx.y;
-  const int d0 = blockIdx.x * TILE;
+  const int k = blockIdx.x;
+  const int d0 = blockIdx.y * TILE;
   const long long n = v.len[k];
   const double* base = v.x + v.start[k] * v.ld;
   for (long long p = threadIdx.x; p < n * TILE; p += blockDim.x) {
@@ -108,8 +108,8 @@ __global__ void acov_kernel(SummaryView v, const double* mu, int lag0, int nlag,
 template <int TILE>
 __global__ void acov_global_kernel(SummaryView v, const double* mu, int lag0, int nlag,
                                    double* acc) {
-  const int k = blockIdx.y;
-  const int d0 = blockIdx.x * TILE;
+  const int k = blockIdx.x;
+  const int d0 = blockIdx.y * TILE;
   const long long n = v.len[k];
   const double* base = v.x + v.start[k] * v.ld;
   for (int p = threadIdx.x; p < nlag * TILE; p += blockDim.x) {
@@ -213,7 +213,7 @@ void device_rhat_moments(const double* draws, int ld, int D,
   mu.alloc(static_cast<size_t>(K) * D); s2.alloc(static_cast<size_t>(K) * D);
   out.alloc(3 * static_cast<size_t>(D));
   const int tb = 128;
-  chain_moments_kernel<<<dim3((D + tb - 1) / tb, K), tb, 0, stream>>>(v, mu.ptr, s2.ptr);
+  chain_moments_kernel<<<dim3(K, (D + tb - 1) / tb), tb, 0, stream>>>(v, mu.ptr, s2.ptr);
   rhat_sums_kernel<<<(D + tb - 1) / tb, tb, 0, stream>>>(v, mu.ptr, s2.ptr, out.ptr);
   WB200_CUDA(cudaGetLastError());
   WB200_CUDA(cudaMemcpyAsync(moments_host, out.ptr, 3 * D * 8, cudaMemcpyDeviceToHost, stream));
@@ -257,7 +257,7 @@ void device_summary(const double* draws, int ld, int D,
   W.alloc(D); B.alloc(D); pm.alloc(D); pv.alloc(D);
   o_rhat.alloc(D); o_ess.alloc(D); o_mcse.alloc(D);
   const int tb = 128;
-  chain_moments_kernel<<<dim3((D + tb - 1) / tb, K), tb, 0, stream>>>(v, mu.ptr, s2.ptr);
+  chain_moments_kernel<<<dim3(K, (D + tb - 1) / tb), tb, 0, stream>>>(v, mu.ptr, s2.ptr);
   WB200_CUDA(cudaGetLastError());
   across_kernel<<<(D + tb - 1) / tb, tb, 0, stream>>>(v, mu.ptr, s2.ptr, W.ptr, B.ptr,
                                                        pm.ptr, pv.ptr);
@@ -290,10 +290,10 @@ void device_summary(const double* draws, int ld, int D,
                                    cudaMemcpyDeviceToDevice, stream));
       }
       if (staged) {
-        acov_kernel<TILE><<<dim3((D + TILE - 1) / TILE, K), 256, smem, stream>>>(
+        acov_kernel<TILE><<<dim3(K, (D + TILE - 1) / TILE), 256, smem, stream>>>(
             v, mu.ptr, nlag, target - nlag, grown.ptr + static_cast<size_t>(nlag) * D);
       } else {
-        acov_global_kernel<TILE><<<dim3((D + TILE - 1) / TILE, K), 256, 0, stream>>>(
+        acov_global_kernel<TILE><<<dim3(K, (D + TILE - 1) / TILE), 256, 0, stream>>>(
             v, mu.ptr, nlag, target - nlag, grown.ptr + static_cast<size_t>(nlag) * D);
       }
       WB200_CUDA(cudaGetLastError());
