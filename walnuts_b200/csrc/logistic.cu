@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "engine.cuh"
@@ -172,6 +173,11 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles;
   int num_k_blocks;        // total K blocks (all planes of A)
   int k_blocks_per_plane;  // K blocks of one plane of A (B wraps around per plane)
+  // split-K (epilogue 2 only): a work item is (tile, split); split s accumulates K blocks
+  // [s * k_blocks_per_split, ...) and ADDS its partial tile to `out` (zeroed beforehand).
+  // Fills the SMs when there are fewer output tiles than SMs (G = R^T X has 64 tiles for a
+  // half batch of 4096 chains, each with a 1564-block K loop).
+  int k_splits, k_blocks_per_split;
   // epilogue 1 (logistic): rows = chains, columns = data rows
   int n_valid;             // data rows < n_valid are real
   __nv_bfloat16* RT;       // [Cpad][ldrt]  sigmoid(z), 0 for padding rows
@@ -283,6 +289,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = gp.num_m_tiles * gp.num_n_tiles;
+  const int num_work = num_tiles * gp.k_splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S::kStages; ++s) {
@@ -310,10 +317,13 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
     // ---------------- TMA producer
     if (lane == 0) {
       int it = 0;  // running k-block count across tiles (stage ring position)
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int t = w % num_tiles, ks = w / num_tiles;
         const int m0 = (t % gp.num_m_tiles) * BM;
         const int n0 = (t / gp.num_m_tiles) * BN;
-        for (int kb = 0; kb < gp.num_k_blocks; ++kb, ++it) {
+        const int kb0 = ks * gp.k_blocks_per_split;
+        const int kb1 = min(gp.num_k_blocks, kb0 + gp.k_blocks_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S::kStages;
           const uint32_t ph = (it / S::kStages) & 1;
           mbar_wait(empty_bar + s, ph ^ 1);
@@ -333,11 +343,14 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       int it = 0, as = 0;
       uint32_t aph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int ks = w / num_tiles;
+        const int kb0 = ks * gp.k_blocks_per_split;
+        const int kb1 = min(gp.num_k_blocks, kb0 + gp.k_blocks_per_split);
         mbar_wait(tmem_empty + as, aph ^ 1);  // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < gp.num_k_blocks; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S::kStages;
           const uint32_t ph = (it / S::kStages) & 1;
           mbar_wait(full_bar + s, ph);
@@ -349,7 +362,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B inside the 128 B swizzle span: +2 in (addr >> 4)
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, kb != kb0 || k != 0);
           }
           umma_commit(empty_bar + s);  // frees the stage when these MMAs retire
         }
@@ -365,7 +378,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
     constexpr int kChunks = BN / 32 / (epi_warps<EPI>() / 4);
     int as = 0;
     uint32_t aph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int t = w % num_tiles;
       const int m0 = (t % gp.num_m_tiles) * BM;
       const int n0 = (t / gp.num_m_tiles) * BN;
       mbar_wait(tmem_full + as, aph);
@@ -406,12 +420,18 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0,
           const int j = part * kChunks + jj;
           uint32_t v[32];
           tmem_ld32(tmem_acc + j * 32, v);
-          float4* dst = reinterpret_cast<float4*>(
-              gp.out + static_cast<long long>(row) * gp.ldo + n0 + j * 32);
+          float* dst_f = gp.out + static_cast<long long>(row) * gp.ldo + n0 + j * 32;
+          if (gp.k_splits > 1) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                 __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            for (int q = 0; q < 32; ++q) atomicAdd(dst_f + q, __uint_as_float(v[q]));
+          } else {
+            float4* dst = reinterpret_cast<float4*>(dst_f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                   __uint_as_float(v[4 * q + 2]),
+                                   __uint_as_float(v[4 * q + 3]));
+            }
           }
         }
       }
@@ -517,62 +537,59 @@ static CUtensorMap make_map(const void* base, long long rows, long long cols, in
 
 static inline long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
-struct LogisticGrad::Impl {
-  int N, D, C, ld;
-  long long Npad, Dpad, Cpad;
-  DeviceBuffer<__nv_bfloat16> X, XT, hi, lo, RT;
-  DeviceBuffer<float> y, G32;
-  DeviceBuffer<double> b, SP;
-  CUtensorMap mapX, mapHi, mapLo, mapRT, mapXT, mapRTst;
+// static data of the model, shared by every batch evaluated against it
+struct LogisticData {
+  int N, D;
+  long long Npad, Dpad;
   int bn2;
+  DeviceBuffer<__nv_bfloat16> X, XT;
+  DeviceBuffer<double> b;
+  CUtensorMap mapX, mapXT;
+};
+
+struct LogisticGrad::Impl {
+  std::shared_ptr<LogisticData> data;
+  int C, ld;
+  long long Cpad;
+  DeviceBuffer<__nv_bfloat16> hi, lo, RT;
+  DeviceBuffer<float> G32;
+  DeviceBuffer<double> SP;
+  CUtensorMap mapHi, mapLo, mapRT, mapRTst;
   int device = 0, sms = 148;
 };
+
+static void logistic_batch_buffers(LogisticGrad::Impl& m, int C, int ld, cudaStream_t stream);
 
 LogisticGrad::LogisticGrad(const double* Xh, const double* yh, size_t N, int D, int C, int ld,
                            cudaStream_t stream)
     : impl_(new Impl) {
   Impl& m = *impl_;
-  m.N = static_cast<int>(N); m.D = D; m.C = C; m.ld = ld;
-  m.Npad = round_up(static_cast<long long>(N), 256);
-  m.Dpad = round_up(D, 64);
-  m.Cpad = round_up(C, 128);
-  WB200_CUDA(cudaGetDevice(&m.device));
-  WB200_CUDA(cudaDeviceGetAttribute(&m.sms, cudaDevAttrMultiProcessorCount, m.device));
-  m.bn2 = (m.Dpad % 256 == 0) ? 256 : (m.Dpad % 128 == 0 ? 128 : 64);
+  m.data = std::make_shared<LogisticData>();
+  LogisticData& d = *m.data;
+  d.N = static_cast<int>(N); d.D = D;
+  d.Npad = round_up(static_cast<long long>(N), 256);
+  d.Dpad = round_up(D, 64);
+  d.bn2 = (d.Dpad % 256 == 0) ? 256 : (d.Dpad % 128 == 0 ? 128 : 64);
   // host staging: X and X^T in bf16 (the benchmark's X is bf16-representable, so this
-  // is exact; otherwise it rounds to nearest), y in fp32, b = X^T y in fp64
-  std::vector<__nv_bfloat16> xb(static_cast<size_t>(m.Npad) * m.Dpad, __float2bfloat16(0.0f));
-  std::vector<__nv_bfloat16> xt(static_cast<size_t>(m.Dpad) * m.Npad, __float2bfloat16(0.0f));
-  std::vector<float> yf(m.Npad, 0.0f);
-  std::vector<double> bh(m.Dpad, 0.0);
+  // is exact; otherwise it rounds to nearest), b = X^T y in fp64
+  std::vector<__nv_bfloat16> xb(static_cast<size_t>(d.Npad) * d.Dpad, __float2bfloat16(0.0f));
+  std::vector<__nv_bfloat16> xt(static_cast<size_t>(d.Dpad) * d.Npad, __float2bfloat16(0.0f));
+  std::vector<double> bh(d.Dpad, 0.0);
   for (size_t n = 0; n < N; ++n) {
-    yf[n] = static_cast<float>(yh[n]);
-    for (int d = 0; d < D; ++d) {
-      const __nv_bfloat16 v = __double2bfloat16(Xh[n * D + d]);
-      xb[n * m.Dpad + d] = v;
-      xt[static_cast<size_t>(d) * m.Npad + n] = v;
-      bh[d] += static_cast<double>(__bfloat162float(v)) * yh[n];
+    for (int j = 0; j < D; ++j) {
+      const __nv_bfloat16 v = __double2bfloat16(Xh[n * D + j]);
+      xb[n * d.Dpad + j] = v;
+      xt[static_cast<size_t>(j) * d.Npad + n] = v;
+      bh[j] += static_cast<double>(__bfloat162float(v)) * yh[n];
     }
   }
-  m.X.alloc(xb.size()); m.XT.alloc(xt.size()); m.y.alloc(yf.size()); m.b.alloc(bh.size());
-  WB200_CUDA(cudaMemcpyAsync(m.X.ptr, xb.data(), xb.size() * 2, cudaMemcpyHostToDevice, stream));
-  WB200_CUDA(cudaMemcpyAsync(m.XT.ptr, xt.data(), xt.size() * 2, cudaMemcpyHostToDevice, stream));
-  WB200_CUDA(cudaMemcpyAsync(m.y.ptr, yf.data(), yf.size() * 4, cudaMemcpyHostToDevice, stream));
-  WB200_CUDA(cudaMemcpyAsync(m.b.ptr, bh.data(), bh.size() * 8, cudaMemcpyHostToDevice, stream));
-  m.hi.alloc(static_cast<size_t>(m.Cpad) * m.Dpad);
-  m.lo.alloc(static_cast<size_t>(m.Cpad) * m.Dpad);
-  m.RT.alloc(static_cast<size_t>(m.Cpad) * m.Npad);
-  m.G32.alloc(static_cast<size_t>(m.Cpad) * m.Dpad);
-  m.SP.alloc(m.Cpad);
-  WB200_CUDA(cudaMemsetAsync(m.hi.ptr, 0, m.hi.count * 2, stream));
-  WB200_CUDA(cudaMemsetAsync(m.lo.ptr, 0, m.lo.count * 2, stream));
+  d.X.alloc(xb.size()); d.XT.alloc(xt.size()); d.b.alloc(bh.size());
+  WB200_CUDA(cudaMemcpyAsync(d.X.ptr, xb.data(), xb.size() * 2, cudaMemcpyHostToDevice, stream));
+  WB200_CUDA(cudaMemcpyAsync(d.XT.ptr, xt.data(), xt.size() * 2, cudaMemcpyHostToDevice, stream));
+  WB200_CUDA(cudaMemcpyAsync(d.b.ptr, bh.data(), bh.size() * 8, cudaMemcpyHostToDevice, stream));
   WB200_CUDA(cudaStreamSynchronize(stream));
-  m.mapX = make_map(m.X.ptr, m.Npad, m.Dpad, 256);         // GEMM 1 B (data rows)
-  m.mapHi = make_map(m.hi.ptr, m.Cpad, m.Dpad, BM);        // GEMM 1 A planes (chains)
-  m.mapLo = make_map(m.lo.ptr, m.Cpad, m.Dpad, BM);
-  m.mapRT = make_map(m.RT.ptr, m.Cpad, m.Npad, BM);        // GEMM 2 A
-  m.mapRTst = make_map(m.RT.ptr, m.Cpad, m.Npad, 32);      // GEMM 1 epilogue stores
-  m.mapXT = make_map(m.XT.ptr, m.Dpad, m.Npad, m.bn2);     // GEMM 2 B
+  d.mapX = make_map(d.X.ptr, d.Npad, d.Dpad, 256);         // GEMM 1 B (data rows)
+  d.mapXT = make_map(d.XT.ptr, d.Dpad, d.Npad, d.bn2);     // GEMM 2 B
   WB200_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<256, 1>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   GemmSmem<256>::kTotal));
@@ -585,6 +602,33 @@ LogisticGrad::LogisticGrad(const double* Xh, const double* yh, size_t N, int D, 
   WB200_CUDA(cudaFuncSetAttribute(gemm_kmajor_kernel<256, 2>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   GemmSmem<256>::kTotal));
+  logistic_batch_buffers(m, C, ld, stream);
+}
+
+LogisticGrad::LogisticGrad(const LogisticGrad& data_of, int C, cudaStream_t stream)
+    : impl_(new Impl) {
+  impl_->data = data_of.impl_->data;
+  logistic_batch_buffers(*impl_, C, data_of.impl_->ld, stream);
+}
+
+static void logistic_batch_buffers(LogisticGrad::Impl& m, int C, int ld, cudaStream_t stream) {
+  const LogisticData& d = *m.data;
+  m.C = C; m.ld = ld;
+  m.Cpad = round_up(C, 128);
+  WB200_CUDA(cudaGetDevice(&m.device));
+  WB200_CUDA(cudaDeviceGetAttribute(&m.sms, cudaDevAttrMultiProcessorCount, m.device));
+  m.hi.alloc(static_cast<size_t>(m.Cpad) * d.Dpad);
+  m.lo.alloc(static_cast<size_t>(m.Cpad) * d.Dpad);
+  m.RT.alloc(static_cast<size_t>(m.Cpad) * d.Npad);
+  m.G32.alloc(static_cast<size_t>(m.Cpad) * d.Dpad);
+  m.SP.alloc(m.Cpad);
+  WB200_CUDA(cudaMemsetAsync(m.hi.ptr, 0, m.hi.count * 2, stream));
+  WB200_CUDA(cudaMemsetAsync(m.lo.ptr, 0, m.lo.count * 2, stream));
+  WB200_CUDA(cudaStreamSynchronize(stream));
+  m.mapHi = make_map(m.hi.ptr, m.Cpad, d.Dpad, BM);        // GEMM 1 A planes (chains)
+  m.mapLo = make_map(m.lo.ptr, m.Cpad, d.Dpad, BM);
+  m.mapRT = make_map(m.RT.ptr, m.Cpad, d.Npad, BM);        // GEMM 2 A
+  m.mapRTst = make_map(m.RT.ptr, m.Cpad, d.Npad, 32);      // GEMM 1 epilogue stores
 }
 
 LogisticGrad::~LogisticGrad() { delete impl_; }
@@ -593,47 +637,59 @@ int LogisticGrad::kernels_per_eval() const { return 5; }
 
 double LogisticGrad::flops_per_eval() const {
   const Impl& m = *impl_;
+  const LogisticData& d = *m.data;
   // what the tensor cores execute: hi + lo passes of GEMM 1, one pass of GEMM 2
-  return 2.0 * m.Npad * m.Cpad * (2.0 * m.Dpad) + 2.0 * m.Cpad * m.Dpad * m.Npad;
+  return 2.0 * d.Npad * m.Cpad * (2.0 * d.Dpad) + 2.0 * m.Cpad * d.Dpad * d.Npad;
 }
 
 void LogisticGrad::evaluate(const double* TH, double* G, double* LP, cudaStream_t stream) {
   Impl& m = *impl_;
-  const long long n = static_cast<long long>(m.C) * m.Dpad;
+  const LogisticData& d = *m.data;
+  const long long n = static_cast<long long>(m.C) * d.Dpad;
   pack_theta_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      TH, m.ld, m.C, m.D, static_cast<int>(m.Dpad), m.hi.ptr, m.lo.ptr);
+      TH, m.ld, m.C, d.D, static_cast<int>(d.Dpad), m.hi.ptr, m.lo.ptr);
   WB200_CUDA(cudaMemsetAsync(m.SP.ptr, 0, m.Cpad * sizeof(double), stream));
   GemmParams g1{};
   g1.num_m_tiles = static_cast<int>(m.Cpad / BM);
-  g1.num_n_tiles = static_cast<int>(m.Npad / 256);
-  g1.k_blocks_per_plane = static_cast<int>(m.Dpad / BK);
+  g1.num_n_tiles = static_cast<int>(d.Npad / 256);
+  g1.k_blocks_per_plane = static_cast<int>(d.Dpad / BK);
   g1.num_k_blocks = 2 * g1.k_blocks_per_plane;
-  g1.n_valid = m.N; g1.RT = m.RT.ptr; g1.ldrt = m.Npad; g1.SP = m.SP.ptr;
+  g1.k_splits = 1; g1.k_blocks_per_split = g1.num_k_blocks;
+  g1.n_valid = d.N; g1.RT = m.RT.ptr; g1.ldrt = d.Npad; g1.SP = m.SP.ptr;
   const int grid1 = std::min(m.sms, g1.num_m_tiles * g1.num_n_tiles);
   gemm_kmajor_kernel<256, 1><<<grid1, gemm_threads<1>(), GemmSmem<256>::kTotal, stream>>>(
-      m.mapHi, m.mapLo, m.mapX, m.mapRTst, g1);
+      m.mapHi, m.mapLo, d.mapX, m.mapRTst, g1);
   WB200_CUDA(cudaGetLastError());
   GemmParams g2{};
   g2.num_m_tiles = static_cast<int>(m.Cpad / BM);
-  g2.num_n_tiles = static_cast<int>(m.Dpad / m.bn2);
-  g2.k_blocks_per_plane = static_cast<int>(m.Npad / BK);
+  g2.num_n_tiles = static_cast<int>(d.Dpad / d.bn2);
+  g2.k_blocks_per_plane = static_cast<int>(d.Npad / BK);
   g2.num_k_blocks = g2.k_blocks_per_plane;
-  g2.out = m.G32.ptr; g2.ldo = m.Dpad;
-  const int grid2 = std::min(m.sms, g2.num_m_tiles * g2.num_n_tiles);
-  if (m.bn2 == 256) {
+  // fewer output tiles than half the SMs: split the K loop so that every SM has work
+  const int tiles2 = g2.num_m_tiles * g2.num_n_tiles;
+  g2.k_splits = std::max(1, std::min({8, m.sms / std::max(tiles2, 1), g2.num_k_blocks / 64}));
+  g2.k_blocks_per_split = (g2.num_k_blocks + g2.k_splits - 1) / g2.k_splits;
+  // every split must own at least one K block (its accumulator is read back and added)
+  g2.k_splits = (g2.num_k_blocks + g2.k_blocks_per_split - 1) / g2.k_blocks_per_split;
+  g2.out = m.G32.ptr; g2.ldo = d.Dpad;
+  if (g2.k_splits > 1) {
+    WB200_CUDA(cudaMemsetAsync(m.G32.ptr, 0, m.G32.count * sizeof(float), stream));
+  }
+  const int grid2 = std::min(m.sms, tiles2 * g2.k_splits);
+  if (d.bn2 == 256) {
     gemm_kmajor_kernel<256, 2><<<grid2, gemm_threads<2>(), GemmSmem<256>::kTotal, stream>>>(
-        m.mapRT, m.mapRT, m.mapXT, m.mapRT, g2);
-  } else if (m.bn2 == 128) {
+        m.mapRT, m.mapRT, d.mapXT, m.mapRT, g2);
+  } else if (d.bn2 == 128) {
     gemm_kmajor_kernel<128, 2><<<grid2, gemm_threads<2>(), GemmSmem<128>::kTotal, stream>>>(
-        m.mapRT, m.mapRT, m.mapXT, m.mapRT, g2);
+        m.mapRT, m.mapRT, d.mapXT, m.mapRT, g2);
   } else {
     gemm_kmajor_kernel<64, 2><<<grid2, gemm_threads<2>(), GemmSmem<64>::kTotal, stream>>>(
-        m.mapRT, m.mapRT, m.mapXT, m.mapRT, g2);
+        m.mapRT, m.mapRT, d.mapXT, m.mapRT, g2);
   }
   WB200_CUDA(cudaGetLastError());
   logistic_finalize_kernel<<<(m.C + 7) / 8, 256, 0, stream>>>(
-      TH, m.ld, m.C, m.D, m.G32.ptr, m.Dpad, m.b.ptr, m.SP.ptr,
-      static_cast<double>(m.Npad - m.N), G, LP);
+      TH, m.ld, m.C, d.D, m.G32.ptr, d.Dpad, d.b.ptr, m.SP.ptr,
+      static_cast<double>(d.Npad - d.N), G, LP);
   WB200_CUDA(cudaGetLastError());
 }
 

@@ -11,6 +11,8 @@ class LogisticGrad {
   // X host fp64 [N][D] row-major, y host fp64 [N] in {0,1}; C chains with row stride ld
   LogisticGrad(const double* X, const double* y, size_t N, int D, int C, int ld,
                cudaStream_t stream);
+  // a second batch of C chains over the SAME data (X, X^T, X^T y stay shared on the device)
+  LogisticGrad(const LogisticGrad& data_of, int C, cudaStream_t stream);
   ~LogisticGrad();
   LogisticGrad(const LogisticGrad&) = delete;
   LogisticGrad& operator=(const LogisticGrad&) = delete;
@@ -18,9 +20,9 @@ class LogisticGrad {
   void evaluate(const double* TH, double* G, double* LP, cudaStream_t stream);
   int kernels_per_eval() const;
   double flops_per_eval() const;  // executed tensor-core flops of one batched evaluation
+  struct Impl;
 
  private:
-  struct Impl;
   Impl* impl_;
 };
 

@@ -19,12 +19,25 @@ struct TickEngine {
   DeviceBuffer<int> active;
   int* active_host = nullptr;  // pinned
   long long vec_stride = 0;
-  LogisticGrad* logistic = nullptr;
+  // The batch is evaluated as two halves: in free-running mode each half runs its own
+  // tick -> pack -> GEMM 1 -> GEMM 2 -> finalize chain on its own stream, so the
+  // element-wise kernels of one half overlap the GEMMs of the other (the tick kernel
+  // co-resides with GEMM 2's CTAs; GEMM 1 fills the register file).  logistic[1] is null
+  // for small batches.
+  LogisticGrad* logistic[2] = {nullptr, nullptr};
+  int half_begin[2] = {0, 0}, half_count[2] = {0, 0};
+  cudaStream_t half_stream[2] = {nullptr, nullptr};
+  cudaEvent_t fork_event = nullptr, join_event[2] = {nullptr, nullptr};
   WB200_BATCH_LOGP_GRAD batch_fn = nullptr;  // kind 4: the caller's batched density
   void* batch_data = nullptr;
   unsigned long long ticks = 0, grad_batches = 0;
   ~TickEngine() {
-    delete logistic;
+    for (int h = 0; h < 2; ++h) {
+      delete logistic[h];
+      if (half_stream[h]) cudaStreamDestroy(half_stream[h]);
+      if (join_event[h]) cudaEventDestroy(join_event[h]);
+    }
+    if (fork_event) cudaEventDestroy(fork_event);
     if (active_host) cudaFreeHost(active_host);
   }
 };
@@ -331,6 +344,7 @@ static TickParams tick_params(wb200_session& s, int n_iter, int adapt, bool stor
   tp.TH = e.TH.ptr; tp.G = e.G.ptr; tp.LP = e.LP.ptr;
   tp.vecs = e.vecs.ptr; tp.vec_stride = e.vec_stride;
   tp.ts = e.ts.ptr; tp.active_count = e.active.ptr;
+  tp.chain_begin = 0; tp.chain_count = s.C;
   return tp;
 }
 
@@ -370,8 +384,12 @@ __global__ void failed_batch_kernel(double* G, double* LP, int C, int ld) {
 static void tick_gradient(wb200_session& s, const TickParams& tp, bool sampling) {
   TickEngine& e = *s.tick;
   if (s.kind == kLogistic) {
-    e.logistic->evaluate(e.TH.ptr, e.G.ptr, e.LP.ptr, s.stream);
-    s.launches += e.logistic->kernels_per_eval();
+    for (int h = 0; h < 2 && e.logistic[h]; ++h) {
+      const long long off = static_cast<long long>(e.half_begin[h]) * s.ld;
+      e.logistic[h]->evaluate(e.TH.ptr + off, e.G.ptr + off, e.LP.ptr + e.half_begin[h],
+                              s.stream);
+      s.launches += e.logistic[h]->kernels_per_eval();
+    }
   } else if (s.kind == kBatchCallback) {
     const int rc = e.batch_fn(static_cast<size_t>(s.C), static_cast<size_t>(s.D),
                               static_cast<size_t>(s.ld), e.TH.ptr, e.G.ptr, e.LP.ptr,
@@ -432,9 +450,26 @@ void tick_create(wb200_session& s, const WalnutModelDesc& model) {
     if (!model.data0 || !model.data1 || model.N < 1) {
       throw std::invalid_argument("logistic needs data0 = X[N][D], data1 = y[N], N >= 1");
     }
-    e.logistic = new LogisticGrad(static_cast<const double*>(model.data0),
-                                  static_cast<const double*>(model.data1), model.N, s.D, s.C,
-                                  s.ld, s.stream);
+    // WB200_TICK_PIPELINE=1: two halves (multiples of the 128-chain GEMM tile), each on
+    // its own stream.  Measured at c4: no gain -- the step is power
+    // capped, GEMM 1 fills the register file so only GEMM 2 can share an SM with the tick
+    // kernel, and the half batches need split-K in GEMM 2 -- so one batch is the default.
+    const char* env = std::getenv("WB200_TICK_PIPELINE");
+    const bool split = s.C >= 2048 && env && std::string(env) == "1";
+    const int first = split ? std::min(s.C, ((s.C / 2 + 127) / 128) * 128) : s.C;
+    e.half_begin[0] = 0; e.half_count[0] = first;
+    e.half_begin[1] = first; e.half_count[1] = s.C - first;
+    e.logistic[0] = new LogisticGrad(static_cast<const double*>(model.data0),
+                                     static_cast<const double*>(model.data1), model.N, s.D,
+                                     first, s.ld, s.stream);
+    if (e.half_count[1] > 0) {
+      e.logistic[1] = new LogisticGrad(*e.logistic[0], e.half_count[1], s.stream);
+      for (int h = 0; h < 2; ++h) {
+        WB200_CUDA(cudaStreamCreateWithFlags(&e.half_stream[h], cudaStreamNonBlocking));
+        WB200_CUDA(cudaEventCreateWithFlags(&e.join_event[h], cudaEventDisableTiming));
+      }
+      WB200_CUDA(cudaEventCreateWithFlags(&e.fork_event, cudaEventDisableTiming));
+    }
   }
 }
 
@@ -528,12 +563,42 @@ void tick_run_ticks(wb200_session& s, int n_ticks, int adapt, bool store) {
   const int grid = (s.C + s.shape.chains_per_cta - 1) / s.shape.chains_per_cta;
   tick_resume_kernel<<<(s.C + 255) / 256, 256, 0, s.stream>>>(e.ts.ptr, s.C, s.rows_written);
   WB200_CUDA(cudaEventRecord(s.ev0, s.stream));
-  for (int t = 0; t < n_ticks; ++t) {
-    WB200_TICK_SHAPE(s.shape, WB200_TICK_RUN);
-    WB200_CUDA(cudaGetLastError());
-    tick_gradient(s, tp, true);
-    s.launches += 1;
-    e.ticks += 1;
+  if (s.kind == kLogistic && e.logistic[1]) {
+    // two half batches, each a self-contained tick / gradient chain on its own stream
+    WB200_CUDA(cudaEventRecord(e.fork_event, s.stream));
+    for (int h = 0; h < 2; ++h) {
+      WB200_CUDA(cudaStreamWaitEvent(e.half_stream[h], e.fork_event, 0));
+    }
+    for (int t = 0; t < n_ticks; ++t) {
+      for (int h = 0; h < 2; ++h) {
+        TickParams th = tp;
+        th.chain_begin = e.half_begin[h];
+        th.chain_count = e.half_count[h];
+        const int hgrid = (th.chain_count + s.shape.chains_per_cta - 1) / s.shape.chains_per_cta;
+#define WB200_TICK_RUN_HALF(T_, K_, CTA_) \
+  walnuts_tick_kernel<T_, K_, CTA_><<<hgrid, CTA_, 0, e.half_stream[h]>>>(th)
+        WB200_TICK_SHAPE(s.shape, WB200_TICK_RUN_HALF);
+        WB200_CUDA(cudaGetLastError());
+        const long long off = static_cast<long long>(th.chain_begin) * s.ld;
+        e.logistic[h]->evaluate(e.TH.ptr + off, e.G.ptr + off, e.LP.ptr + th.chain_begin,
+                                e.half_stream[h]);
+        s.launches += 1 + e.logistic[h]->kernels_per_eval();
+      }
+      e.ticks += 1;
+      e.grad_batches += 1;
+    }
+    for (int h = 0; h < 2; ++h) {
+      WB200_CUDA(cudaEventRecord(e.join_event[h], e.half_stream[h]));
+      WB200_CUDA(cudaStreamWaitEvent(s.stream, e.join_event[h], 0));
+    }
+  } else {
+    for (int t = 0; t < n_ticks; ++t) {
+      WB200_TICK_SHAPE(s.shape, WB200_TICK_RUN);
+      WB200_CUDA(cudaGetLastError());
+      tick_gradient(s, tp, true);
+      s.launches += 1;
+      e.ticks += 1;
+    }
   }
   WB200_CUDA(cudaEventRecord(s.ev1, s.stream));
 }

@@ -63,6 +63,7 @@ struct TickParams {
   long long vec_stride;
   TickState* ts;       // [C]
   int* active_count;   // chains that still have transitions to run after this tick
+  int chain_begin, chain_count;  // the launch advances chains [begin, begin + count)
 };
 
 template <int T, int K>
@@ -597,9 +598,9 @@ __global__ void __launch_bounds__(CTA, (CTA <= 128 ? 512 / CTA : 1)) walnuts_tic
     grp.warp = threadIdx.x >> 5;
     chain = blockIdx.x;
   }
-  if (chain >= tp.cp.C) return;
+  if (chain >= tp.chain_count) return;
   TickRunner<T, K> runner(tp, grp);
-  runner.tick(chain);
+  runner.tick(tp.chain_begin + chain);
 }
 #endif
 
