@@ -65,6 +65,7 @@ typedef struct {
   size_t N;
   const void* data0;
   const void* data1;
+  int precision;  /* 0 = fp64, 1 = fp32 mode (see WalnutTuning::precision); kinds 0-2 */
 } WalnutModelDesc;
 
 /* The 26 tuning arguments of walnutpie_sample_cfunc (walnutpy.cpp:134-149),
@@ -80,6 +81,14 @@ typedef struct {
   double step_accept_rate_target, step_learning_rate, step_gradient_decay;
   double step_sq_gradient_decay, step_stabilization, step_learn_rate_decay;
   int publish_stride;   /* WarmupConfig::publish_stride, config.hpp:639 (0 -> 5) */
+  /* 0 = fp64 (the reference's arithmetic).  1 = fp32 mode (element-wise targets): the
+   * integrator state theta / rho / grad / M^-1 and the leapfrog, gradient, kinetic and
+   * U-turn products are single precision inside a transition; energies and U-turn dots
+   * are accumulated across threads in fp64, every scalar decision (energy error, merge
+   * weights, Adam) and the adaptation statistics are fp64, stored draws and all
+   * host-visible state stay fp64.  Tolerance: fixed-step orbits within
+   * 2e-6 * sqrt(steps) relative of the fp64 integrator (tests/test_gpu_fp32.py). */
+  int precision;
 } WalnutTuning;
 
 /* Reference defaults (config.hpp:626-640, :947-953; step_size_init as pyfunc.py:74) */

@@ -295,13 +295,14 @@ class Checker:
                     seconds_warmup=sw.value, seconds_sampling=ss.value)
 
     # -- oracle-only ------------------------------------------------------
-    def orbit(self, target: Target, theta, rho, inv_mass, step, num_steps):
+    def orbit(self, target: Target, theta, rho, inv_mass, step, num_steps, f32=False):
+        """f32: the orbit in the device's fp32 mode (float state, double energies)."""
         D = target.D
         t = target.c()
         a = [np.ascontiguousarray(v, np.float64) for v in (theta, rho, inv_mass)]
         th, rh, g = np.zeros(D), np.zeros(D), np.zeros(D)
         lp, jt = C.c_double(0), C.c_double(0)
-        self._check(self.lib.oracle_orbit(
+        self._check((self.lib.oracle_orbit_f32 if f32 else self.lib.oracle_orbit)(
             C.byref(t), _dp(a[0]), _dp(a[1]), _dp(a[2]), C.c_double(step),
             C.c_int(num_steps), _dp(th), _dp(rh), _dp(g), C.byref(lp),
             C.byref(jt)))

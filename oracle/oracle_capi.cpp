@@ -354,6 +354,69 @@ int oracle_sampling_rhat(size_t num_chains, const double* mean, const double* va
   });
 }
 
+namespace {
+inline float maddf(float a, float b, float c) {
+  return oracle::fused_arith() ? std::fmaf(a, b, c) : a * b + c;
+}
+// log density and gradient of kinds 0-2 in float (funnel scalars in double, as the device)
+void logp_grad_f32(const OracleTarget* t, const std::vector<float>& x, double& lp,
+                   std::vector<float>& g) {
+  const size_t D = t->D;
+  if (t->kind == 0 || t->kind == 1) {
+    const double* prec = static_cast<const double*>(t->data0);
+    float s = 0.0f;
+    for (size_t i = 0; i < D; ++i) {
+      const float tt = t->kind == 0 ? x[i] : x[i] * static_cast<float>(prec[i]);
+      s = maddf(x[i], tt, s);
+      g[i] = -tt;
+    }
+    lp = static_cast<double>(-0.5f * s);
+  } else if (t->kind == 2) {
+    float ss = 0.0f;
+    for (size_t i = 1; i < D; ++i) ss = maddf(x[i], x[i], ss);
+    const double v = x[0], ev = std::exp(-v), hd = 0.5 * static_cast<double>(D - 1);
+    const double q = 0.5 * ev * static_cast<double>(ss);
+    const float evf = static_cast<float>(ev);
+    for (size_t i = 1; i < D; ++i) g[i] = -(x[i] * evf);
+    g[0] = static_cast<float>(-v / 9.0 - hd + q);
+    lp = static_cast<double>(static_cast<float>(-(v * v) / 18.0 - hd * v - q));
+  } else {
+    throw std::invalid_argument("fp32 mode covers the element-wise targets (kinds 0-2)");
+  }
+}
+}  // namespace
+
+int oracle_orbit_f32(const OracleTarget* target, const double* theta,
+                     const double* rho, const double* inv_mass, double step,
+                     int num_steps, double* theta_out, double* rho_out,
+                     double* grad_out, double* logp_out, double* joint_out) {
+  return guarded([&] {
+    const size_t D = target->D;
+    std::vector<float> th(D), rh(D), im(D), g(D);
+    for (size_t i = 0; i < D; ++i) {
+      th[i] = static_cast<float>(theta[i]);
+      rh[i] = static_cast<float>(rho[i]);
+      im[i] = static_cast<float>(inv_mass[i]);
+    }
+    double lp;
+    logp_grad_f32(target, th, lp, g);
+    const float h = static_cast<float>(step), hh = static_cast<float>(0.5 * step);
+    for (int n = 0; n < num_steps; ++n) {   // walnuts.hpp:329-332 in float
+      for (size_t i = 0; i < D; ++i) rh[i] = maddf(hh, g[i], rh[i]);
+      for (size_t i = 0; i < D; ++i) th[i] = maddf(h * im[i], rh[i], th[i]);
+      logp_grad_f32(target, th, lp, g);
+      for (size_t i = 0; i < D; ++i) rh[i] = maddf(hh, g[i], rh[i]);
+    }
+    float kin = 0.0f;
+    for (size_t i = 0; i < D; ++i) kin = maddf(im[i], rh[i] * rh[i], kin);
+    for (size_t i = 0; i < D; ++i) {
+      theta_out[i] = th[i]; rho_out[i] = rh[i]; grad_out[i] = g[i];
+    }
+    *logp_out = lp;
+    *joint_out = lp + (-0.5 * static_cast<double>(kin));
+  });
+}
+
 int oracle_set_fused_arith(int fused) {
   const int before = oracle::fused_arith() ? 1 : 0;
   oracle::fused_arith() = fused != 0;

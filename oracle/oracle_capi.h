@@ -125,6 +125,13 @@ int oracle_sampling_rhat(size_t num_chains, const double* mean, const double* va
  * baseline build, separate roundings (default; the policy pinned to the reference);
  * 1 = fused multiply-add, what the device kernels ship.  Returns the previous value. */
 int oracle_set_fused_arith(int fused);
+/* The fixed-step orbit in the device's fp32 mode (include/walnuts_b200.h,
+ * WalnutTuning::precision = 1): state and element-wise arithmetic in float, energies
+ * in double; kinds 0-2.  Inputs and outputs are fp64 arrays (rounded to float inside). */
+int oracle_orbit_f32(const OracleTarget* target, const double* theta,
+                     const double* rho, const double* inv_mass, double step,
+                     int num_steps, double* theta_out, double* rho_out,
+                     double* grad_out, double* logp_out, double* joint_out);
 int oracle_logp_grad(const OracleTarget* target, const double* theta,
                      double* logp, double* grad);
 void oracle_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -66,7 +66,8 @@ def print_callback(msg, size, is_error):
 
 class WalnutModelDesc(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int), ("D", ctypes.c_int), ("N", ctypes.c_size_t),
-                ("data0", ctypes.c_void_p), ("data1", ctypes.c_void_p)]
+                ("data0", ctypes.c_void_p), ("data1", ctypes.c_void_p),
+                ("precision", ctypes.c_int)]
 
 
 class WalnutTuning(ctypes.Structure):
@@ -90,6 +91,7 @@ class WalnutTuning(ctypes.Structure):
         ("step_stabilization", ctypes.c_double),
         ("step_learn_rate_decay", ctypes.c_double),
         ("publish_stride", ctypes.c_int),
+        ("precision", ctypes.c_int),
     ]
 
 

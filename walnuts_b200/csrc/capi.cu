@@ -88,6 +88,7 @@ void walnuts_b200_default_tuning(WalnutTuning* t) {
   t->step_gradient_decay = 0.8; t->step_sq_gradient_decay = 0.9;
   t->step_stabilization = 1e-4; t->step_learn_rate_decay = 0.5;
   t->publish_stride = 5;
+  t->precision = 0;
 }
 
 // ------------------------------------------------------------- session ----
@@ -112,6 +113,13 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
     s->chain_offset = chain_offset;
     s->tuning = *tuning;
     if (s->tuning.publish_stride <= 0) s->tuning.publish_stride = 5;
+    if (tuning->precision != 0 && tuning->precision != 1) {
+      throw std::invalid_argument("precision must be 0 (fp64) or 1 (fp32)");
+    }
+    if (model->precision != 0 && model->precision != 1) {
+      throw std::invalid_argument("precision must be 0 (fp64) or 1 (fp32)");
+    }
+    s->precision = (tuning->precision || model->precision) ? 1 : 0;
     s->shape = shape_for_dim(s->D);
     // rows are padded to the 2*T*K element slots of a chain's group: vector loads and
     // stores need no bounds checks (padding: theta = rho = grad = 0, unit metric)
@@ -157,6 +165,10 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
     const bool use_tick = s->kind == kLogistic || s->kind == kBatchCallback ||
                           (eng && std::string(eng) == "tick");
     if (use_tick) {
+      if (s->precision == 1) {
+        throw std::invalid_argument("fp32 mode is implemented by the chain-resident kernel "
+                                    "(element-wise targets); the lock-step engine is fp64");
+      }
       tick_create(*s, *model);
       WB200_CUDA(cudaStreamSynchronize(s->stream));
       *out = s.release();
@@ -164,7 +176,7 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
     }
     // slots: resident groups of the chain kernel
     int occ_adapt = 1, occ_sample = 1;
-    occupancy_for(s->kind, s->shape, s->ld, &occ_adapt, &occ_sample);
+    occupancy_for(s->kind, s->shape, s->ld, s->precision, &occ_adapt, &occ_sample);
     int sms = 0;
     WB200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const int need = (s->C + s->shape.chains_per_cta - 1) / s->shape.chains_per_cta;
@@ -554,7 +566,7 @@ int wb200_orbit(const WalnutModelDesc* model, size_t num_chains,
       WB200_CUDA(cudaMemset(tp.ptr, 0, ld * 8));
       WB200_CUDA(cudaMemcpy(tp.ptr, model->data0, D * 8, cudaMemcpyHostToDevice));
     }
-    launch_orbit(model->kind, D, ld, static_cast<int>(C), tp.ptr, th.ptr, rh.ptr,
+    launch_orbit(model->kind, model->precision, D, ld, static_cast<int>(C), tp.ptr, th.ptr, rh.ptr,
                  im.ptr, g.ptr, lp.ptr, jt.ptr, step, num_steps, st);
     download_rows(theta_out, D, th.ptr, ld, C, st);
     download_rows(rho_out, D, rh.ptr, ld, C, st);

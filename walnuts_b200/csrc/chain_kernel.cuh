@@ -70,6 +70,18 @@ __device__ __forceinline__ double madd(double a, double b, double c) {
 // one weight (adaptive_walnuts.hpp:54-80), so it cancels in var_draws / var_scores
 // (:89-94), and the mean update divides by that scalar weight (online_moments.hpp:187),
 // i.e. multiplies by a reciprocal taken once per transition.
+// fp32 mode (Real = float): the integrator state and its element-wise arithmetic are
+// single precision; energies, U-turn dots (beyond a thread's own <= 16 terms), every
+// scalar decision and the adaptation statistics stay fp64.
+__device__ __forceinline__ float madd(float a, float b, float c) {
+  if constexpr (kFusedArith) return __fmaf_rn(a, b, c);
+  return __fadd_rn(__fmul_rn(a, b), c);
+}
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
 __device__ __forceinline__ double metric_from_sums(double S_draw, double S_score, double w) {
   if constexpr (kFusedArith) return sqrt(S_draw / S_score);
   return sqrt((S_draw / w) / (S_score / w));
@@ -275,40 +287,66 @@ constexpr int group_smem_doubles() {
 // ---------------------------------------------------------------------------
 // Rows are padded to the 2*T*K element slots of their group (row_stride()), so loads and
 // stores need no bounds checks; padding holds theta = rho = grad = 0 and a unit metric.
-template <int T, int K>
-struct Vec {
+template <class Real> struct PairOf;
+template <> struct PairOf<double> { using type = double2; };
+template <> struct PairOf<float> { using type = float2; };
+
+template <int T, int K, class Real>
+struct VecT {
+  using Pair = typename PairOf<Real>::type;
   // element pair owned by this thread in chunk k: 2*(tid + k*T), +1
-  __device__ __forceinline__ static void load(const double* row, int, int tid,
-                                              double (&x)[K][2]) {
+  __device__ __forceinline__ static void load(const Real* row, int, int tid,
+                                              Real (&x)[K][2]) {
+    const Pair* r2 = reinterpret_cast<const Pair*>(row) + tid;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const Pair v = r2[k * T];
+      x[k][0] = v.x; x[k][1] = v.y;
+    }
+  }
+  __device__ __forceinline__ static void store(Real* row, int, int tid,
+                                               const Real (&x)[K][2]) {
+    Pair* r2 = reinterpret_cast<Pair*>(row) + tid;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      Pair v;
+      v.x = x[k][0]; v.y = x[k][1];
+      r2[k * T] = v;
+    }
+  }
+  // the same against fp64 rows (host-visible state is always fp64)
+  __device__ __forceinline__ static void load64(const double* row, int tid, Real (&x)[K][2]) {
     const double2* r2 = reinterpret_cast<const double2*>(row) + tid;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const double2 v = r2[k * T];
-      x[k][0] = v.x; x[k][1] = v.y;
+      x[k][0] = static_cast<Real>(v.x); x[k][1] = static_cast<Real>(v.y);
     }
   }
-  __device__ __forceinline__ static void store(double* row, int, int tid,
-                                               const double (&x)[K][2]) {
+  __device__ __forceinline__ static void store64(double* row, int tid, const Real (&x)[K][2]) {
     double2* r2 = reinterpret_cast<double2*>(row) + tid;
 #pragma unroll
-    for (int k = 0; k < K; ++k) r2[k * T] = make_double2(x[k][0], x[k][1]);
+    for (int k = 0; k < K; ++k) {
+      r2[k * T] = make_double2(static_cast<double>(x[k][0]), static_cast<double>(x[k][1]));
+    }
   }
-  __device__ __forceinline__ static void copy(double (&dst)[K][2],
-                                              const double (&src)[K][2]) {
+  __device__ __forceinline__ static void copy(Real (&dst)[K][2], const Real (&src)[K][2]) {
 #pragma unroll
     for (int k = 0; k < K; ++k) { dst[k][0] = src[k][0]; dst[k][1] = src[k][1]; }
   }
 };
+template <int T, int K>
+using Vec = VecT<T, K, double>;
 
 // ---------------------------------------------------------------------------
 // Targets.  grad() fills g and a per-thread partial `lp_part` whose group sum
 // is logp (so Gaussians need no reduction inside a micro-step).
-template <int T, int K>
-struct StdNormalTarget {  // examples/walnutpie_api.cpp:39-43
+template <int T, int K, class Real>
+struct StdNormalTargetT {  // examples/walnutpie_api.cpp:39-43
   __device__ __forceinline__ void init(const ChainParams&, int) {}
-  __device__ __forceinline__ void grad(const double (&th)[K][2], double (&g)[K][2],
-                                       double& lp_part, Group<T>&) const {
-    double s = 0.0;
+  __device__ __forceinline__ void grad(const Real (&th)[K][2], Real (&g)[K][2],
+                                       Real& lp_part, Group<T>&) const {
+    Real s = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
@@ -317,34 +355,34 @@ struct StdNormalTarget {  // examples/walnutpie_api.cpp:39-43
         g[k][v] = -th[k][v];
       }
     }
-    lp_part = -0.5 * s;
+    lp_part = static_cast<Real>(-0.5) * s;
   }
 };
 
-template <int T, int K>
-struct DiagGaussianTarget {  // generalises examples/examples.cpp:20-31
-  double prec[K][2];
+template <int T, int K, class Real>
+struct DiagGaussianTargetT {  // generalises examples/examples.cpp:20-31
+  Real prec[K][2];
   __device__ __forceinline__ void init(const ChainParams& p, int tid) {
-    Vec<T, K>::load(p.tparam, p.ld, tid, prec);
+    VecT<T, K, Real>::load64(p.tparam, tid, prec);
   }
-  __device__ __forceinline__ void grad(const double (&th)[K][2], double (&g)[K][2],
-                                       double& lp_part, Group<T>&) const {
-    double s = 0.0;
+  __device__ __forceinline__ void grad(const Real (&th)[K][2], Real (&g)[K][2],
+                                       Real& lp_part, Group<T>&) const {
+    Real s = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        double t = __dmul_rn(th[k][v], prec[k][v]);
+        Real t = mul_rn(th[k][v], prec[k][v]);
         s = madd(th[k][v], t, s);
         g[k][v] = -t;
       }
     }
-    lp_part = -0.5 * s;
+    lp_part = static_cast<Real>(-0.5) * s;
   }
 };
 
-template <int T, int K>
-struct FunnelTarget {
+template <int T, int K, class Real>
+struct FunnelTargetT {
   double half_dm1;
   bool owner;  // owns element 0 (v)
   int room;    // D - 2 * tid: element slot 2 * k * T + v of this thread is real iff < room
@@ -353,9 +391,9 @@ struct FunnelTarget {
     owner = (tid == 0);
     room = p.D - 2 * tid;
   }
-  __device__ __forceinline__ void grad(const double (&th)[K][2], double (&g)[K][2],
-                                       double& lp_part, Group<T>& grp) const {
-    double ss = 0.0;
+  __device__ __forceinline__ void grad(const Real (&th)[K][2], Real (&g)[K][2],
+                                       Real& lp_part, Group<T>& grp) const {
+    Real ss = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
@@ -364,29 +402,36 @@ struct FunnelTarget {
         ss = is_v ? ss : madd(th[k][v], th[k][v], ss);
       }
     }
-    double r[2] = {ss, owner ? th[0][0] : 0.0};
+    double r[2] = {static_cast<double>(ss), owner ? static_cast<double>(th[0][0]) : 0.0};
     grp.sum(r);
     const double v0 = r[1];
     const double ev = exp(-v0);
     const double q = __dmul_rn(__dmul_rn(0.5, ev), r[0]);
+    const Real ev_r = static_cast<Real>(ev);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
         // padding slots hold theta = 0: 0 * exp(-v0) must stay 0 when exp overflows
-        g[k][v] = (2 * k * T + v < room) ? -__dmul_rn(th[k][v], ev) : 0.0;
+        g[k][v] = (2 * k * T + v < room) ? -mul_rn(th[k][v], ev_r) : static_cast<Real>(0);
       }
     }
     if (owner) {
       double lp = __dadd_rn(__dadd_rn(-__dmul_rn(v0, v0) / 18.0,
                                       -__dmul_rn(half_dm1, v0)), -q);
-      g[0][0] = __dadd_rn(__dadd_rn(-v0 / 9.0, -half_dm1), q);
-      lp_part = lp;
+      g[0][0] = static_cast<Real>(__dadd_rn(__dadd_rn(-v0 / 9.0, -half_dm1), q));
+      lp_part = static_cast<Real>(lp);
     } else {
-      lp_part = 0.0;
+      lp_part = 0;
     }
   }
 };
+template <int T, int K> using StdNormalTarget = StdNormalTargetT<T, K, double>;
+template <int T, int K> using DiagGaussianTarget = DiagGaussianTargetT<T, K, double>;
+template <int T, int K> using FunnelTarget = FunnelTargetT<T, K, double>;
+template <int T, int K> using StdNormalTargetF = StdNormalTargetT<T, K, float>;
+template <int T, int K> using DiagGaussianTargetF = DiagGaussianTargetT<T, K, float>;
+template <int T, int K> using FunnelTargetF = FunnelTargetT<T, K, float>;
 
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double log_sum_exp2(double x1, double x2) {
@@ -554,9 +599,9 @@ __device__ __noinline__ inline double sqrt_noinline(double a) { return sqrt(a); 
 // Start of a transition (adaptive_walnuts.hpp:235-245): M^-1 from the estimators ->
 // scratch row `im_row`; thread 0 publishes step = exp(adam_x) and min-micro in `sc`.
 // Returns the group's barrier parity.
-template <int T, int K>
+template <int T, int K, class Real>
 __device__ __noinline__ int adapt_begin(const ChainParams& p, Group<T> grp, ChainScalars& sc,
-                                        const double* est_row, double* im_row) {
+                                        const double* est_row, Real* im_row) {
   using V = Vec<T, K>;
   const int ld = p.ld, tid = grp.tid;
   grp.sync();  // thread 0's updates at the end of the previous transition are visible
@@ -575,7 +620,17 @@ __device__ __noinline__ int adapt_begin(const ChainParams& p, Group<T> grp, Chai
                                                   div_noinline(Ss[k][v], est_w)));
     }
   }
-  V::store(im_row, ld, tid, im);
+  if constexpr (sizeof(Real) == 8) {
+    V::store(im_row, ld, tid, im);
+  } else {
+    Real im_r[K][2];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      im_r[k][0] = static_cast<Real>(im[k][0]);
+      im_r[k][1] = static_cast<Real>(im[k][1]);
+    }
+    VecT<T, K, Real>::store(im_row, ld, tid, im_r);
+  }
   if (tid == 0) {
     sc.step = exp(sc.adam_x);
     sc.min_micro = min_micro_steps(sc.mm_total, sc.mm_count, p);
@@ -586,15 +641,15 @@ __device__ __noinline__ int adapt_begin(const ChainParams& p, Group<T> grp, Chai
 
 // End of a transition (adaptive_walnuts.hpp:247-250): gradient at the selected draw,
 // discounted Welford updates of draws and scores, estimator weight, min-micro controller.
-template <class Target, int T, int K>
+template <class Target, int T, int K, class Real>
 __device__ __noinline__ int adapt_end(const ChainParams& p, Group<T> grp, ChainScalars& sc,
-                                      double* est_row, const double* sel_row, int depth) {
+                                      double* est_row, const Real* sel_row, int depth) {
   using V = Vec<T, K>;
   const int ld = p.ld, tid = grp.tid;
   Target tgt;
   tgt.init(p, tid);
-  double cur[K][2], gsel[K][2], lp_dummy;
-  V::load(sel_row, ld, tid, cur);
+  Real cur[K][2], gsel[K][2], lp_dummy;
+  VecT<T, K, Real>::load(sel_row, ld, tid, cur);
   tgt.grad(cur, gsel, lp_dummy, grp);  // grad_select (cached by the reference)
   const double gamma = 1.0 - 1.0 / (p.mass_init_count + static_cast<double>(sc.warm_iter));
   const double est_w = gamma * sc.est_w + 1.0;
@@ -608,7 +663,7 @@ __device__ __noinline__ int adapt_end(const ChainParams& p, Group<T> grp, ChainS
     for (int k = 0; k < K; ++k) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        const double y = e == 0 ? cur[k][v] : gsel[k][v];
+        const double y = static_cast<double>(e == 0 ? cur[k][v] : gsel[k][v]);
         // online_moments.hpp:185-191 (both factors see the updated mean)
         mu[k][v] = kFusedArith
                        ? madd(__dadd_rn(y, -mu[k][v]), r_w, mu[k][v])
@@ -632,20 +687,20 @@ __device__ __noinline__ int adapt_end(const ChainParams& p, Group<T> grp, ChainS
 
 // ADAPT is a compile-time copy of ChainParams::adapt: the sampling instance carries none
 // of the adaptation code (the kernel competes for the instruction cache)
-template <class Target, int T, int K, bool ADAPT = true>
+template <class Target, int T, int K, bool ADAPT = true, class Real = double>
 struct ChainRunner {
-  using V = Vec<T, K>;
+  using V = VecT<T, K, Real>;
   const ChainParams& p;
   Group<T>& grp;
   Target tgt;
-  double* scr;   // this slot's scratch
+  double* scr;   // this slot's scratch (rows of Real, then the Adam queue in doubles)
   int ld, tid;
   // registers: the live integrator state / newest leaf, and the metric
-  double th[K][2], rho[K][2], g[K][2];
-  double im[K][2];
+  Real th[K][2], rho[K][2], g[K][2];
+  Real im[K][2];
   // shared memory of this chain (chain_smem_doubles): the macro-step start state =
   // previous leaf, and the stack of finished sub-trees
-  double* s_ths; double* s_rhos; double* s_gs;
+  Real* s_ths; Real* s_rhos; Real* s_gs;
   double* st_logW; double* st_lp;
   // per-chain scalars live in shared memory; read-modify-write only by thread 0,
   // read by others only after a barrier.
@@ -662,15 +717,15 @@ struct ChainRunner {
   __device__ ChainRunner(const ChainParams& p_, Group<T>& grp_, double* scr_,
                          ChainScalars& sc_, double* chain_smem)
       : p(p_), grp(grp_), scr(scr_), ld(p_.ld), tid(grp_.tid), sc(sc_) {
-    s_ths = chain_smem;
-    s_rhos = chain_smem + p_.ld;
-    s_gs = chain_smem + 2 * p_.ld;
-    st_logW = chain_smem + 3 * p_.ld;
+    st_logW = chain_smem;
     st_lp = st_logW + kMaxDepth;
+    s_ths = reinterpret_cast<Real*>(chain_smem + 2 * kMaxDepth);
+    s_rhos = s_ths + p_.ld;
+    s_gs = s_ths + 2 * p_.ld;
   }
 
-  __device__ __forceinline__ double* sv(int v) const {
-    return scr + static_cast<long long>(v) * ld;
+  __device__ __forceinline__ Real* sv(int v) const {
+    return reinterpret_cast<Real*>(scr) + static_cast<long long>(v) * ld;
   }
 
   // the live state becomes / is restored from the macro-step start state
@@ -686,13 +741,13 @@ struct ChainRunner {
   }
 
   // one leapfrog micro-step, walnuts.hpp:329-332
-  __device__ __forceinline__ void leapfrog(double h, double hh, double& lp_part) {
+  __device__ __forceinline__ void leapfrog(Real h, Real hh, Real& lp_part) {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
         rho[k][v] = madd(hh, g[k][v], rho[k][v]);
-        th[k][v] = madd(__dmul_rn(h, im[k][v]), rho[k][v], th[k][v]);
+        th[k][v] = madd(mul_rn(h, im[k][v]), rho[k][v], th[k][v]);
       }
     }
     tgt.grad(th, g, lp_part, grp);
@@ -711,40 +766,41 @@ struct ChainRunner {
   __device__ __forceinline__ void integrate(int n, double h, double& lp, double& H,
                                             bool with_dots, double& dot_new,
                                             double& dot_old) {
-    const double hh = 0.5 * h;
-    double lp_part = 0.0;
-    for (int j = 0; j < n; ++j) leapfrog(h, hh, lp_part);
+    const Real h_r = static_cast<Real>(h), hh = static_cast<Real>(0.5 * h);
+    Real lp_part = 0;
+    for (int j = 0; j < n; ++j) leapfrog(h_r, hh, lp_part);
     evals += static_cast<unsigned long long>(n);
-    double kin = 0.0;
+    Real kin = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        kin = madd(im[k][v], __dmul_rn(rho[k][v], rho[k][v]), kin);
+        kin = madd(im[k][v], mul_rn(rho[k][v], rho[k][v]), kin);
       }
     }
     if (with_dots) {
-      double a = 0.0, b = 0.0;
-      double ths[K][2], rhos[K][2];
+      Real a = 0, b = 0;
+      Real ths[K][2], rhos[K][2];
       V::load(s_ths, ld, tid, ths);
       V::load(s_rhos, ld, tid, rhos);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
-          double sd = __dmul_rn(im[k][v], __dadd_rn(th[k][v], -ths[k][v]));
+          Real sd = mul_rn(im[k][v], add_rn(th[k][v], -ths[k][v]));
           a = madd(rho[k][v], sd, a);
           b = madd(rhos[k][v], sd, b);
         }
       }
-      double r[4] = {lp_part, kin, a, b};
+      double r[4] = {static_cast<double>(lp_part), static_cast<double>(kin),
+                     static_cast<double>(a), static_cast<double>(b)};
       grp.sum(r);
       lp = r[0];
       H = r[0] + (-0.5 * r[1]);
       dot_new = r[2];
       dot_old = r[3];
     } else {
-      double r[2] = {lp_part, kin};
+      double r[2] = {static_cast<double>(lp_part), static_cast<double>(kin)};
       grp.sum(r);
       lp = r[0];
       H = r[0] + (-0.5 * r[1]);
@@ -813,22 +869,22 @@ struct ChainRunner {
 
   // uturn (:192-201) between a far state F (in scratch) and the newest leaf
   // L = (th, rho); dir gives the time order.
-  __device__ __forceinline__ bool uturn(const double* thF_row, const double* rhoF_row,
+  __device__ __forceinline__ bool uturn(const Real* thF_row, const Real* rhoF_row,
                                         int dir) {
-    double thF[K][2], rhoF[K][2];
+    Real thF[K][2], rhoF[K][2];
     V::load(thF_row, ld, tid, thF);
     V::load(rhoF_row, ld, tid, rhoF);
-    double a = 0.0, b = 0.0;
+    Real a = 0, b = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        double sd = __dmul_rn(im[k][v], __dadd_rn(th[k][v], -thF[k][v]));
+        Real sd = mul_rn(im[k][v], add_rn(th[k][v], -thF[k][v]));
         a = madd(rho[k][v], sd, a);
         b = madd(rhoF[k][v], sd, b);
       }
     }
-    double r[2] = {a, b};
+    double r[2] = {static_cast<double>(a), static_cast<double>(b)};
     grp.sum(r);
     if (dir < 0) { r[0] = -r[0]; r[1] = -r[1]; }
     return r[0] < 0 || r[1] < 0;
@@ -866,10 +922,21 @@ struct ChainRunner {
   }
 
   // copy one vector between rows (parked state / scratch), through registers
-  __device__ __forceinline__ void copy_row(double* dst, const double* src) {
-    double t[K][2];
+  __device__ __forceinline__ void copy_row(Real* dst, const Real* src) {
+    Real t[K][2];
     V::load(src, ld, tid, t);
     V::store(dst, ld, tid, t);
+  }
+  // fp64 rows of the session (theta, stored draws) <-> rows of the working precision
+  __device__ __forceinline__ void row_from64(Real* dst, const double* src) {
+    Real t[K][2];
+    V::load64(src, tid, t);
+    V::store(dst, ld, tid, t);
+  }
+  __device__ __forceinline__ void row_to64(double* dst, const Real* src) {
+    Real t[K][2];
+    V::load(src, ld, tid, t);
+    V::store64(dst, tid, t);
   }
 
   __device__ __forceinline__ void run(int chain) {
@@ -889,18 +956,21 @@ struct ChainRunner {
     // in shared memory and are read where they are used
     auto est_row = [&]() { return p.est + static_cast<long long>(chain) * 4 * ld; };
     // the chain's current position lives in scratch row A_SEL between transitions
-    copy_row(sv(A_SEL), theta_row);
+    row_from64(sv(A_SEL), theta_row);
     if (!ADAPT) {
-      V::load(p.inv_mass + static_cast<long long>(chain) * ld, ld, tid, im);
       // Cholesky factor of the fixed metric, sqrt().inverse() (walnuts.hpp:647): constant
       // over the launch, so its square roots and divisions are paid once per chain
-      double c[K][2];
+      double im64[K][2];
+      Vec<T, K>::load(p.inv_mass + static_cast<long long>(chain) * ld, ld, tid, im64);
+      Real c[K][2];
 #pragma unroll
       for (int k = 0; k < K; ++k) {
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           const bool pad = 2 * (tid + k * T) + v >= p.D;
-          c[k][v] = div_noinline(1.0, sqrt_noinline(pad ? 1.0 : im[k][v]));
+          im[k][v] = static_cast<Real>(im64[k][v]);
+          c[k][v] = static_cast<Real>(
+              div_noinline(1.0, sqrt_noinline(pad ? 1.0 : im64[k][v])));
         }
       }
       V::store(sv(A_IM), ld, tid, c);
@@ -913,7 +983,7 @@ struct ChainRunner {
       int min_micro;
       // ---- metric, step, min-micro for this transition
       if (ADAPT) {
-        grp.parity = adapt_begin<T, K>(p, grp, sc, est_row(), sv(A_IM));
+        grp.parity = adapt_begin<T, K, Real>(p, grp, sc, est_row(), sv(A_IM));
         V::load(sv(A_IM), ld, tid, im);
       }
       step = sc.step;
@@ -924,18 +994,17 @@ struct ChainRunner {
       for (int k = 0; k < K; ++k) {
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
-          if (2 * (tid + k * T) + v >= p.D) im[k][v] = 1.0;
+          if (2 * (tid + k * T) + v >= p.D) im[k][v] = 1;
         }
       }
       const long long row = p.draw_base + it;
       if (p.im_out) {
-        V::store(p.im_out + (static_cast<long long>(chain) * p.draw_cap + row) * ld,
-                 ld, tid, im);
+        V::store64(p.im_out + (static_cast<long long>(chain) * p.draw_cap + row) * ld, tid, im);
       }
       // ---- momentum refresh rho = chol_mass * z  (walnuts.hpp:528-529)
       V::load(sv(A_SEL), ld, tid, th);
       {
-        double c[K][2];
+        Real c[K][2];
         if (!ADAPT) V::load(sv(A_IM), ld, tid, c);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -948,27 +1017,29 @@ struct ChainRunner {
           }
           // adaptive: inverse().sqrt() (adaptive_walnuts.hpp:236);
           // fixed:    sqrt().inverse() (walnuts.hpp:647), precomputed above
-          const double c0 = ADAPT ? sqrt_noinline(div_noinline(1.0, im[k][0])) : c[k][0];
-          const double c1 = ADAPT ? sqrt_noinline(div_noinline(1.0, im[k][1])) : c[k][1];
-          rho[k][0] = __dmul_rn(c0, z0);
-          rho[k][1] = __dmul_rn(c1, z1);
+          const Real c0 = ADAPT ? static_cast<Real>(sqrt_noinline(div_noinline(
+                                      1.0, static_cast<double>(im[k][0])))) : c[k][0];
+          const Real c1 = ADAPT ? static_cast<Real>(sqrt_noinline(div_noinline(
+                                      1.0, static_cast<double>(im[k][1])))) : c[k][1];
+          rho[k][0] = mul_rn(c0, static_cast<Real>(z0));
+          rho[k][1] = mul_rn(c1, static_cast<Real>(z1));
         }
       }
       // ---- initial point (walnuts.hpp:532-535)
       double lp0, H0;
       {
-        double lp_part;
+        Real lp_part;
         tgt.grad(th, g, lp_part, grp);
         evals += 1;
-        double kin = 0.0;
+        Real kin = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
-            kin = madd(im[k][v], __dmul_rn(rho[k][v], rho[k][v]), kin);
+            kin = madd(im[k][v], mul_rn(rho[k][v], rho[k][v]), kin);
           }
         }
-        double r[2] = {lp_part, kin};
+        double r[2] = {static_cast<double>(lp_part), static_cast<double>(kin)};
         grp.sum(r);
         lp0 = r[0];
         H0 = r[0] + (-0.5 * r[1]);
@@ -1090,7 +1161,7 @@ struct ChainRunner {
       }
       // ---- the draw (scratch row A_SEL)
       if (ADAPT) {
-        grp.parity = adapt_end<Target, T, K>(p, grp, sc, est_row(), sv(A_SEL), depth);
+        grp.parity = adapt_end<Target, T, K, Real>(p, grp, sc, est_row(), sv(A_SEL), depth);
       } else if (tid == 0) {
         // WelfordAccumulator::observe (sampler.hpp:87-88)
         sc.lp_n += 1;
@@ -1105,7 +1176,7 @@ struct ChainRunner {
         sc.last_lp = lp_sel;
       }
       if (p.draws) {
-        copy_row(p.draws + (static_cast<long long>(chain) * p.draw_cap + row) * ld,
+        row_to64(p.draws + (static_cast<long long>(chain) * p.draw_cap + row) * ld,
                  sv(A_SEL));
       }
       if (tid == 0) {
@@ -1115,7 +1186,7 @@ struct ChainRunner {
         if (p.step_out) p.step_out[o] = ADAPT ? exp_noinline(sc.adam_x) : sc.step;
       }
     }
-    copy_row(theta_row, sv(A_SEL));
+    row_to64(theta_row, sv(A_SEL));
     if (tid == 0) {
       sc.grad_evals += evals;
       sc.iter = u_iter;
@@ -1127,7 +1198,7 @@ struct ChainRunner {
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------
-template <class Target, int T, int K, int CTA, int MINB, bool ADAPT>
+template <class Target, int T, int K, int CTA, int MINB, bool ADAPT, class Real = double>
 __global__ void __launch_bounds__(CTA, MINB)
 walnuts_chain_kernel(const ChainParams p) {
   extern __shared__ double chain_smem[];  // [CTA / T][chain_smem_doubles(ld)]
@@ -1152,7 +1223,7 @@ walnuts_chain_kernel(const ChainParams p) {
     slot = blockIdx.x;
   }
   double* scr = p.scratch + static_cast<long long>(slot) * p.scratch_stride;
-  ChainRunner<Target, T, K, ADAPT> runner(
+  ChainRunner<Target, T, K, ADAPT, Real> runner(
       p, grp, scr, sc_smem[threadIdx.x / T],
       chain_smem + static_cast<int>(threadIdx.x / T) * chain_smem_doubles(p.ld));
   if (grp.tid == 0) {

@@ -52,6 +52,33 @@ LaunchShape shape_for_dim(int D) {
     else { MACRO(TARGET, 512, 4, 512, 1, 1); }                                 \
   } while (0)
 
+// fp32 mode: half the register footprint per element, so more resident CTAs
+#ifndef WB200_MINB_128X4_F32
+#define WB200_MINB_128X4_F32 5
+#endif
+#define WB200_FOR_SHAPE_F32(S, MACRO, TARGET)                                  \
+  do {                                                                         \
+    if ((S).T == 32 && (S).K == 1) { MACRO(TARGET, 32, 1, 128, 4, 4); }        \
+    else if ((S).T == 32 && (S).K == 2) { MACRO(TARGET, 32, 2, 128, 4, 4); }   \
+    else if ((S).T == 64) { MACRO(TARGET, 64, 2, 64, 6, 8); }                  \
+    else if ((S).T == 128 && (S).K == 2) { MACRO(TARGET, 128, 2, 128, 4, 5); } \
+    else if ((S).T == 128 && (S).K == 4) { MACRO(TARGET, 128, 4, 128, 4, WB200_MINB_128X4_F32); } \
+    else if ((S).T == 256 && (S).K == 2) { MACRO(TARGET, 256, 2, 256, 2, 2); } \
+    else if ((S).T == 256 && (S).K == 4) { MACRO(TARGET, 256, 4, 256, 1, 2); } \
+    else { MACRO(TARGET, 512, 4, 512, 1, 1); }                                 \
+  } while (0)
+
+#define WB200_FOR_TARGET_F32(KIND, S, MACRO)                                   \
+  do {                                                                         \
+    switch (KIND) {                                                            \
+      case kStdNormal: WB200_FOR_SHAPE_F32(S, MACRO, StdNormalTargetF); break; \
+      case kDiagGaussian: WB200_FOR_SHAPE_F32(S, MACRO, DiagGaussianTargetF); break; \
+      case kFunnel: WB200_FOR_SHAPE_F32(S, MACRO, FunnelTargetF); break;       \
+      default: throw std::invalid_argument("model kind has no chain-resident " \
+                                           "kernel");                          \
+    }                                                                          \
+  } while (0)
+
 #define WB200_FOR_TARGET(KIND, S, MACRO)                                       \
   do {                                                                         \
     switch (KIND) {                                                            \
@@ -246,10 +273,10 @@ struct OrbitParams {
   double step; int num_steps;
 };
 
-template <template <int, int> class TargetT, int T, int K, int CTA>
+template <template <int, int> class TargetT, int T, int K, int CTA, class Real>
 __global__ void __launch_bounds__(CTA) orbit_kernel(const OrbitParams op) {
   using Target = TargetT<T, K>;
-  using V = Vec<T, K>;
+  using V = VecT<T, K, Real>;
   __shared__ double red_smem[group_smem_doubles<T>()];
   const ChainParams& p = op.cp;
   Group<T> grp;
@@ -264,13 +291,13 @@ __global__ void __launch_bounds__(CTA) orbit_kernel(const OrbitParams op) {
   }
   if (chain >= p.C) return;
   ChainScalars unused_sc{};
-  ChainRunner<Target, T, K, false> r(p, grp, nullptr, unused_sc, nullptr);
+  ChainRunner<Target, T, K, false, Real> r(p, grp, nullptr, unused_sc, nullptr);
   r.tgt.init(p, grp.tid);
   const long long off = static_cast<long long>(chain) * p.ld;
-  V::load(p.theta + off, p.ld, grp.tid, r.th);
-  V::load(op.rho + off, p.ld, grp.tid, r.rho);
-  V::load(p.inv_mass + off, p.ld, grp.tid, r.im);
-  double lp_part;
+  V::load64(p.theta + off, grp.tid, r.th);
+  V::load64(op.rho + off, grp.tid, r.rho);
+  V::load64(p.inv_mass + off, grp.tid, r.im);
+  Real lp_part;
   r.tgt.grad(r.th, r.g, lp_part, grp);
   r.evals = 0;
   double lp, H;
@@ -278,16 +305,16 @@ __global__ void __launch_bounds__(CTA) orbit_kernel(const OrbitParams op) {
     double d0, d1;
     r.integrate(op.num_steps, op.step, lp, H, false, d0, d1);
   } else {
-    double kin = 0.0;
+    Real kin = 0;
     for (int k = 0; k < K; ++k)
       for (int v = 0; v < 2; ++v) kin = madd(r.im[k][v], r.rho[k][v] * r.rho[k][v], kin);
-    double s[2] = {lp_part, kin};
+    double s[2] = {static_cast<double>(lp_part), static_cast<double>(kin)};
     grp.sum(s);
     lp = s[0]; H = s[0] + (-0.5 * s[1]);
   }
-  V::store(p.theta + off, p.ld, grp.tid, r.th);
-  V::store(op.rho + off, p.ld, grp.tid, r.rho);
-  V::store(op.grad + off, p.ld, grp.tid, r.g);
+  V::store64(p.theta + off, grp.tid, r.th);
+  V::store64(op.rho + off, grp.tid, r.rho);
+  V::store64(op.grad + off, grp.tid, r.g);
   if (grp.tid == 0) { op.logp[chain] = lp; op.joint[chain] = H; }
 }
 
@@ -332,16 +359,42 @@ static int sm_count(int device) {
           <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
     }                                                                          \
   } while (0)
+#define WB200_OCC_F32(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)                  \
+  do {                                                                         \
+    occ_adapt = blocks_per_sm(                                                 \
+        walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true, float>, CTA_, \
+        dyn_smem);                                                             \
+    occ_sample = blocks_per_sm(                                                \
+        walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false, float>, CTA_, \
+        dyn_smem);                                                             \
+  } while (0)
+#define WB200_LAUNCH_CHAIN_F32(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)         \
+  do {                                                                         \
+    if (p.adapt) {                                                             \
+      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true, float> \
+          <<<s.grid_adapt, CTA_, dyn_smem, s.stream>>>(p);                     \
+    } else {                                                                   \
+      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false, float> \
+          <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
+    }                                                                          \
+  } while (0)
 #define WB200_LAUNCH_INIT(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)              \
   init_kernel<TARGET, T_, K_, CTA_><<<grid, CTA_, 0, s.stream>>>(ip)
 #define WB200_LAUNCH_ORBIT(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)             \
-  orbit_kernel<TARGET, T_, K_, CTA_><<<grid, CTA_, 0, stream>>>(op)
+  orbit_kernel<TARGET, T_, K_, CTA_, double><<<grid, CTA_, 0, stream>>>(op)
+#define WB200_LAUNCH_ORBIT_F32(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)         \
+  orbit_kernel<TARGET, T_, K_, CTA_, float><<<grid, CTA_, 0, stream>>>(op)
 
 // resident CTAs per SM of the adaptive and of the sampling instance
-void occupancy_for(int kind, const LaunchShape& shape, int ld, int* adapt, int* sample) {
+void occupancy_for(int kind, const LaunchShape& shape, int ld, int precision, int* adapt,
+                   int* sample) {
   int occ_adapt = 1, occ_sample = 1;
   const size_t dyn_smem = chain_dyn_smem(shape, ld);
-  WB200_FOR_TARGET(kind, shape, WB200_OCC);
+  if (precision == 1) {
+    WB200_FOR_TARGET_F32(kind, shape, WB200_OCC_F32);
+  } else {
+    WB200_FOR_TARGET(kind, shape, WB200_OCC);
+  }
   *adapt = occ_adapt;
   *sample = occ_sample;
 }
@@ -351,7 +404,11 @@ void launch_chains(wb200_session& s, int n_iter, int adapt, bool store) {
   const size_t dyn_smem = chain_dyn_smem(s.shape, s.ld);
   WB200_CUDA(cudaMemsetAsync(s.ticket.ptr, 0, sizeof(unsigned int), s.stream));
   WB200_CUDA(cudaEventRecord(s.ev0, s.stream));
-  WB200_FOR_TARGET(s.kind, s.shape, WB200_LAUNCH_CHAIN);
+  if (s.precision == 1) {
+    WB200_FOR_TARGET_F32(s.kind, s.shape, WB200_LAUNCH_CHAIN_F32);
+  } else {
+    WB200_FOR_TARGET(s.kind, s.shape, WB200_LAUNCH_CHAIN);
+  }
   WB200_CUDA(cudaGetLastError());
   WB200_CUDA(cudaEventRecord(s.ev1, s.stream));
   s.launches += 1;
@@ -385,7 +442,7 @@ void launch_freeze(wb200_session& s) {
   s.launches += 1;
 }
 
-void launch_orbit(int kind, int D, int ld, int C, const double* tparam,
+void launch_orbit(int kind, int precision, int D, int ld, int C, const double* tparam,
                   double* theta, double* rho, const double* inv_mass, double* grad,
                   double* logp, double* joint, double step, int num_steps,
                   cudaStream_t stream) {
@@ -399,7 +456,11 @@ void launch_orbit(int kind, int D, int ld, int C, const double* tparam,
   op.step = step; op.num_steps = num_steps;
   LaunchShape shape = shape_for_dim(D);
   const int grid = (C + shape.chains_per_cta - 1) / shape.chains_per_cta;
-  WB200_FOR_TARGET(kind, shape, WB200_LAUNCH_ORBIT);
+  if (precision == 1) {
+    WB200_FOR_TARGET_F32(kind, shape, WB200_LAUNCH_ORBIT_F32);
+  } else {
+    WB200_FOR_TARGET(kind, shape, WB200_LAUNCH_ORBIT);
+  }
   WB200_CUDA(cudaGetLastError());
 }
 

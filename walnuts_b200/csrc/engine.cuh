@@ -91,7 +91,8 @@ struct LaunchShape {
   int T, K, cta, chains_per_cta;
 };
 LaunchShape shape_for_dim(int D);
-void occupancy_for(int kind, const LaunchShape& shape, int ld, int* adapt, int* sample);
+void occupancy_for(int kind, const LaunchShape& shape, int ld, int precision, int* adapt,
+                   int* sample);
 
 // errors.hpp:30-33: the user pressed Ctrl+C (interrupts.hpp)
 struct InterruptException {};
@@ -144,6 +145,7 @@ struct wb200_session {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
   int kind = 0, D = 0, ld = 0;
+  int precision = 0;  // 0: fp64; 1: fp32 integrator state inside transitions (chain kernel)
   size_t N = 0;
   int C = 0;
   uint32_t seed = 0, chain_offset = 0;
@@ -192,7 +194,7 @@ void stream_update(wb200_session& s, const long long* rows_c, long long rows_uni
 void stream_flush(wb200_session& s);
 void tick_abort_inflight(wb200_session& s);
 unsigned long long tick_count(const wb200_session& s);
-void launch_orbit(int kind, int D, int ld, int C, const double* tparam,
+void launch_orbit(int kind, int precision, int D, int ld, int C, const double* tparam,
                   double* theta, double* rho, const double* inv_mass, double* grad,
                   double* logp, double* joint, double step, int num_steps,
                   cudaStream_t stream);

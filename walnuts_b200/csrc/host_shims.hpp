@@ -11,6 +11,9 @@
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fmul_rn(float a, float b) { return a * b; }
 inline double __shfl_xor_sync(unsigned, double v, int) { return v; }
 inline int __shfl_sync(unsigned, int v, int) { return v; }
 inline int __ffs(int x) { return __builtin_ffs(x); }

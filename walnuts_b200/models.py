@@ -31,12 +31,16 @@ class DeviceModel:
     X: Optional[np.ndarray] = None           # logistic: [N][D]
     y: Optional[np.ndarray] = None           # logistic: [N]
     callback: Optional[object] = None        # batch_callback: a BATCH_LOGP_GRAD instance
+    dtype: str = "f64"                       # "f32": fp32 mode (element-wise targets)
     errors: list = field(default_factory=list, repr=False)  # exceptions raised inside it
     _keep: list = field(default_factory=list, repr=False)
 
     def desc(self) -> WalnutModelDesc:
+        if self.dtype not in ("f64", "f32"):
+            raise ValueError("dtype must be 'f64' or 'f32'")
         d = WalnutModelDesc(kind=KINDS[self.kind], D=int(self.num_params), N=0,
-                            data0=None, data1=None)
+                            data0=None, data1=None,
+                            precision=1 if self.dtype == "f32" else 0)
         if self.kind == "diag_gaussian":
             p = np.ascontiguousarray(self.precision, dtype=np.float64)
             if p.shape != (self.num_params,):
@@ -55,28 +59,30 @@ class DeviceModel:
         return d
 
 
-def std_normal(num_params: int) -> DeviceModel:
-    """p(x) = N(0, I) (examples/walnutpie_api.cpp:39-43)."""
-    return DeviceModel("std_normal", num_params)
+def std_normal(num_params: int, dtype: str = "f64") -> DeviceModel:
+    """p(x) = N(0, I) (examples/walnutpie_api.cpp:39-43).  dtype "f32": fp32 mode
+    (include/walnuts_b200.h, WalnutTuning::precision)."""
+    return DeviceModel("std_normal", num_params, dtype=dtype)
 
 
-def diag_gaussian(variances) -> DeviceModel:
+def diag_gaussian(variances, dtype: str = "f64") -> DeviceModel:
     """p(x) = N(0, diag(variances)); generalises ``ill_normal``
     (examples/examples.cpp:20-31)."""
     v = np.asarray(variances, dtype=np.float64)
-    return DeviceModel("diag_gaussian", v.size, precision=1.0 / v)
+    return DeviceModel("diag_gaussian", v.size, precision=1.0 / v, dtype=dtype)
 
 
-def ill_conditioned_gaussian(num_params: int, condition: float = 1e4) -> DeviceModel:
+def ill_conditioned_gaussian(num_params: int, condition: float = 1e4,
+                             dtype: str = "f64") -> DeviceModel:
     """BASELINE config c2: variances log-spaced over `condition`."""
     d = np.arange(num_params, dtype=np.float64)
     var = condition ** (d / max(num_params - 1, 1))
-    return diag_gaussian(var)
+    return diag_gaussian(var, dtype=dtype)
 
 
-def funnel(num_params: int) -> DeviceModel:
+def funnel(num_params: int, dtype: str = "f64") -> DeviceModel:
     """Neal's funnel: x0 ~ N(0, 9), x_i | x0 ~ N(0, exp(x0))."""
-    return DeviceModel("funnel", num_params)
+    return DeviceModel("funnel", num_params, dtype=dtype)
 
 
 def logistic(X, y) -> DeviceModel:
