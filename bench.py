@@ -560,7 +560,8 @@ def one_shot(model, wl, C, rank, n_warm, n_samp, summaries, inits):
     return dt, float(_ffi.last_run_stats()["grad_evals"]), inits.nbytes, d2h, result
 
 
-def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=True):
+def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=True,
+                      dtype="f64"):
     """c2 / c3 on the chain-resident kernel: device-timed sampling steps, the one-shot
     C-ABI calls, the posterior check and (cpu_leg) the reference on the host cores."""
     import torch
@@ -572,10 +573,11 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
     world, rank, local_rank = comm.world, comm.rank, comm.local_rank
     wl = ELEMENTWISE[name]
     Dw, n_warm, burn = wl["D"], wl["warmup_iters"], wl["burn_iters"]
-    alg_bytes = 7 * Dw * 8
+    width = 4 if dtype == "f32" else 8
+    alg_bytes = 7 * Dw * width
     C = args.chains if (args.chains and name == args.workload) else wl["chains"]
-    model = (wb.models.diag_gaussian(variances()) if wl["kind"] == "diag_gaussian"
-             else wb.models.funnel(Dw))
+    model = (wb.models.diag_gaussian(variances(), dtype=dtype)
+             if wl["kind"] == "diag_gaussian" else wb.models.funnel(Dw, dtype=dtype))
     tune = dict(max_trajectory_doublings=wl["max_doublings"],
                 max_step_halvings=wl["max_halvings"])
     sess = wb.Session(model, C, seed=SEED, chain_offset=rank * C, device=local_rank, **tune)
@@ -690,10 +692,13 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
     line = {
         "metric": "grad_evals_per_sec", "value": value, "unit": "grad_evals/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": max_ms / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if dtype == "f64" else
+        "f32 integrator state and element-wise arithmetic, f64 energies / decisions / "
+        "adaptation / stored draws",
         "data": "synthetic",
         "config": {
-            "workload": wl["label"],
+            "workload": wl["label"] if dtype == "f64" else wl["label"].replace("fp64", "fp32 mode"),
             "dims": Dw, "chains_per_gpu": C, "chains_total": C * world,
             "iters_per_step": ips, "adaptive_warmup_iters": n_warm,
             "unstored_sampling_iters_before_timing": burn,
@@ -733,7 +738,8 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
                     "kernel could be; what binds it is in roofline_binding",
         },
         "roofline_binding": binding_roofline(f"{name}_sampling", total_evals / world /
-                                             (max_ms * 1e-3), clock_summary.get("sm_mhz")),
+                                             (max_ms * 1e-3), clock_summary.get("sm_mhz"))
+        if dtype == "f64" else None,
         "clocks": clock_summary,
     }
     if e2e_all:
@@ -782,6 +788,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true",
                     help="skip the CPU leg (scaling sweeps)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="c2 / c3: fp32 mode of the chain-resident kernel")
     ap.add_argument("--no-extra-workloads", action="store_true",
                     help="c2 line only: skip the c3 / c4 / c5 blocks")
     args = ap.parse_args()
@@ -798,12 +806,18 @@ def main():
                                   C4["warmup_ticks"], chains=args.chains, cpu_leg=cpu)
         else:
             line = bench_elementwise(args, comm, args.workload, K, W, args.iters_per_step,
-                                     cpu_leg=cpu)
-        if args.workload == "c2" and not args.no_extra_workloads:
+                                     cpu_leg=cpu, dtype=args.dtype)
+        if args.workload == "c2" and args.dtype == "f64" and not args.no_extra_workloads:
             # the other BASELINE.json configs, short, in the same process
             extra = {}
             extra["c3"] = compact(bench_elementwise(args, comm, "c3", 5, 3, 10, cpu_leg=False,
                                                     all_draws_leg=False))
+            extra["c2_f32"] = compact(bench_elementwise(args, comm, "c2", 5, 3, 10,
+                                                        cpu_leg=False, all_draws_leg=False,
+                                                        dtype="f32"))
+            extra["c3_f32"] = compact(bench_elementwise(args, comm, "c3", 5, 3, 10,
+                                                        cpu_leg=False, all_draws_leg=False,
+                                                        dtype="f32"))
             extra["c4"] = compact(bench_logistic(args, comm, False, 3, 3, 2000, cpu_leg=False))
             extra["c5"] = compact(bench_logistic(args, comm, True, 2, 3, 1200, cpu_leg=False))
             if line is not None:
