@@ -176,6 +176,8 @@ static void run_tick(const EmuTuning& t, int D, const double* tparam, uint32_t s
   p.lp_out = lp; p.depth_out = depth; p.step_out = step_trace; p.im_out = d_im.data();
   p.tparam = tp_.data();
   tp.TH = TH.data(); tp.G = G.data(); tp.LP = &LP; tp.vecs = vecs.data();
+  std::vector<double> stk_logW(kMaxDepth, 0.0), stk_lp(kMaxDepth, 0.0);
+  tp.st_logW = stk_logW.data(); tp.st_lp = stk_lp.data();
   tp.vec_stride = vecs.size(); tp.ts = &ts; tp.active_count = &active;
   Group<1> grp{};
   using Target = TargetT<1, kEmuK>;

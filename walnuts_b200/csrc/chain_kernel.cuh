@@ -141,6 +141,9 @@ struct ChainParams {
   double* scratch;      // [slots][nvec][ld]
   long long scratch_stride;
   unsigned int* ticket;
+  // ticket -> chain: chains in descending order of the work their previous launch took
+  // (longest-processing-time-first, engine.cu); null: identity
+  const int* order;
   const double* tparam; // target parameters (e.g. precision[ld])
 };
 
@@ -1246,7 +1249,7 @@ walnuts_chain_kernel(const ChainParams p) {
       __syncthreads();
     }
     if (chain >= p.C) break;
-    runner.run(chain);
+    runner.run(p.order ? p.order[chain] : chain);
   }
 }
 #endif  // __CUDACC__

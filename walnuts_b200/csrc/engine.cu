@@ -399,9 +399,58 @@ void occupancy_for(int kind, const LaunchShape& shape, int ld, int precision, in
   *sample = occ_sample;
 }
 
+// Longest-processing-time-first hand-out.  A launch ends when its slowest ticket does, and
+// orbit lengths differ by orders of magnitude where the geometry varies (the funnel:
+// 2^1 .. 2^10 leaves of 1 .. 2^8 micro-steps) but are strongly autocorrelated along a
+// chain -- so the gradient evaluations a chain needed in its previous launch predict the
+// next one.  Chains are bucketed by half-octaves of that count (counting sort, one CTA)
+// and tickets walk the buckets from the most expensive down; light chains fill the tail.
+// Scheduling only: every chain computes exactly what it would in any other order.
+constexpr int kOrderBuckets = 96;
+__global__ void __launch_bounds__(1024)
+lpt_order_kernel(const ChainScalars* sc, unsigned long long* prev, int C, int* order) {
+  __shared__ int count[kOrderBuckets], start[kOrderBuckets];
+  for (int b = threadIdx.x; b < kOrderBuckets; b += blockDim.x) count[b] = 0;
+  __syncthreads();
+  auto bucket_of = [](unsigned long long cost) {
+    // descending cost: bucket 0 = the most expensive; two buckets per octave
+    if (cost == 0) return kOrderBuckets - 1;
+    const int lg = 63 - __clzll(static_cast<long long>(cost));
+    const int half = (cost >> (lg > 0 ? lg - 1 : 0)) & 1;
+    const int key = 2 * lg + (lg > 0 ? half : 0);
+    return max(0, kOrderBuckets - 2 - key);
+  };
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&count[bucket_of(sc[c].grad_evals - prev[c])], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < kOrderBuckets; ++b) { start[b] = acc; acc += count[b]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const unsigned long long now = sc[c].grad_evals;
+    order[atomicAdd(&start[bucket_of(now - prev[c])], 1)] = c;
+    prev[c] = now;
+  }
+}
+
 void launch_chains(wb200_session& s, int n_iter, int adapt, bool store) {
   ChainParams p = s.params(n_iter, adapt, store);
   const size_t dyn_smem = chain_dyn_smem(s.shape, s.ld);
+  if (s.C > s.slots) {  // more chains than resident groups: the hand-out order matters
+    if (s.order.count == 0) {
+      s.order.alloc(s.C);
+      s.prev_evals.alloc(s.C);
+      WB200_CUDA(cudaMemsetAsync(s.prev_evals.ptr, 0, s.C * sizeof(unsigned long long),
+                                 s.stream));
+    }
+    lpt_order_kernel<<<1, 1024, 0, s.stream>>>(s.sc.ptr, s.prev_evals.ptr, s.C, s.order.ptr);
+    WB200_CUDA(cudaGetLastError());
+    s.launches += 1;
+    p.order = s.order.ptr;
+  }
   WB200_CUDA(cudaMemsetAsync(s.ticket.ptr, 0, sizeof(unsigned int), s.stream));
   WB200_CUDA(cudaEventRecord(s.ev0, s.stream));
   if (s.precision == 1) {

@@ -167,6 +167,8 @@ struct wb200_session {
   wb200::DeviceBuffer<int> depth_out;
   wb200::DeviceBuffer<wb200::ChainScalars> sc;
   wb200::DeviceBuffer<unsigned int> ticket;
+  wb200::DeviceBuffer<int> order;                      // [C] ticket -> chain (LPT order)
+  wb200::DeviceBuffer<unsigned long long> prev_evals;  // [C] grad_evals before the last launch
   wb200::TickEngine* tick = nullptr;  // lock-step engine (logistic; WB200_ENGINE=tick)
   wb200::StreamState* acc = nullptr;  // streaming summary accumulators (stream.cu)
 

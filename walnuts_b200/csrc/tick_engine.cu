@@ -14,7 +14,7 @@
 namespace wb200 {
 
 struct TickEngine {
-  DeviceBuffer<double> TH, G, LP, vecs;
+  DeviceBuffer<double> TH, G, LP, vecs, st_logW, st_lp;
   DeviceBuffer<TickState> ts;
   DeviceBuffer<int> active;
   int* active_host = nullptr;  // pinned
@@ -344,6 +344,7 @@ static TickParams tick_params(wb200_session& s, int n_iter, int adapt, bool stor
   tp.TH = e.TH.ptr; tp.G = e.G.ptr; tp.LP = e.LP.ptr;
   tp.vecs = e.vecs.ptr; tp.vec_stride = e.vec_stride;
   tp.ts = e.ts.ptr; tp.active_count = e.active.ptr;
+  tp.st_logW = e.st_logW.ptr; tp.st_lp = e.st_lp.ptr;
   tp.chain_begin = 0; tp.chain_count = s.C;
   return tp;
 }
@@ -435,6 +436,8 @@ void tick_create(wb200_session& s, const WalnutModelDesc& model) {
   e.TH.alloc(CL); e.G.alloc(CL); e.LP.alloc(s.C);
   e.vecs.alloc(static_cast<size_t>(e.vec_stride) * s.C);
   e.ts.alloc(s.C);
+  e.st_logW.alloc(static_cast<size_t>(s.C) * kMaxDepth);
+  e.st_lp.alloc(static_cast<size_t>(s.C) * kMaxDepth);
   e.active.alloc(1);
   WB200_CUDA(cudaMallocHost(&e.active_host, sizeof(int)));
   WB200_CUDA(cudaMemsetAsync(e.TH.ptr, 0, CL * 8, s.stream));

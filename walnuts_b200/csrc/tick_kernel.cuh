@@ -51,8 +51,11 @@ struct TickState {
   // macro step
   int rung, n, cur_n, micro_done, reversing, first_rev, with_dots;
   double h, cur_h, Hs, lps, lpn, Hn, dot_new, dot_old;
-  double st_logW[kMaxDepth], st_lp[kMaxDepth];
 };
+// The (logW, lp) stack of finished sub-trees lives in its own arrays (TickParams::st_logW /
+// st_lp, [C][kMaxDepth]) and is accessed in place: inside TickState its dynamic indexing
+// forced every thread's copy of the whole record into local memory (904 B of stack per
+// thread, two thirds of the kernel's DRAM writes were evictions of those copies).
 
 struct TickParams {
   ChainParams cp;      // tuning, seeds, est / sc / draws as in the chain kernel
@@ -62,6 +65,8 @@ struct TickParams {
   double* vecs;        // [C][nvec][ld]
   long long vec_stride;
   TickState* ts;       // [C]
+  double* st_logW;     // [C][kMaxDepth] sub-tree stack: log weights
+  double* st_lp;       // [C][kMaxDepth]                 log densities of the selections
   int* active_count;   // chains that still have transitions to run after this tick
   int chain_begin, chain_count;  // the launch advances chains [begin, begin + count)
 };
@@ -188,6 +193,8 @@ struct TickRunner {
     grp.sync();
     if (st.pc == PC_DONE) return;
     vb = tp.vecs + static_cast<long long>(chain) * tp.vec_stride;
+    double* stk_logW = tp.st_logW + static_cast<long long>(chain) * kMaxDepth;
+    double* stk_lp = tp.st_lp + static_cast<long long>(chain) * kMaxDepth;
     double* th_row = tp.TH + static_cast<long long>(chain) * ld;
     double* g_row = tp.G + static_cast<long long>(chain) * ld;
     unsigned long long evals = 0;
@@ -364,7 +371,10 @@ struct TickRunner {
                 const int s = st.sp - 1;
                 const int sb = TV_ST_BASE + 4 * s;
                 if (uturn(sb + TS_THF, sb + TS_RHOF, st.dir)) { ok = false; break; }
-                merge_decision(false, st.st_logW[s], cur_logW, gchain, sc.iter, st.sctr++,
+                // entry s is read before the barrier inside merge_decision; thread 0
+                // rewrites it (below) only after it
+                const double logW_s = stk_logW[s], lp_s = stk_lp[s];
+                merge_decision(false, logW_s, cur_logW, gchain, sc.iter, st.sctr++,
                                take_new, lw);
                 if (take_new) {
                   if (cur_sel >= 0) {
@@ -374,7 +384,7 @@ struct TickRunner {
                   }
                 } else {
                   cur_sel = s;
-                  cur_lp = st.st_lp[s];
+                  cur_lp = lp_s;
                 }
                 cur_logW = lw;
                 st.sp = s;
@@ -394,8 +404,11 @@ struct TickRunner {
                 copy_vec(sb + TS_SEL, TV_THS);
                 copy_vec(sb + TS_SEL_G, TV_GS);
               }
-              st.st_logW[st.sp] = cur_logW;
-              st.st_lp[st.sp] = cur_lp;
+              if constexpr (T <= 32) grp.sync();  // no lane still reads the old entry
+              if (tid == 0) {
+                stk_logW[st.sp] = cur_logW;
+                stk_lp[st.sp] = cur_lp;
+              }
               st.sp += 1;
             }
           }
