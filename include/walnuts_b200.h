@@ -146,6 +146,31 @@ int walnutpie_sample_device_summary(
     int* final_lengths, double* stepsize_out, double* inv_metric_out, int refresh,
     PRINT_CALLBACK print, WalnutpyError** err);
 
+/* The same call over several GPUs of this process -- walnutpie::walnuts (api.hpp:33-69) is
+ * ONE call that runs every chain and both controllers, and so is this.  Chains are sharded
+ * over `devices` in contiguous blocks of global chain ids (which select the Philox streams:
+ * the chains of a G-GPU run are exactly those of a 1-GPU run), one host thread drives each
+ * device, and the only exchange is the cross-chain summaries, all-reduced with NCCL over
+ * NVLink inside the library (ncclCommInitAll; libnccl.so.2 is loaded at run time): the
+ * warm-up controller's sums and maxima (adapt.hpp:186-224), the sampling controller's lp
+ * moments (sampler.hpp:132-151) and the two phases of the streaming summaries.  inits,
+ * init_inv_metric, final_lengths, stepsize_out, inv_metric_out cover ALL chains, in global
+ * chain order.  With one device no NCCL is needed. */
+int walnutpie_sample_device_multi(
+    const int* devices, int num_devices, const WalnutModelDesc* model, int num_params,
+    const double* inits, size_t num_chains, unsigned int seed, unsigned int id,
+    double init_radius, const double* init_inv_metric, int min_warmup_iter,
+    int max_warmup_iter, int min_sampling_iter, int max_sampling_iter,
+    int max_trajectory_doublings, int max_step_halvings, int min_micro_steps,
+    double max_hamiltonian_error, double step_size_converge_tol, double mass_converge_tol,
+    double rhat_converge_tol, double mass_init_count, double mass_additive_smoothing,
+    double max_macro_steps_target, double step_size_init, double step_accept_rate_target,
+    double step_learning_rate, double step_gradient_decay, double step_sq_gradient_decay,
+    double step_stabilization, double step_learn_rate_decay, int max_lags, double* mean_out,
+    double* var_out, double* rhat_out, double* ess_out, double* mcse_out, int* truncated_out,
+    int* final_lengths, double* stepsize_out, double* inv_metric_out, int refresh,
+    PRINT_CALLBACK print, WalnutpyError** err);
+
 /* walnutpie_sample_cfunc (walnutpy.cpp:134): exported for link compatibility; a
  * host callback cannot feed a device batch, so it fails with a `generic` error that
  * names walnutpie_sample_device and the batched device callback (WalnutModelDesc

@@ -707,10 +707,26 @@ def test_c4_size_gradient_operator_matches_oracle(wb, oracle):
     lp, g, _ = logistic_logp_grad(X, y, theta)
     assert np.all(np.isfinite(lp)) and np.all(np.isfinite(g))
     t = Target("logistic", D, X=X, y=y)
+    worst = 0.0
     for c in (0, 127, 128, 4095, 4096, C - 1):
         olp, og = oracle.logp_grad(t, theta[c])
-        assert abs(lp[c] - olp) <= 1e-5 * abs(olp)
+        worst = max(worst, abs(lp[c] - olp))
+        assert abs(lp[c] - olp) <= 2e-6 * abs(olp)     # |logp| ~ 7e4: 0.14 absolute
         assert np.max(np.abs(g[c] - og)) <= 3e-3 * np.max(np.abs(og))
+    # What the sampler acts on is the energy DIFFERENCE along an orbit (compared with
+    # max_hamiltonian_error = 0.5): the error of logp is a smooth function of theta (bf16
+    # split of theta, fp32 accumulation), so it cancels between nearby points.
+    theta2 = theta.copy()
+    theta2[1::2] = theta[0::2] + 0.02 * np.random.default_rng(5).normal(size=(C // 2, D))
+    lp2, _, _ = logistic_logp_grad(X, y, theta2)
+    worst_diff = 0.0
+    for c in (0, 126, 2048, 4094, C - 2):
+        o0, _ = oracle.logp_grad(t, theta2[c])
+        o1, _ = oracle.logp_grad(t, theta2[c + 1])
+        worst_diff = max(worst_diff, abs((lp2[c + 1] - lp2[c]) - (o1 - o0)))
+    print(f"\nlogp at c4 size: worst |device - fp64| = {worst:.4f}; worst error of the "
+          f"logp difference between points one step apart = {worst_diff:.5f}")
+    assert worst_diff <= 0.02
 
 
 def test_c2_size_posterior_and_sharding(wb):

@@ -202,3 +202,30 @@ def test_cross_rank_streamed_summaries_equal_one_session_with_all_chains(tmp_pat
             np.testing.assert_allclose(r[k], one[k], rtol=1e-8, atol=1e-12, err_msg=k)
         assert r["truncated"] == one["truncated"]
     assert two[0] == two[1]       # identical on every rank
+
+
+def test_multi_device_one_shot_call_equals_the_single_device_call(wb, oracle):
+    """walnutpie_sample_device_multi (one call, one host thread per GPU, controllers and
+    summaries all-reduced by NCCL inside the library) against walnutpie_sample_device_summary
+    on one device: same stop iterations, same per-chain step sizes and metrics, summaries
+    equal to 1e-8 -- with early stopping enabled, so the all-reduced controllers decide.
+    On a single-GPU box the multi-device call runs with one device (no NCCL)."""
+    import torch
+    D, C = 16, 48
+    model = wb.models.diag_gaussian(np.linspace(0.3, 5.0, D))
+    kw = dict(min_warmup_iter=20, max_warmup_iter=300, min_sampling_iter=40,
+              max_sampling_iter=300, mass_converge_tol=0.9, step_size_converge_tol=0.35,
+              rhat_converge_tol=1.01)
+    one = wb.walnuts_device_summary(model, num_chains=C, seed=5, **kw)
+    ndev = min(torch.cuda.device_count(), 2)
+    many = wb.walnuts_device_summary(model, num_chains=C, seed=5, devices=list(range(ndev)),
+                                     **kw)
+    print(f"\n{ndev} device(s): sampling stopped at {many['sampling_iters']} iterations, "
+          f"min ESS {many['ess'].min():.1f}")
+    assert many["sampling_iters"] == one["sampling_iters"]
+    np.testing.assert_array_equal(many["stepsize"], one["stepsize"])
+    np.testing.assert_array_equal(many["inv_metric"], one["inv_metric"])
+    for k in ("mean", "variance", "r_hat", "ess", "mcse"):
+        np.testing.assert_allclose(many[k], one[k], rtol=1e-8, atol=1e-12, err_msg=k)
+    with pytest.raises(ValueError, match="more devices than chains"):
+        wb.walnuts_device_summary(model, num_chains=1, devices=[0, 0], **kw)

@@ -205,6 +205,11 @@ _ffi_sample_device_summary.argtypes = [
     nullable_double_array, nullable_double_array, nullable_int_array,
 ] + _common_sampling_argtypes[29:]
 
+_ffi_sample_device_multi = erroring(_lib.walnutpie_sample_device_multi)
+_ffi_sample_device_multi.argtypes = [
+    int_array, ctypes.c_int,  # devices
+] + _ffi_sample_device_summary.__wrapped__.argtypes
+
 _ffi_sample_cfunc = erroring(_lib.walnutpie_sample_cfunc)
 _ffi_sample_cfunc.argtypes = [
     logp_cfunc_type, ctypes.c_void_p, ctypes.c_int, nullable_double_array,
@@ -378,6 +383,7 @@ EXPORTED_SYMBOLS = [
     "wb200_session_warmup_deviation", "wb200_session_lp_moments",
     "wb200_session_lp_moments_centered", "wb200_session_logp_exceptions",
     "walnutpie_sample_bridgestan", "walnutpie_sample_device_summary",
+    "walnutpie_sample_device_multi",
     "wb200_session_stream_begin",
     "wb200_session_stream_phase1", "wb200_session_stream_phase2", "wb200_stream_finish",
     "wb200_session_stream_summary", "wb200_session_stream_counts",

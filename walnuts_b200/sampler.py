@@ -173,13 +173,16 @@ def walnuts_device_summary(logp: DeviceModel, *, num_chains: int = 4, seed: Opti
                            id: int = 1, inits: Optional[np.ndarray] = None,
                            init_radius: float = 2.0,
                            init_inv_metric: Optional[np.ndarray] = None, max_lags: int = 32,
-                           refresh: int = 0, **tuning):
+                           refresh: int = 0, devices=None, **tuning):
     """``walnuts_device`` for runs whose draws are too many to keep: the same sampler run
     (``walnutpie_sample_device_summary``), returning the posterior summaries computed on
     the device by streaming accumulators -- ``mean``, ``variance``, ``r_hat``, ``ess``,
     ``mcse`` per parameter (summary.hpp:371-405,594-769), ``truncated`` flags, per-chain
     ``stepsize`` / ``inv_metric`` and the iteration counts.  ``tuning`` takes the tuning
-    keywords of ``walnuts_device`` (reference defaults)."""
+    keywords of ``walnuts_device`` (reference defaults).  ``devices``: a list of CUDA device
+    ordinals -- the chains are sharded over them inside the one call
+    (``walnutpie_sample_device_multi``: one host thread per GPU, controllers and summaries
+    all-reduced with NCCL); the results do not depend on the number of devices."""
     if not isinstance(logp, DeviceModel):
         raise TypeError("walnuts_b200 samples device models only")
     D = logp.num_params
@@ -199,8 +202,13 @@ def walnuts_device_summary(logp: DeviceModel, *, num_chains: int = 4, seed: Opti
     stepsize = np.zeros(num_chains)
     inv_metric = np.zeros((num_chains, D))
     desc = logp.desc()
+    if devices is not None:
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        call = lambda *args: _ffi._ffi_sample_device_multi(dev, len(dev), *args)  # noqa: E731
+    else:
+        call = _ffi._ffi_sample_device_summary
     with _reraise_callback_errors(logp):
-        _ffi._ffi_sample_device_summary(
+        call(
             ctypes.byref(desc), D, inits, num_chains, seed, id, init_radius, init_inv_metric,
             t.min_warmup_iter, t.max_warmup_iter, t.min_sampling_iter, t.max_sampling_iter,
             t.max_trajectory_doublings, t.max_step_halvings, t.min_micro_steps,
@@ -213,7 +221,8 @@ def walnuts_device_summary(logp: DeviceModel, *, num_chains: int = 4, seed: Opti
             out["mcse"], cut, lengths, stepsize, inv_metric, refresh, _ffi.print_callback)
     # final_lengths reports SAVED warm-up draws (0 here); the iterations run are in the stats
     out.update(truncated=cut, stepsize=stepsize, inv_metric=inv_metric,
-               warmup_iters=_ffi.last_run_stats()["warmup_iters"],
+               warmup_iters=(_ffi.last_run_stats()["warmup_iters"] if devices is None
+                             else None),
                sampling_iters=int(lengths[num_chains]))
     return out
 
