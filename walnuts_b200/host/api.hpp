@@ -13,8 +13,14 @@
 //   chain handler    on_warmup(position, lp, step_size, diag_inv_mass)
 //                    on_warmup_complete(step_size, diag_inv_mass)
 //                    on_sample(position, lp)
+//                    on_logp_exception(position, exception) noexcept   [optional]
 //   global handler   on_r_hat(r_hat)
 //   interrupt        throw_if_interrupted()
+//
+// on_logp_exception (concepts.hpp:196-201, util.hpp:336-346): a batched device density
+// (model kind 4) that returns non-zero inside a transition gives every chain of that
+// evaluation logp = -inf and a zero gradient, and sampling goes on; each chain handler
+// that has the method is told once per failed evaluation, with the chain's latest draw.
 //
 // The batch runs in blocks of WarmupConfig::publish_stride iterations; after each block
 // the handlers of every chain receive that block's iterations in order, then the
@@ -26,6 +32,8 @@
 #include <cstddef>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/walnuts_b200.h"
@@ -94,6 +102,15 @@ inline WalnutTuning tuning_from(const WalnutsConfig& c) {
   t.min_micro_steps = static_cast<int>(s.min_micro_steps());
   return t;
 }
+
+// ErrorCallback is optional here (the built-in device densities cannot throw)
+template <class H, class = void>
+struct has_on_logp_exception : std::false_type {};
+template <class H>
+struct has_on_logp_exception<
+    H, std::void_t<decltype(std::declval<H&>().on_logp_exception(
+           std::declval<const Vector&>(), std::declval<const std::exception&>()))>>
+    : std::true_type {};
 
 inline std::vector<double> flatten(const std::vector<Vector>& rows, std::size_t dims) {
   std::vector<double> out(rows.size() * dims);
@@ -167,6 +184,25 @@ inline void walnuts(std::size_t seed, std::vector<H>& chain_handlers, GH& global
     }
   };
 
+  // failed evaluations of a batched density since the last call (util.hpp:336-346)
+  unsigned long long exceptions_seen = 0;
+  auto report_exceptions = [&](long long last_row) {
+    unsigned long long total = 0;
+    if (wb200_session_logp_exceptions(s, &total) != 0 || total == exceptions_seen) return;
+    if constexpr (detail::has_on_logp_exception<H>::value) {
+      const std::runtime_error exn("logp failed: the batched density returned non-zero");
+      draws.resize(C * D);
+      detail::check(wb200_session_get_draws(s, last_row, 1, draws.data(), &e), e);
+      for (unsigned long long k = exceptions_seen; k < total; ++k) {
+        for (std::size_t m = 0; m < C; ++m) {
+          position.assign(draws.begin() + m * D, draws.begin() + (m + 1) * D);
+          chain_handlers[m].on_logp_exception(position, exn);
+        }
+      }
+    }
+    exceptions_seen = total;
+  };
+
   // ---- detail::adapt (adapt.hpp:173-259): blocks of publish_stride, controller between
   int warm_done = 0;
   while (warm_done < max_warm) {
@@ -174,6 +210,7 @@ inline void walnuts(std::size_t seed, std::vector<H>& chain_handlers, GH& global
     detail::check(wb200_session_warmup(s, n, 1, &e), e);
     publish(warm_done, n, true);
     warm_done += n;
+    report_exceptions(warm_done - 1);
     interrupt_callback.throw_if_interrupted();  // adapt.hpp:227
     if (warm_done >= tuning.min_warmup_iter && warm_done < max_warm) {
       double deviation[2];
@@ -203,10 +240,13 @@ inline void walnuts(std::size_t seed, std::vector<H>& chain_handlers, GH& global
     detail::check(wb200_session_sample(s, n, 1, &e), e);
     publish(static_cast<long long>(warm_done) + samp_done, n, false);
     samp_done += n;
+    report_exceptions(static_cast<long long>(warm_done) + samp_done - 1);
     interrupt_callback.throw_if_interrupted();  // sampler.hpp:154
     if (samp_done >= tuning.min_sampling_iter && samp_done < max_samp) {
-      double m4[4];
-      detail::check(wb200_session_lp_moments(s, m4, &e), e);
+      // util.hpp:401-404 is a two-pass variance: the mean of the chain means first
+      double m0[4], m4[4];
+      detail::check(wb200_session_lp_moments(s, m0, &e), e);
+      detail::check(wb200_session_lp_moments_centered(s, m0[0] / m0[3], m4, &e), e);
       const double M = m4[3];
       const double var_of_means = (m4[1] - m4[0] * m4[0] / M) / (M - 1.0);
       const double mean_of_vars = m4[2] / M;
