@@ -582,7 +582,10 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
                 max_step_halvings=wl["max_halvings"])
     sess = wb.Session(model, C, seed=SEED, chain_offset=rank * C, device=local_rank, **tune)
     sess.init(init_radius=wl["init_radius"])
-    sess.reserve((W + K) * ips)
+    # rows of the quota steps, then room for the free-running steps (ragged: chains with
+    # short orbits complete several times the average number of transitions)
+    free_factor = 8 if wl["kind"] == "funnel" else 2
+    sess.reserve((W + K) * ips * (1 + free_factor))
     # ---- untimed set-up: adaptive warm-up (device time reported separately)
     sess.sync()
     c0 = sess.counters()
@@ -623,6 +626,41 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
     first = W * ips
     local = sess.summary(first, K * ips)
     draws_last = sess.draws(first + K * ips - 1, 1)[:, 0]       # one draw per chain
+
+    # ---- free-running steps: the same mean work per chain and step as above, handed out
+    # as a budget of gradient evaluations (wb200_session_sample_ticks) instead of an
+    # iteration count, so no launch waits for the chain with the longest orbits; every
+    # chain stores its draws in its own rows (ragged counts per chain)
+    budget = max(1, int(round(evals / (C * K))))
+    for _ in range(W):
+        sess.sample_ticks(budget)
+    sess.sync()
+    f0 = sess.counters()
+    comm.barrier()
+    sess.timer_start()
+    for _ in range(K):
+        sess.sample_ticks(budget)
+    free_ms = sess.timer_stop_ms()
+    torch.cuda.synchronize()
+    comm.barrier()
+    f1 = sess.counters()
+    free_counts = sess.chain_rows() - (W + K) * ips
+    free_summary = sess.summary_ragged((W + K) * ips)
+    (free_max_ms,) = comm.reduce([free_ms], "max")
+    (free_evals,) = comm.reduce([float(f1["grad_evals"] - f0["grad_evals"])], "sum")
+    (free_min_ess,) = comm.reduce([float(np.min(free_summary["ess"]))], "sum")
+    free_running = {
+        "value": free_evals / (free_max_ms * 1e-3), "unit": "grad_evals/s",
+        "ms_per_step": free_max_ms / K, "eval_budget_per_chain_and_step": budget,
+        "gpu_launches": int(f1["kernel_launches"] - f0["kernel_launches"]),
+        "draws_per_chain_min_max": [int(free_counts.min()), int(free_counts.max())],
+        "min_ess": free_min_ess, "max_r_hat": float(np.max(free_summary["r_hat"])),
+        "roofline_frac": None,
+        "what": "K steps of wb200_session_sample_ticks: every chain gets the same number of "
+                "gradient evaluations per launch and completes the transitions that fit "
+                "(ragged draw counts, like the reference's per-thread chains, "
+                "sampler.hpp:79-94); summaries over every chain's own rows, warm-up "
+                "steps included"}
     sess.close()
     comm.barrier()
     # cross-rank moments of the timed draws (chains independent: pooled over ranks)
@@ -688,6 +726,7 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
         return None
 
     hbm_peak, peak_src = measured_peaks()
+    free_running["roofline_frac"] = (free_running["value"] / world) * alg_bytes / 1e9 / hbm_peak
     achieved = (total_evals / world) * alg_bytes / (max_ms * 1e-3) / 1e9
     line = {
         "metric": "grad_evals_per_sec", "value": value, "unit": "grad_evals/s",
@@ -717,6 +756,7 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
         "warmup_phase": {"iters": n_warm, "ms": warm_ms,
                          "grad_evals_per_sec": warm_evals / (warm_ms * 1e-3)},
         "e2e": e2e,
+        "free_running": free_running,
         "gpu_launches": int(launches),
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -771,7 +811,8 @@ def compact(line):
     keep = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling",
             "dtype", "config", "min_ess", "min_ess_per_sec", "max_r_hat", "posterior_check",
             "summary_phase", "active_lane_fraction", "grad_evals_per_transition",
-            "warmup_phase", "roofline", "roofline_binding", "e2e", "gpu_launches", "clocks")
+            "warmup_phase", "roofline", "roofline_binding", "e2e", "free_running",
+            "gpu_launches", "clocks")
     return {k: line[k] for k in keep if k in line}
 
 

@@ -264,10 +264,18 @@ int wb200_session_warmup(wb200_session* s, int n_iter, int store,
 int wb200_session_freeze(wb200_session* s, WalnutpyError** err);
 int wb200_session_sample(wb200_session* s, int n_iter, int store,
                          WalnutpyError** err);
-/* Lock-step sessions only: exactly n_ticks ticks (one batched gradient each); every
- * chain completes as many transitions as fit, so draw counts become ragged, as in the
- * reference's adaptive runs.  wb200_session_chain_rows returns the rows stored per
- * chain; wb200_session_summary summarises rows [first, rows_c) of every chain. */
+/* Free-running sampling: the reference's chains are threads that run at their own pace
+ * until the controller stops them (sampler.hpp:79-94), so draw counts are ragged.  The
+ * device analogue of equal time is equal work -- n_ticks gradient evaluations per chain:
+ *   lock-step sessions     exactly n_ticks ticks (one batched gradient each); transitions
+ *                          in flight carry over to the next call;
+ *   chain-resident sessions  every chain completes the transitions that fit into n_ticks
+ *                          evaluations (the one that exhausts the budget is finished and
+ *                          its excess comes off the chain's next budget).
+ * No launch waits for the chain with the longest orbits.  wb200_session_chain_rows returns
+ * the rows stored per chain; wb200_session_summary summarises rows [first, rows_c) of
+ * every chain.  Chain c's rows are the first rows_c draws of the very chain a fixed-length
+ * run produces (the Philox streams are keyed by chain and iteration). */
 int wb200_session_sample_ticks(wb200_session* s, int n_ticks, int store,
                                WalnutpyError** err);
 /* The same for the adaptive phase (AdaptiveWalnuts::operator(), adaptive_walnuts.hpp:234):
@@ -275,6 +283,17 @@ int wb200_session_sample_ticks(wb200_session* s, int n_ticks, int store,
  * chains.  wb200_session_freeze abandons the transitions still in flight. */
 int wb200_session_warmup_ticks(wb200_session* s, int n_ticks, int store,
                                WalnutpyError** err);
+/* Chain-resident sessions: the free-running launch with the phase's iteration limit --
+ * sampling = 0 warm-up / 1 sampling; no chain goes beyond iter_cap iterations of the phase
+ * in total (<= 0: no limit), as each reference chain stops at max_iter (adapt.hpp:116,
+ * sampler.hpp:82).  wb200_session_iter_stats returns stats4 = {min, max, sum} over the
+ * chains of the phase's per-chain iteration counts -- what the reference's controllers
+ * read from the chains' snapshots (adapt.hpp:196-203,219; sampler.hpp:134-141,149) -- and
+ * the gradient evaluations of all chains since initialisation. */
+int wb200_session_run_evals(wb200_session* s, int sampling, long long eval_budget,
+                            long long iter_cap, int store, WalnutpyError** err);
+int wb200_session_iter_stats(wb200_session* s, int sampling, long long* stats4,
+                             WalnutpyError** err);
 int wb200_session_chain_rows(wb200_session* s, long long* rows, WalnutpyError** err);
 int wb200_session_summary(wb200_session* s, long long first, double* rhat, double* ess,
                           double* mcse, double* mean, double* var, WalnutpyError** err);

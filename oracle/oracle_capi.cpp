@@ -378,8 +378,8 @@ void logp_grad_f32(const OracleTarget* t, const std::vector<float>& x, double& l
     const double q = 0.5 * ev * static_cast<double>(ss);
     const float evf = static_cast<float>(ev);
     for (size_t i = 1; i < D; ++i) g[i] = -(x[i] * evf);
-    g[0] = static_cast<float>(-v / 9.0 - hd + q);
-    lp = static_cast<double>(static_cast<float>(-(v * v) / 18.0 - hd * v - q));
+    g[0] = static_cast<float>(-(v * oracle::Funnel::kInv9) - hd + q);
+    lp = static_cast<double>(static_cast<float>(-((v * v) * oracle::Funnel::kInv18) - hd * v - q));
   } else {
     throw std::invalid_argument("fp32 mode covers the element-wise targets (kinds 0-2)");
   }

@@ -76,7 +76,11 @@ struct DiagGaussian {
 
 // Neal's funnel: v = x_0 ~ N(0, 3^2); x_i | v ~ N(0, e^v), i >= 1
 // logp = -v^2/18 - (D-1)/2 v - 1/2 e^{-v} sum_i x_i^2
+// The prior's constants enter as the rounded reciprocals 1/18 and 1/9 (one multiplication
+// each): this target is specified here, not in the reference, and an fp64 division is
+// 30 instructions per gradient on the device for the same density to 1 ulp.
 struct Funnel {
+  static constexpr double kInv18 = 1.0 / 18.0, kInv9 = 1.0 / 9.0;
   void operator()(const Vec& x, double& lp, Vec& g) const {
     g.resize(x.size());
     eval(x.data(), x.size(), lp, g.data());
@@ -91,8 +95,8 @@ struct Funnel {
     }
     const double half_dm1 = 0.5 * static_cast<double>(D - 1);
     const double q = 0.5 * ev * ss;
-    lp = -(v * v) / 18.0 - half_dm1 * v - q;
-    g[0] = -v / 9.0 - half_dm1 + q;
+    lp = -((v * v) * kInv18) - half_dm1 * v - q;
+    g[0] = -(v * kInv9) - half_dm1 + q;
   }
 };
 

@@ -34,12 +34,15 @@ def build(exact_arith: bool = False):
 
 
 def run_chain(lib, kind, D, tparam, cfg, seed, chain, th0, m0, step0, nw, ns, engine="chain",
-              warm_ticks=-1, samp_ticks=-1):
+              warm_ticks=-1, samp_ticks=-1, eval_budget=0):
     """cfg is an oracle.binding.OracleConfig; returns the device-code results.
     engine: "chain" (chain_kernel.cuh) or "tick" (tick_kernel.cuh).
     engine "tick" with warm_ticks / samp_ticks >= 0: that phase runs free for exactly
     that many ticks (nw + ns is then the draw capacity); result["rows"] = (rows after
-    warm-up, rows at the end)."""
+    warm-up, rows at the end).
+    engine "chain" with eval_budget > 0: both phases as free-running launches of that many
+    gradient evaluations each (ChainParams::eval_budget) until nw / ns iterations are done;
+    result["launches"] counts them."""
     t = EmuTuning(cfg.max_trajectory_doublings, cfg.max_step_halvings, cfg.min_micro_steps,
                   cfg.max_hamiltonian_error, cfg.mass_init_count,
                   cfg.max_macro_steps_target, cfg.step_accept_rate_target,
@@ -66,6 +69,19 @@ def run_chain(lib, kind, D, tparam, cfg, seed, chain, th0, m0, step0, nw, ns, en
             C.c_uint32(chain), dp(th0), dp(m0), C.c_double(step0), nw, ns, warm_ticks,
             samp_ticks, dp(draws), dp(lp), depth.ctypes.data_as(C.POINTER(C.c_int)), dp(st),
             dp(im), dp(imo), C.byref(so), C.byref(mm), C.byref(ev), rows)
+    elif eval_budget > 0:
+        assert engine == "chain"
+        launches = C.c_int(0)
+        rc = lib.emu_run_chain_free(
+            KIND[kind], D, None if tp is None else dp(tp), C.byref(t), C.c_uint32(seed),
+            C.c_uint32(chain), dp(th0), dp(m0), C.c_double(step0), nw, ns,
+            C.c_longlong(eval_budget), dp(draws), dp(lp),
+            depth.ctypes.data_as(C.POINTER(C.c_int)), dp(st), dp(im), dp(imo),
+            C.byref(so), C.byref(mm), C.byref(ev), C.byref(launches))
+        if rc == 0:
+            return dict(rows=(nw, nw + ns), draws=draws, lp=lp, depth=depth, step_trace=st,
+                        warmup_inv_mass=im[:nw], inv_mass=imo, step=so.value,
+                        min_micro=mm.value, grad_evals=ev.value, launches=launches.value)
     else:
         fn = lib.emu_run_chain if engine == "chain" else lib.emu_run_chain_tick
         rc = fn(KIND[kind], D, None if tp is None else dp(tp), C.byref(t),

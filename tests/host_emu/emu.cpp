@@ -25,7 +25,10 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
                 uint32_t chain, const double* theta0, const double* mass0, double step0,
                 int n_warmup, int n_sampling, double* draws, double* lp, int* depth,
                 double* step_trace, double* im_trace, double* inv_mass_out,
-                double* step_out, int* min_micro_out, unsigned long long* evals) {
+                double* step_out, int* min_micro_out, unsigned long long* evals,
+                long long budget = 0, int* launches = nullptr) {
+  // budget > 0: both phases as free-running launches of `budget` gradient evaluations
+  // (ChainParams::eval_budget) until the phase's iteration count is reached
   const int ld = 2 * kEmuK;  // rows padded to the group's element slots
   const int total = n_warmup + n_sampling;
   std::vector<double> theta(ld, 0.0), inv_mass(ld, 0.0), est(4 * ld, 0.0), tp(ld, 0.0);
@@ -64,8 +67,14 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   ChainScalars sc_shared{};  // stands in for the per-chain record in shared memory
   DecisionCache decision_cache{};
   AdamQueue adam_queue{};
+  RunLimits run_limits{};
   std::vector<double> chain_smem(static_cast<size_t>(chain_smem_doubles(ld)), 0.0);
   using Target = TargetT<1, kEmuK>;
+  long long rows = 0;
+  int n_launch = 0;
+  if (budget > 0) {
+    p.eval_budget = budget; p.rows = &rows;
+  }
   // warm-up launch
   p.n_iter = n_warmup; p.adapt = 1; p.draw_base = 0;
   {
@@ -73,7 +82,13 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
                                            chain_smem.data());
     r.dc = &decision_cache;
     r.aq = &adam_queue;
-    if (n_warmup > 0) r.run(0);
+    r.rl = &run_limits;
+    if (budget > 0) {
+      p.n_iter = 1; p.free_cap = 0x7fffffff; p.iter_cap = n_warmup;
+      while (static_cast<int>(sc.warm_iter) < n_warmup) { r.advance(0); ++n_launch; }
+    } else if (n_warmup > 0) {
+      r.advance(0);
+    }
   }
   // freeze_kernel
   for (int i = 0; i < ld; ++i) {
@@ -89,8 +104,16 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
     ChainRunner<Target, 1, kEmuK, false> r(p, grp, scratch.data(), sc_shared,
                                             chain_smem.data());
     r.dc = &decision_cache;
-    if (n_sampling > 0) r.run(0);
+    r.rl = &run_limits;
+    if (budget > 0) {
+      p.n_iter = 1; p.free_cap = 0x7fffffff; p.iter_cap = n_sampling;
+      sc.eval_debt = 0;  // freeze_kernel
+      while (static_cast<int>(sc.lp_n) < n_sampling) { r.advance(0); ++n_launch; }
+    } else if (n_sampling > 0) {
+      r.advance(0);
+    }
   }
+  if (launches) *launches = n_launch;
   for (int i = 0; i < total; ++i) {
     std::memcpy(draws + static_cast<size_t>(i) * D, d_draws.data() + static_cast<size_t>(i) * ld, D * 8);
     if (i < n_warmup && im_trace) {
@@ -118,6 +141,34 @@ extern "C" int emu_run_chain(int kind, int D, const double* tparam, const EmuTun
     case 2: run<FunnelTarget>(*t, D, tparam, seed, chain, theta0, mass0, step0, n_warmup,
                               n_sampling, draws, lp, depth, step_trace, im_trace,
                               inv_mass_out, step_out, min_micro_out, evals); break;
+    default: return -2;
+  }
+  return 0;
+}
+
+// the same chain advanced by free-running launches of `budget` evaluations each
+extern "C" int emu_run_chain_free(int kind, int D, const double* tparam, const EmuTuning* t,
+                                  uint32_t seed, uint32_t chain, const double* theta0,
+                                  const double* mass0, double step0, int n_warmup,
+                                  int n_sampling, long long budget, double* draws,
+                                  double* lp, int* depth, double* step_trace,
+                                  double* im_trace, double* inv_mass_out, double* step_out,
+                                  int* min_micro_out, unsigned long long* evals,
+                                  int* launches) {
+  if (D > 2 * kEmuK || t->max_depth > kMaxDepth || budget <= 0) return -1;
+  switch (kind) {
+    case 0: run<StdNormalTarget>(*t, D, tparam, seed, chain, theta0, mass0, step0, n_warmup,
+                                 n_sampling, draws, lp, depth, step_trace, im_trace,
+                                 inv_mass_out, step_out, min_micro_out, evals, budget,
+                                 launches); break;
+    case 1: run<DiagGaussianTarget>(*t, D, tparam, seed, chain, theta0, mass0, step0,
+                                    n_warmup, n_sampling, draws, lp, depth, step_trace,
+                                    im_trace, inv_mass_out, step_out, min_micro_out, evals,
+                                    budget, launches); break;
+    case 2: run<FunnelTarget>(*t, D, tparam, seed, chain, theta0, mass0, step0, n_warmup,
+                              n_sampling, draws, lp, depth, step_trace, im_trace,
+                              inv_mass_out, step_out, min_micro_out, evals, budget,
+                              launches); break;
     default: return -2;
   }
   return 0;

@@ -157,11 +157,14 @@ def test_sampling_controller_statistics_equal_the_reference_math(wb, oracle, mon
                                oracle.r_hat([draws[c] for c in range(C)]), rtol=1e-9)
 
 
-def test_one_shot_stop_decisions_equal_a_replay_of_the_controllers(wb, oracle):
-    """walnutpie_sample_device with min < max: the iteration at which the library stops
-    warm-up and sampling equals the first publish_stride boundary at which the reference's
-    tests (adapt.hpp:218-219, sampler.hpp:147-148) pass on the same chains, replayed block
-    by block on a Session with the oracle evaluating the statistics."""
+def test_one_shot_stop_decisions_equal_a_replay_of_the_controllers(wb, oracle, monkeypatch):
+    """walnutpie_sample_device with min < max and blocks of equal iteration counts
+    (WB200_BLOCKS=uniform; the free-running default is replayed in test_gpu_ragged.py):
+    the iteration at which the library stops warm-up and sampling equals the first
+    publish_stride boundary at which the reference's tests (adapt.hpp:218-219,
+    sampler.hpp:147-148) pass on the same chains, replayed block by block on a Session
+    with the oracle evaluating the statistics."""
+    monkeypatch.setenv("WB200_BLOCKS", "uniform")
     D, C = 16, 32
     model, _ = make(wb, "diag_gaussian", D)
     kw = dict(min_warmup_iter=20, max_warmup_iter=400, min_sampling_iter=20,

@@ -204,13 +204,16 @@ def test_cross_rank_streamed_summaries_equal_one_session_with_all_chains(tmp_pat
     assert two[0] == two[1]       # identical on every rank
 
 
-def test_multi_device_one_shot_call_equals_the_single_device_call(wb, oracle):
+def test_multi_device_one_shot_call_equals_the_single_device_call(wb, oracle, monkeypatch):
     """walnutpie_sample_device_multi (one call, one host thread per GPU, controllers and
     summaries all-reduced by NCCL inside the library) against walnutpie_sample_device_summary
     on one device: same stop iterations, same per-chain step sizes and metrics, summaries
     equal to 1e-8 -- with early stopping enabled, so the all-reduced controllers decide.
-    On a single-GPU box the multi-device call runs with one device (no NCCL)."""
+    On a single-GPU box the multi-device call runs with one device (no NCCL).  The
+    multi-device call advances all chains by blocks of equal iteration counts; the
+    single-device call is put in the same mode (its default is free-running chains)."""
     import torch
+    monkeypatch.setenv("WB200_BLOCKS", "uniform")
     D, C = 16, 48
     model = wb.models.diag_gaussian(np.linspace(0.3, 5.0, D))
     kw = dict(min_warmup_iter=20, max_warmup_iter=300, min_sampling_iter=40,

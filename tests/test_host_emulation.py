@@ -75,6 +75,34 @@ EDGE_CASES = [
 ]
 
 
+@pytest.mark.parametrize("budget", [1, 37, 400])
+@pytest.mark.parametrize("kind,D,over,step0,nw,ns", CASES[:5])
+def test_chain_engine_free_running_launches_equal_oracle_bitwise(emu, oracle, budget, kind, D,
+                                                                 over, step0, nw, ns):
+    """ChainParams::eval_budget: a chain advanced by launches of `budget` gradient
+    evaluations each -- the transition that exhausts a budget is finished, its excess is
+    taken off the next budget -- is the very chain of the fixed-length run (the reference's
+    threads, adapt.hpp:110-129 / sampler.hpp:79-94, stop between iterations, too), and the
+    long-run cost of a launch is the budget."""
+    rng = np.random.default_rng(100 * D + nw)
+    prec = rng.uniform(0.05, 20.0, D) if kind == "diag_gaussian" else None
+    target = Target(kind, D, prec=prec)
+    cfg = default_config(**over)
+    th0 = rng.normal(size=D)
+    m0 = rng.uniform(0.3, 3.0, D)
+    e = host_emu.run_chain(emu, kind, D, prec, cfg, 4242, 3, th0, m0, step0, nw, ns,
+                           eval_budget=budget)
+    o = oracle.run_chain(target, cfg, 4242, 3, th0, m0, step0, nw, ns, rng_policy=1)
+    np.testing.assert_array_equal(e["draws"], np.concatenate([o["warmup_draws"], o["draws"]]))
+    np.testing.assert_array_equal(e["lp"], np.concatenate([o["warmup_lp"], o["lp"]]))
+    np.testing.assert_array_equal(e["inv_mass"], o["inv_mass"])
+    assert e["step"] == o["step"] and e["grad_evals"] == o["grad_evals"]
+    # debts carry over: launches * budget brackets the work (each phase ends inside a launch)
+    assert (e["launches"] - 2) * budget <= e["grad_evals"]
+    if budget == 1:  # at least one launch per iteration, idle launches pay the debts off
+        assert e["launches"] >= nw + ns
+
+
 @pytest.mark.parametrize("engine", ["chain", "tick"])
 @pytest.mark.parametrize("kind,D,scale,step0", EDGE_CASES)
 def test_extreme_inputs_take_the_reference_decisions(emu, oracle, engine, kind, D, scale, step0):

@@ -260,6 +260,10 @@ session_sample_ticks = _sess("wb200_session_sample_ticks",
                              [session_p, ctypes.c_int, ctypes.c_int])
 session_warmup_ticks = _sess("wb200_session_warmup_ticks",
                              [session_p, ctypes.c_int, ctypes.c_int])
+session_run_evals = _sess("wb200_session_run_evals", [
+    session_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int])
+session_iter_stats = _sess("wb200_session_iter_stats", [
+    session_p, ctypes.c_int, ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")])
 session_chain_rows = _sess("wb200_session_chain_rows", [
     session_p, ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")])
 session_rhat_moments = _sess("wb200_session_rhat_moments", [
@@ -379,6 +383,7 @@ EXPORTED_SYMBOLS = [
     "wb200_session_reserve_draws", "wb200_session_warmup", "wb200_session_freeze",
     "wb200_session_sample", "wb200_session_sync", "wb200_session_sample_ticks",
     "wb200_session_warmup_ticks",
+    "wb200_session_run_evals", "wb200_session_iter_stats",
     "wb200_session_chain_rows", "wb200_session_summary", "wb200_session_rhat_moments", "wb200_session_warmup_sums",
     "wb200_session_warmup_deviation", "wb200_session_lp_moments",
     "wb200_session_lp_moments_centered", "wb200_session_logp_exceptions",

@@ -262,12 +262,17 @@ int wb200_session_reserve_draws(wb200_session* s, long long capacity, int trace,
     }
     s->draw_cap = capacity;
     s->rows_written = 0;
+    if (!s->tick) s->ragged = false;
   });
 }
 
 static void check_room(wb200_session* s, int n_iter, int store) {
   if (!s->initialised) throw std::runtime_error("session is not initialised");
   if (n_iter < 0) throw std::invalid_argument("n_iter must be non-negative");
+  if (store && s->ragged && !s->tick) {
+    throw std::runtime_error("chains hold different numbers of rows after a free-running "
+                             "phase: store further draws with free-running launches");
+  }
   if (store && s->rows_written + n_iter > s->draw_cap) {
     throw std::runtime_error("draw buffer too small: reserve more capacity");
   }
@@ -285,16 +290,76 @@ int wb200_session_warmup(wb200_session* s, int n_iter, int store, WalnutpyError*
   });
 }
 
+// Free-running launch of the chain-resident engine: every chain gets `budget` gradient
+// evaluations and completes the transitions that fit (chain_kernel.cuh, eval_budget);
+// draws go to per-chain row counters.
+static void chain_free_run(wb200_session* s, long long budget, long long iter_cap, int adapt,
+                           bool store) {
+  constexpr int kNoIterLimit = 0x7fffffff;
+  if (iter_cap <= 0) iter_cap = 0x7fffffffffffffffll;
+  if (!store) {
+    launch_chains(*s, kNoIterLimit, adapt, false, budget, iter_cap, nullptr);
+    return;
+  }
+  if (s->draw_cap == 0) throw std::runtime_error("reserve draws first");
+  if (s->acc && !adapt) {
+    // streaming summaries: every chain refills the staging block from row 0 and
+    // stream_update folds each chain's rows into its running sums
+    stream_flush(*s);
+    WB200_CUDA(cudaMemsetAsync(s->acc_rows(), 0, s->C * sizeof(long long), s->stream));
+    launch_chains(*s, kNoIterLimit, 0, true, budget, iter_cap, s->acc_rows());
+    stream_update(*s, s->acc_rows(), 0);
+    return;
+  }
+  if (!s->ragged) {  // the rows stored so far are uniform: start every counter there
+    std::vector<long long> rows(s->C, s->rows_written);
+    s->chain_rows.alloc(s->C);
+    WB200_CUDA(cudaMemcpyAsync(s->chain_rows.ptr, rows.data(), s->C * sizeof(long long),
+                               cudaMemcpyHostToDevice, s->stream));
+    WB200_CUDA(cudaStreamSynchronize(s->stream));
+    s->ragged = true;
+  }
+  launch_chains(*s, kNoIterLimit, adapt, true, budget, iter_cap, s->chain_rows.ptr);
+}
+
 int wb200_session_warmup_ticks(wb200_session* s, int n_ticks, int store,
                                WalnutpyError** err) {
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));
-    if (!s->tick) throw std::runtime_error("warmup_ticks needs the lock-step engine");
+    if (!s->initialised) throw std::runtime_error("session is not initialised");
     if (s->frozen) throw std::runtime_error("warm-up after freeze");
     if (n_ticks < 0) throw std::invalid_argument("n_ticks must be non-negative");
     if (store && s->draw_cap == 0) throw std::runtime_error("reserve draws first");
+    if (!s->tick) {
+      if (n_ticks > 0) chain_free_run(s, n_ticks, 0, 1, store != 0);
+      return;
+    }
     tick_run_ticks(*s, n_ticks, 1, store != 0);
     if (store) s->ragged = true;
+  });
+}
+
+int wb200_session_run_evals(wb200_session* s, int sampling, long long eval_budget,
+                            long long iter_cap, int store, WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    if (!s->initialised) throw std::runtime_error("session is not initialised");
+    if (s->tick) throw std::runtime_error("run_evals is the chain-resident engine's "
+                                          "free-running launch; use *_ticks here");
+    if (sampling && !s->frozen) throw std::runtime_error("sample before freeze");
+    if (!sampling && s->frozen) throw std::runtime_error("warm-up after freeze");
+    if (eval_budget <= 0) throw std::invalid_argument("eval_budget must be positive");
+    chain_free_run(s, eval_budget, iter_cap, sampling ? 0 : 1, store != 0);
+  });
+}
+
+int wb200_session_iter_stats(wb200_session* s, int sampling, long long* stats4,
+                             WalnutpyError** err) {
+  return catch_exceptions(err, [&] {
+    WB200_CUDA(cudaSetDevice(s->device));
+    if (!s->initialised) throw std::runtime_error("session is not initialised");
+    if (s->tick) throw std::runtime_error("iter_stats: chain-resident engine only");
+    chain_iter_stats(*s, sampling != 0, stats4);
   });
 }
 
@@ -338,10 +403,14 @@ int wb200_session_sample_ticks(wb200_session* s, int n_ticks, int store,
                                WalnutpyError** err) {
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));
-    if (!s->tick) throw std::runtime_error("sample_ticks needs the lock-step engine");
+    if (!s->initialised) throw std::runtime_error("session is not initialised");
     if (!s->frozen) throw std::runtime_error("sample before freeze");
     if (n_ticks < 0) throw std::invalid_argument("n_ticks must be non-negative");
     if (store && s->draw_cap == 0) throw std::runtime_error("reserve draws first");
+    if (!s->tick) {
+      if (n_ticks > 0) chain_free_run(s, n_ticks, 0, 0, store != 0);
+      return;
+    }
     if (s->acc && store) {
       // streaming: chains restart their staging rows at 0; a chain that fills the block
       // before the ticks are over idles until the next call (reserve generously)
@@ -362,6 +431,10 @@ int wb200_session_chain_rows(wb200_session* s, long long* rows, WalnutpyError** 
     if (s->tick) {
       tick_chain_rows(*s, rows);
       for (int c = 0; c < s->C; ++c) rows[c] = std::max(rows[c], s->rows_written);
+    } else if (s->ragged) {
+      WB200_CUDA(cudaMemcpyAsync(rows, s->chain_rows.ptr, s->C * sizeof(long long),
+                                 cudaMemcpyDeviceToHost, s->stream));
+      WB200_CUDA(cudaStreamSynchronize(s->stream));
     } else {
       for (int c = 0; c < s->C; ++c) rows[c] = s->rows_written;
     }

@@ -107,16 +107,43 @@ struct ChainScalars {
   unsigned long long grad_evals;
   unsigned long long macro_steps;   // leaves attempted
   unsigned long long rung_sum;      // sum of accepted rung indices (diagnostic)
+  // free-running launches (ChainParams::eval_budget): evaluations spent beyond the budgets
+  // handed out so far -- the transition that exhausts a budget is finished, and its excess
+  // is taken off the next budget, so every chain's long-run evaluation rate is the same
+  long long eval_debt;
   unsigned int iter;       // global transition index (Philox addressing)
   unsigned int warm_iter;  // AdaptiveWalnuts::iteration_
   int min_micro;
   int last_depth;
 };
 
+// A launch's limits for the chain a slot is working on: worked out once per chain by thread 0
+// and read from shared memory where they are needed (registers are what the hot loop is
+// short of).
+struct RunLimits {  // free-running launches only (ChainRunner::advance)
+  long long rows;    // draw row of the next transition
+  long long budget;  // gradient evaluations within which transitions may start
+  long long cap;     // transitions at most in this launch
+  long long done;    // transitions completed in this launch
+  int keep_metric;   // run() is re-entered for the same chain: its Cholesky factor stands
+};
+
 struct ChainParams {
   int C, D, ld;
   int n_iter;
   int adapt;
+  // Free-running mode (0: every chain does exactly n_iter transitions).  The reference's
+  // chains are threads that each run at their own pace until the controller stops them
+  // (adapt.hpp:110-129, sampler.hpp:79-94), so a chain with long orbits completes fewer
+  // iterations than one with short orbits.  The device analogue of "equal time" is equal
+  // WORK: every chain gets eval_budget gradient evaluations per launch and completes the
+  // transitions that fit (at most free_cap of them, and never beyond iter_cap transitions
+  // of the current phase in total); per-chain draw rows are counted in `rows`.  A launch
+  // no longer waits for the chain with the longest orbits.  n_iter is 1 in this mode.
+  long long eval_budget;
+  long long free_cap;
+  long long iter_cap;
+  long long* rows;      // nullable [C]: next draw row of each chain (else draw_base + it)
   int max_depth, max_halvings, min_micro_cfg;
   double max_error;
   double mass_init_count, macro_target;
@@ -173,6 +200,41 @@ __host__ __device__ inline int chain_smem_doubles(int ld) { return 3 * ld + 2 * 
 // bcast(): values computed by the control warp reach every thread.
 constexpr int kRedStride = 4;  // doubles per warp row / broadcast row
 
+#if defined(__CUDACC__)
+// One-warp groups (D <= 128: four independent chains per CTA, sixteen instruction streams
+// per SM) keep ONE out-of-line copy of each butterfly: the kernel's executed footprint is
+// what its warps fight over in the 32 KB instruction cache (ncu: 57 % of the D = 100
+// kernel's stall samples were instruction fetches with the butterflies inlined at every
+// reduction site).  Same operations in the same order as the inline code below.
+struct Sum2 { double a, b; };
+struct Sum4 { double a, b, c, d; };
+__device__ __noinline__ inline Sum2 warp_allsum2(double v0, double v1, int lane) {
+  const bool hi16 = (lane & 16) != 0;
+  double a = (hi16 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, hi16 ? v0 : v1, 16);
+  a += __shfl_xor_sync(0xffffffffu, a, 8);
+  a += __shfl_xor_sync(0xffffffffu, a, 4);
+  a += __shfl_xor_sync(0xffffffffu, a, 2);
+  a += __shfl_xor_sync(0xffffffffu, a, 1);
+  return Sum2{__shfl_sync(0xffffffffu, a, 0), __shfl_sync(0xffffffffu, a, 16)};
+}
+__device__ __noinline__ inline Sum4 warp_allsum4(double v0, double v1, double v2, double v3,
+                                                 int lane) {
+  const bool hi16 = (lane & 16) != 0;
+  double a = hi16 ? v2 : v0;
+  double b = hi16 ? v3 : v1;
+  a += __shfl_xor_sync(0xffffffffu, hi16 ? v0 : v2, 16);
+  b += __shfl_xor_sync(0xffffffffu, hi16 ? v1 : v3, 16);
+  const bool hi8 = (lane & 8) != 0;
+  const double keep = hi8 ? b : a, give = hi8 ? a : b;
+  a = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+  a += __shfl_xor_sync(0xffffffffu, a, 4);
+  a += __shfl_xor_sync(0xffffffffu, a, 2);
+  a += __shfl_xor_sync(0xffffffffu, a, 1);
+  return Sum4{__shfl_sync(0xffffffffu, a, 0), __shfl_sync(0xffffffffu, a, 8),
+              __shfl_sync(0xffffffffu, a, 16), __shfl_sync(0xffffffffu, a, 24)};
+}
+#endif
+
 template <int T>
 struct Group {
   static constexpr int W = T / 32;
@@ -199,6 +261,18 @@ struct Group {
   template <int N>
   __device__ __forceinline__ void sum(double (&v)[N]) {
     static_assert(N <= kRedStride, "too many values");
+#if defined(__CUDACC__)
+    if constexpr (T == 32 && N == 2) {
+      const Sum2 r = warp_allsum2(v[0], v[1], lane);
+      v[0] = r.a; v[1] = r.b;
+      return;
+    }
+    if constexpr (T == 32 && N == 4) {
+      const Sum4 r = warp_allsum4(v[0], v[1], v[2], v[3], lane);
+      v[0] = r.a; v[1] = r.b; v[2] = r.c; v[3] = r.d;
+      return;
+    }
+#endif
     if constexpr (T >= 32 && (N == 2 || N == 4)) {
       double a = v[0], b = v[N > 2 ? 1 : 0];
       if constexpr (N == 4) {
@@ -420,9 +494,13 @@ struct FunnelTargetT {
       }
     }
     if (owner) {
-      double lp = __dadd_rn(__dadd_rn(-__dmul_rn(v0, v0) / 18.0,
+      // the prior's 1/18 and 1/9 as rounded constants (this target is specified by the
+      // north star, not the reference): two fp64 divisions were a tenth of the executed
+      // instructions of the D = 100 kernel
+      constexpr double kInv18 = 1.0 / 18.0, kInv9 = 1.0 / 9.0;
+      double lp = __dadd_rn(__dadd_rn(-__dmul_rn(__dmul_rn(v0, v0), kInv18),
                                       -__dmul_rn(half_dm1, v0)), -q);
-      g[0][0] = static_cast<Real>(__dadd_rn(__dadd_rn(-v0 / 9.0, -half_dm1), q));
+      g[0][0] = static_cast<Real>(__dadd_rn(__dadd_rn(-__dmul_rn(v0, kInv9), -half_dm1), q));
       lp_part = static_cast<Real>(lp);
     } else {
       lp_part = 0;
@@ -710,6 +788,7 @@ struct ChainRunner {
   ChainScalars& sc;
   DecisionCache* dc = nullptr;  // shared memory, control warp only (null: no look-ahead)
   AdamQueue* aq = nullptr;      // shared memory; the entries live behind the scratch vectors
+  RunLimits* rl = nullptr;      // shared memory
   static constexpr int kAdamLanes = T >= 32 ? 32 : T;
   __device__ __forceinline__ double* adam_dH() const {
     return scr + static_cast<long long>(scratch_vectors(p.max_depth)) * ld;
@@ -960,7 +1039,7 @@ struct ChainRunner {
     auto est_row = [&]() { return p.est + static_cast<long long>(chain) * 4 * ld; };
     // the chain's current position lives in scratch row A_SEL between transitions
     row_from64(sv(A_SEL), theta_row);
-    if (!ADAPT) {
+    if (!ADAPT && !(p.eval_budget > 0 && rl->keep_metric)) {
       // Cholesky factor of the fixed metric, sqrt().inverse() (walnuts.hpp:647): constant
       // over the launch, so its square roots and divisions are paid once per chain
       double im64[K][2];
@@ -979,6 +1058,9 @@ struct ChainRunner {
       V::store(sv(A_IM), ld, tid, c);
     }
 
+    // draw row of transition `it`; evaluated where it is used (limits and parameters come
+    // from the constant bank and shared memory: nothing is kept live across a transition)
+    auto row_of = [&](int it) -> long long { return (p.rows ? rl->rows : p.draw_base) + it; };
     for (int it = 0; it < p.n_iter; ++it) {
       const uint32_t iter = u_iter;
       uint32_t sctr = 0;
@@ -1000,9 +1082,9 @@ struct ChainRunner {
           if (2 * (tid + k * T) + v >= p.D) im[k][v] = 1;
         }
       }
-      const long long row = p.draw_base + it;
       if (p.im_out) {
-        V::store64(p.im_out + (static_cast<long long>(chain) * p.draw_cap + row) * ld, tid, im);
+        V::store64(p.im_out + (static_cast<long long>(chain) * p.draw_cap + row_of(it)) * ld,
+                   tid, im);
       }
       // ---- momentum refresh rho = chol_mass * z  (walnuts.hpp:528-529)
       V::load(sv(A_SEL), ld, tid, th);
@@ -1179,11 +1261,11 @@ struct ChainRunner {
         sc.last_lp = lp_sel;
       }
       if (p.draws) {
-        row_to64(p.draws + (static_cast<long long>(chain) * p.draw_cap + row) * ld,
+        row_to64(p.draws + (static_cast<long long>(chain) * p.draw_cap + row_of(it)) * ld,
                  sv(A_SEL));
       }
       if (tid == 0) {
-        const long long o = static_cast<long long>(chain) * p.draw_cap + row;
+        const long long o = static_cast<long long>(chain) * p.draw_cap + row_of(it);
         if (p.lp_out) p.lp_out[o] = lp_sel;
         if (p.depth_out) p.depth_out[o] = depth;
         if (p.step_out) p.step_out[o] = ADAPT ? exp_noinline(sc.adam_x) : sc.step;
@@ -1194,6 +1276,57 @@ struct ChainRunner {
       sc.grad_evals += evals;
       sc.iter = u_iter;
       p.sc[chain] = sc;
+    }
+    grp.sync();
+  }
+
+  // One ticket.  Quota launch: run() once, n_iter transitions.  Free-running launch
+  // (ChainParams::eval_budget): the chain's transitions one run() at a time while its
+  // budget -- less what earlier launches overspent -- is not used up.  run() has this one
+  // call site and its hot loop is untouched; per transition the free-running mode adds the
+  // chain record's round trip and one copy of the position row.
+  __device__ __forceinline__ void advance(int chain) {
+    const bool free_run = p.eval_budget > 0;
+    unsigned long long evals0 = 0;
+    if (free_run) {
+      if (tid == 0) {
+        const ChainScalars& g = p.sc[chain];
+        const long long done0 = ADAPT ? static_cast<long long>(g.warm_iter)
+                                      : static_cast<long long>(g.lp_n);
+        rl->budget = p.eval_budget - g.eval_debt;
+        rl->rows = p.rows ? p.rows[chain] : p.draw_base;
+        long long cap = p.free_cap;
+        if (p.iter_cap - done0 < cap) cap = p.iter_cap > done0 ? p.iter_cap - done0 : 0;
+        if (p.rows && p.draws && p.draw_cap - rl->rows < cap) {  // the chain's rows are full
+          cap = p.draw_cap > rl->rows ? p.draw_cap - rl->rows : 0;
+        }
+        rl->cap = cap;
+        rl->done = 0;
+        rl->keep_metric = 0;
+      }
+      grp.sync();
+      evals0 = p.sc[chain].grad_evals;
+    }
+    long long spent = 0;
+    while (true) {
+      if (free_run && !(rl->done < rl->cap && spent < rl->budget)) break;
+      run(chain);  // ends with a barrier: thread 0's update of the record is visible
+      if (!free_run) return;
+      spent = static_cast<long long>(p.sc[chain].grad_evals - evals0);
+      grp.sync();  // every thread has read the limits this round
+      if (tid == 0) {
+        rl->done += 1;
+        rl->rows += 1;
+        rl->keep_metric = 1;
+      }
+      grp.sync();
+    }
+    if (tid == 0) {
+      // a chain that stopped at a cap (block full, last iteration of the phase) idles and
+      // owes nothing; otherwise the excess of its last transition is carried over
+      const long long over = spent - rl->budget;
+      p.sc[chain].eval_debt = (rl->done < rl->cap || over > 0) ? over : 0;
+      if (p.rows && p.draws) p.rows[chain] = rl->rows;
     }
     grp.sync();
   }
@@ -1209,6 +1342,7 @@ walnuts_chain_kernel(const ChainParams p) {
   __shared__ ChainScalars sc_smem[CTA / T];
   __shared__ DecisionCache dc_smem[CTA / T];
   __shared__ AdamQueue aq_smem[ADAPT ? CTA / T : 1];
+  __shared__ RunLimits rl_smem[CTA / T];
   __shared__ int next_chain;
   Group<T> grp;
   grp.lane = threadIdx.x & 31;
@@ -1235,6 +1369,7 @@ walnuts_chain_kernel(const ChainParams p) {
   }
   grp.sync();
   runner.dc = &dc_smem[threadIdx.x / T];
+  runner.rl = &rl_smem[threadIdx.x / T];
   if (ADAPT) runner.aq = &aq_smem[threadIdx.x / T];
   while (true) {
     int chain;
@@ -1249,7 +1384,7 @@ walnuts_chain_kernel(const ChainParams p) {
       __syncthreads();
     }
     if (chain >= p.C) break;
-    runner.run(p.order ? p.order[chain] : chain);
+    runner.advance(p.order ? p.order[chain] : chain);
   }
 }
 #endif  // __CUDACC__

@@ -524,7 +524,96 @@ static int sample_device_impl(
       if (min_iter == max_iter) return std::min(std::max(stride, 20), max_iter - done);
       return std::min(stride, max_iter - done);
     };
-    while (warm_done < max_warmup_iter) {
+    // Free-running phases (chain-resident engine, min < max): as in the reference, where
+    // every chain is a thread that runs at its own pace until the controller stops it
+    // (adapt.hpp:110-129, sampler.hpp:79-94), chains advance by equal WORK per block -- a
+    // budget of gradient evaluations worth `stride` average iterations -- and not by equal
+    // iteration counts, so the final lengths differ from chain to chain and no block waits
+    // for the chain with the longest orbits.  The controllers keep the reference's rules:
+    // no decision before every chain has done min_iter (adapt.hpp:196-203), stop on
+    // convergence or when every chain has reached max_iter (:219-221).
+    // WB200_BLOCKS=uniform restores blocks of equal iteration counts.
+    const char* blocks_env = std::getenv("WB200_BLOCKS");
+    const bool allow_free = !s->tick && !(blocks_env && std::string(blocks_env) == "uniform");
+    long long evals_seen = 0, iters_seen = 0;  // all chains, both phases: the mean cost
+    long long warm_max = 0;
+    std::vector<long long> warm_rows;  // per chain, when the warm-up ran free
+    auto free_budget = [&] {
+      const double per_iter = iters_seen > 0 ? static_cast<double>(evals_seen) /
+                                                   static_cast<double>(iters_seen)
+                                             : 16.0;
+      return std::max<long long>(1, std::llround(per_iter * stride));
+    };
+    // per-chain progress lines (handlers.hpp:38-48) of a free-running block
+    std::vector<long long> count_before, count_after;
+    auto chain_counts = [&](bool sampling, std::vector<long long>& out) {
+      std::vector<wb200::ChainScalars> h(C);
+      WB200_CUDA(cudaMemcpyAsync(h.data(), s->sc.ptr, C * sizeof(wb200::ChainScalars),
+                                 cudaMemcpyDeviceToHost, s->stream));
+      WB200_CUDA(cudaStreamSynchronize(s->stream));
+      out.resize(C);
+      for (size_t c = 0; c < C; ++c) {
+        out[c] = sampling ? static_cast<long long>(h[c].lp_n)
+                          : static_cast<long long>(h[c].warm_iter);
+      }
+    };
+    auto progress_ragged = [&](bool sampling) {
+      if (refresh == 0 || !print) return;
+      chain_counts(sampling, count_after);
+      if (count_before.size() != C) count_before.assign(C, 0);
+      for (size_t c = 0; c < C; ++c) {
+        // sampling iterations are numbered on from the chain's own warm-up
+        const long long offset = !sampling ? 0 : warm_rows.size() == C ? warm_rows[c] : warm_max;
+        for (long long it = count_before[c] + 1; it <= count_after[c]; ++it) {
+          if ((offset + it) % refresh != 0) continue;
+          std::stringstream ss;
+          ss << "Chain [" << (c + 1) << "]: Iteration " << (offset + it) << "\t"
+             << (sampling ? "(Sampling)" : "(Warmup)") << std::endl;
+          say(ss.str());
+        }
+      }
+      count_before = count_after;
+    };
+    // one free-running phase; returns the largest per-chain iteration count
+    auto free_phase = [&](bool sampling, int min_iter, int max_iter, bool store,
+                          auto&& converged) -> long long {
+      long long st[4] = {0, 0, 0, 0};
+      long long evals0 = 0;
+      check(wb200_session_iter_stats(s, sampling ? 1 : 0, st, &e), e);
+      evals0 = st[3];
+      const long long iters_before = iters_seen;
+      count_before.assign(C, 0);
+      while (st[2] < static_cast<long long>(C) * max_iter) {
+        throttle();
+        check(wb200_session_run_evals(s, sampling ? 1 : 0, free_budget(), max_iter,
+                                      store ? 1 : 0, &e), e);
+        launched();
+        progress_ragged(sampling);
+        report_exceptions();
+        interrupt.throw_if_interrupted();  // adapt.hpp:227, sampler.hpp:154
+        check(wb200_session_iter_stats(s, sampling ? 1 : 0, st, &e), e);
+        evals_seen += st[3] - evals0;
+        evals0 = st[3];
+        iters_seen = iters_before + st[2];
+        if (st[0] >= min_iter && st[2] < static_cast<long long>(C) * max_iter &&
+            converged()) {
+          break;
+        }
+      }
+      return st[1];
+    };
+    const bool free_warm = allow_free && min_warmup_iter < max_warmup_iter;
+    if (free_warm) {
+      warm_max = free_phase(false, min_warmup_iter, max_warmup_iter, save_warmup, [&] {
+        double dev[2];
+        check(wb200_session_warmup_sums(s, sums.ptr, &e), e);
+        check(wb200_session_warmup_deviation(s, sums.ptr, dev, &e), e);
+        return dev[0] <= mass_converge_tol && dev[1] <= step_size_converge_tol;
+      });
+      warm_done = static_cast<int>(warm_max);
+      chain_counts(false, warm_rows);
+    }
+    while (!free_warm && warm_done < max_warmup_iter) {
       const int n = block(warm_done, min_warmup_iter, max_warmup_iter);
       throttle();
       check(wb200_session_warmup(s, n, save_warmup ? 1 : 0, &e), e);
@@ -550,7 +639,29 @@ static int sample_device_impl(
     const int saved_warm = save_warmup ? warm_done : 0;
     // ---- sampling: R-hat of lp between blocks (sampler.hpp:132-151)
     int samp_done = 0;
-    while (samp_done < max_sampling_iter) {
+    if (!free_warm) warm_max = warm_done;
+    const bool free_samp = allow_free && (min_sampling_iter < max_sampling_iter || free_warm);
+    if (free_samp) {
+      const long long samp_max =
+          free_phase(true, min_sampling_iter, max_sampling_iter, true, [&] {
+            double m0[4], m[4];  // util.hpp:401-404, as in the uniform loop below
+            check(wb200_session_lp_moments(s, m0, &e), e);
+            check(wb200_session_lp_moments_centered(s, m0[0] / m0[3], m, &e), e);
+            const double M = m[3];
+            const double var_of_means = (m[1] - m[0] * m[0] / M) / (M - 1.0);
+            const double mean_of_vars = m[2] / M;
+            const double r_hat = std::sqrt(1 + var_of_means / mean_of_vars);
+            if (refresh != 0 && print) {  // handlers.hpp:164-172
+              std::stringstream ss;
+              ss.precision(10);
+              ss << "Controller: R-hat at " << r_hat << std::endl;
+              say(ss.str());
+            }
+            return r_hat <= rhat_converge_tol;
+          });
+      samp_done = static_cast<int>(samp_max);
+    }
+    while (!free_samp && samp_done < max_sampling_iter) {
       const int n = block(samp_done, min_sampling_iter, max_sampling_iter);
       throttle();
       check(wb200_session_sample(s, n, 1, &e), e);
@@ -582,6 +693,19 @@ static int sample_device_impl(
         if (r_hat <= rhat_converge_tol) break;
       }
     }
+    std::vector<long long> samp_rows;  // per chain, when sampling ran free
+    if (free_samp) {
+      chain_counts(true, samp_rows);
+      if (!so) {  // every row any chain holds, in one strided copy
+        long long rows_max = 0;
+        for (size_t c = 0; c < C; ++c) {
+          rows_max = std::max(rows_max, samp_rows[c] + (save_warmup && free_warm
+                                                            ? warm_rows[c] : saved_warm));
+        }
+        pending_from = std::min<long long>(pending_from, rows_max);
+        mark_block(rows_max);
+      }
+    }
     if (!so) flush_pending();
     check(wb200_session_sync(s, &e), e);
     phase("sampling");
@@ -594,8 +718,10 @@ static int sample_device_impl(
     phase("copy tail");
     // ---- outputs (walnutpy.cpp:196-221; handlers.hpp:73-100)
     for (size_t c = 0; c < C; ++c) {
-      final_lengths[c] = saved_warm;
-      final_lengths[c + C] = samp_done;
+      final_lengths[c] = !save_warmup ? 0
+                         : free_warm  ? static_cast<int>(warm_rows[c])
+                                      : saved_warm;
+      final_lengths[c + C] = free_samp ? static_cast<int>(samp_rows[c]) : samp_done;
     }
     check(wb200_session_get_state(s, nullptr, inv_metric_out, stepsize_out, nullptr,
                                   nullptr, &e), e);

@@ -262,6 +262,7 @@ __global__ void freeze_kernel(ChainParams p) {
       ChainScalars& sc = p.sc[c];
       sc.step = exp(sc.adam_x);
       sc.min_micro = min_micro_steps(sc, p);
+      sc.eval_debt = 0;  // sampling starts every chain level
     }
   }
 }
@@ -436,8 +437,13 @@ lpt_order_kernel(const ChainScalars* sc, unsigned long long* prev, int C, int* o
   }
 }
 
-void launch_chains(wb200_session& s, int n_iter, int adapt, bool store) {
-  ChainParams p = s.params(n_iter, adapt, store);
+void launch_chains(wb200_session& s, int n_iter, int adapt, bool store,
+                   long long eval_budget, long long iter_cap, long long* rows) {
+  ChainParams p = s.params(eval_budget > 0 ? 1 : n_iter, adapt, store);
+  p.eval_budget = eval_budget;  // > 0: free-running launch (chain_kernel.cuh), one
+  p.free_cap = n_iter;          // transition per ChainRunner::run, at most n_iter of them
+  p.iter_cap = iter_cap;
+  p.rows = rows;
   const size_t dyn_smem = chain_dyn_smem(s.shape, s.ld);
   if (s.C > s.slots) {  // more chains than resident groups: the hand-out order matters
     if (s.order.count == 0) {
@@ -461,7 +467,53 @@ void launch_chains(wb200_session& s, int n_iter, int adapt, bool store) {
   WB200_CUDA(cudaGetLastError());
   WB200_CUDA(cudaEventRecord(s.ev1, s.stream));
   s.launches += 1;
-  if (store) s.rows_written += n_iter;
+  if (store && eval_budget == 0) s.rows_written += n_iter;
+}
+
+// per-chain iteration counts of the current phase (warm-up: AdaptiveWalnuts::iteration_,
+// sampling: draws observed by the lp accumulator): {min, max, sum}, then the gradient
+// evaluations of all chains so far -- what the reference's
+// controllers read from the chains' snapshots (adapt.hpp:196-203, sampler.hpp:134-141)
+__global__ void __launch_bounds__(1024)
+iter_stats_kernel(const ChainScalars* sc, int C, int sampling, long long* out4) {
+  __shared__ long long smin[32], smax[32], ssum[32], sev[32];
+  long long mn = 0x7fffffffffffffffll, mx = 0, sm = 0, ev = 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const long long n = sampling ? static_cast<long long>(sc[c].lp_n)
+                                 : static_cast<long long>(sc[c].warm_iter);
+    mn = n < mn ? n : mn; mx = n > mx ? n : mx; sm += n;
+    ev += static_cast<long long>(sc[c].grad_evals);
+  }
+  for (int m = 16; m >= 1; m >>= 1) {
+    const long long a = __shfl_xor_sync(0xffffffffu, mn, m);
+    const long long b = __shfl_xor_sync(0xffffffffu, mx, m);
+    sm += __shfl_xor_sync(0xffffffffu, sm, m);
+    ev += __shfl_xor_sync(0xffffffffu, ev, m);
+    mn = a < mn ? a : mn; mx = b > mx ? b : mx;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; ssum[threadIdx.x >> 5] = sm;
+    sev[threadIdx.x >> 5] = ev;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) {
+      mn = smin[w] < mn ? smin[w] : mn; mx = smax[w] > mx ? smax[w] : mx; sm += ssum[w];
+      ev += sev[w];
+    }
+    out4[0] = mn; out4[1] = mx; out4[2] = sm; out4[3] = ev;
+  }
+}
+
+void chain_iter_stats(wb200_session& s, bool sampling, long long* out4_host) {
+  if (s.iter_stats.count == 0) s.iter_stats.alloc(4);
+  iter_stats_kernel<<<1, 1024, 0, s.stream>>>(s.sc.ptr, s.C, sampling ? 1 : 0,
+                                              s.iter_stats.ptr);
+  WB200_CUDA(cudaGetLastError());
+  s.launches += 1;
+  WB200_CUDA(cudaMemcpyAsync(out4_host, s.iter_stats.ptr, 4 * sizeof(long long),
+                             cudaMemcpyDeviceToHost, s.stream));
+  WB200_CUDA(cudaStreamSynchronize(s.stream));
 }
 
 void launch_init(wb200_session& s, bool have_mass, bool have_steps,

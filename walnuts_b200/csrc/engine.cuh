@@ -169,6 +169,8 @@ struct wb200_session {
   wb200::DeviceBuffer<unsigned int> ticket;
   wb200::DeviceBuffer<int> order;                      // [C] ticket -> chain (LPT order)
   wb200::DeviceBuffer<unsigned long long> prev_evals;  // [C] grad_evals before the last launch
+  wb200::DeviceBuffer<long long> chain_rows;  // [C] draw rows per chain (free-running chain engine)
+  wb200::DeviceBuffer<long long> iter_stats;  // {min, max, sum} of per-chain iteration counts, total evals
   wb200::TickEngine* tick = nullptr;  // lock-step engine (logistic; WB200_ENGINE=tick)
   wb200::StreamState* acc = nullptr;  // streaming summary accumulators (stream.cu)
 
@@ -177,7 +179,13 @@ struct wb200_session {
 };
 
 namespace wb200 {
-void launch_chains(wb200_session& s, int n_iter, int adapt, bool store);
+// eval_budget > 0: free-running launch (every chain completes the transitions that fit
+// into that many gradient evaluations, at most n_iter, never beyond iter_cap of the phase;
+// rows = per-chain draw row counters)
+void launch_chains(wb200_session& s, int n_iter, int adapt, bool store,
+                   long long eval_budget = 0, long long iter_cap = 0,
+                   long long* rows = nullptr);
+void chain_iter_stats(wb200_session& s, bool sampling, long long* out4_host);
 void launch_init(wb200_session& s, bool have_mass, bool have_steps,
                  bool have_positions, double init_radius);
 void launch_freeze(wb200_session& s);

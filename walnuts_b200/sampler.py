@@ -102,10 +102,12 @@ def walnuts_device(
 
     Arguments, defaults, validation errors and the returned list of
     :class:`WalnutsOutputArray` follow ``walnuts_pyfunc`` (pyfunc.py:45-286).
-    Differences: (i) ``logp`` is a :class:`DeviceModel`; (ii) early stopping is
-    evaluated every ``publish_stride`` (5) iterations for all chains at once, so
-    every chain stops at the same iteration (the reference's chain lengths are
-    thread-schedule dependent, docs/py.rst:13-20); (iii) random numbers come
+    Differences: (i) ``logp`` is a :class:`DeviceModel`; (ii) with ``min < max`` the
+    chains of an element-wise model run free like the reference's threads -- by equal
+    work (gradient evaluations) per block, so final lengths differ by chain as in the
+    reference (docs/py.rst:13-20) but are reproducible; lock-step (logistic, callback)
+    models and ``WB200_BLOCKS=uniform`` stop all chains at the same iteration, decided
+    every ``publish_stride`` (5) iterations; (iii) random numbers come
     from a counter-based Philox stream keyed by ``(seed + id + num_chains,
     chain)``, not from ``std::mt19937_64``.
     """
@@ -223,7 +225,8 @@ def walnuts_device_summary(logp: DeviceModel, *, num_chains: int = 4, seed: Opti
     out.update(truncated=cut, stepsize=stepsize, inv_metric=inv_metric,
                warmup_iters=(_ffi.last_run_stats()["warmup_iters"] if devices is None
                              else None),
-               sampling_iters=int(lengths[num_chains]))
+               sampling_iters=int(lengths[num_chains:].max()),
+               sampling_lengths=lengths[num_chains:].astype(np.int64))
     return out
 
 
@@ -297,14 +300,34 @@ class Session:
         return self
 
     def sample_ticks(self, n_ticks: int, store: bool = True):
-        """Lock-step sessions: exactly ``n_ticks`` ticks (one batched gradient each);
-        chains complete as many transitions as fit (ragged draw counts)."""
+        """Free-running sampling: ``n_ticks`` gradient evaluations per chain; chains
+        complete as many transitions as fit (ragged draw counts, like the reference's
+        per-thread chains, sampler.hpp:79-94).  Lock-step sessions: exactly ``n_ticks``
+        ticks, transitions in flight carry over.  Chain-resident sessions: the transition
+        that exhausts the budget is finished and its excess comes off the next budget."""
         return self._run(_ffi.session_sample_ticks, int(n_ticks), int(store))
 
     def warmup_ticks(self, n_ticks: int, store: bool = False):
-        """Lock-step sessions: adaptive warm-up for exactly ``n_ticks`` ticks; every chain
-        adapts over as many transitions as fit.  ``freeze`` abandons those in flight."""
+        """Free-running adaptive warm-up: ``n_ticks`` gradient evaluations per chain; every
+        chain adapts over as many transitions as fit.  On lock-step sessions ``freeze``
+        abandons the transitions in flight."""
         return self._run(_ffi.session_warmup_ticks, int(n_ticks), int(store))
+
+    def run_evals(self, eval_budget: int, *, sampling: bool, iter_cap: int = 0,
+                  store: bool = True):
+        """Chain-resident sessions: one free-running launch of ``eval_budget`` gradient
+        evaluations per chain in which no chain exceeds ``iter_cap`` iterations of the
+        phase in total (0: no limit) -- a reference chain stops at ``max_iter``."""
+        _ffi.session_run_evals(self._h, int(sampling), int(eval_budget), int(iter_cap),
+                               int(store))
+        return self
+
+    def iter_stats(self, *, sampling: bool) -> tuple:
+        """(min, max, sum) over the chains of the phase's per-chain iteration counts, and
+        the gradient evaluations of all chains since initialisation."""
+        out = np.zeros(4, np.int64)
+        _ffi.session_iter_stats(self._h, int(sampling), out)
+        return int(out[0]), int(out[1]), int(out[2]), int(out[3])
 
     def chain_rows(self) -> np.ndarray:
         rows = np.zeros(self.num_chains, np.int64)
