@@ -80,14 +80,16 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   {
     ChainRunner<Target, 1, kEmuK, true> r(p, grp, scratch.data(), sc_shared,
                                            chain_smem.data());
-    r.dc = &decision_cache;
-    r.aq = &adam_queue;
-    r.rl = &run_limits;
+    ChainRunner<Target, 1, kEmuK, true, double, true> rf(p, grp, scratch.data(), sc_shared,
+                                                         chain_smem.data());
+    r.dc = rf.dc = &decision_cache;
+    r.aq = rf.aq = &adam_queue;
+    rf.rl = &run_limits;
     if (budget > 0) {
       p.n_iter = 1; p.free_cap = 0x7fffffff; p.iter_cap = n_warmup;
-      while (static_cast<int>(sc.warm_iter) < n_warmup) { r.advance(0); ++n_launch; }
+      while (static_cast<int>(sc.warm_iter) < n_warmup) { rf.advance(0); ++n_launch; }
     } else if (n_warmup > 0) {
-      r.advance(0);
+      r.run(0);
     }
   }
   // freeze_kernel
@@ -103,14 +105,16 @@ static void run(const EmuTuning& t, int D, const double* tparam, uint32_t seed,
   {
     ChainRunner<Target, 1, kEmuK, false> r(p, grp, scratch.data(), sc_shared,
                                             chain_smem.data());
-    r.dc = &decision_cache;
-    r.rl = &run_limits;
+    ChainRunner<Target, 1, kEmuK, false, double, true> rf(p, grp, scratch.data(), sc_shared,
+                                                          chain_smem.data());
+    r.dc = rf.dc = &decision_cache;
+    rf.rl = &run_limits;
     if (budget > 0) {
       p.n_iter = 1; p.free_cap = 0x7fffffff; p.iter_cap = n_sampling;
       sc.eval_debt = 0;  // freeze_kernel
-      while (static_cast<int>(sc.lp_n) < n_sampling) { r.advance(0); ++n_launch; }
+      while (static_cast<int>(sc.lp_n) < n_sampling) { rf.advance(0); ++n_launch; }
     } else if (n_sampling > 0) {
-      r.advance(0);
+      r.run(0);
     }
   }
   if (launches) *launches = n_launch;

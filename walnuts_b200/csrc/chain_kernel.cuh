@@ -125,6 +125,8 @@ struct RunLimits {  // free-running launches only (ChainRunner::advance)
   long long budget;  // gradient evaluations within which transitions may start
   long long cap;     // transitions at most in this launch
   long long done;    // transitions completed in this launch
+  long long spent;   // gradient evaluations used in this launch
+  unsigned long long evals0;  // the chain's evaluation count when the launch took it up
   int keep_metric;   // run() is re-entered for the same chain: its Cholesky factor stands
 };
 
@@ -768,7 +770,10 @@ __device__ __noinline__ int adapt_end(const ChainParams& p, Group<T> grp, ChainS
 
 // ADAPT is a compile-time copy of ChainParams::adapt: the sampling instance carries none
 // of the adaptation code (the kernel competes for the instruction cache)
-template <class Target, int T, int K, bool ADAPT = true, class Real = double>
+// FREE: the free-running mode (advance(), ChainParams::eval_budget) -- one transition per
+// run(), draw rows and the re-use of the metric's factor taken from RunLimits
+template <class Target, int T, int K, bool ADAPT = true, class Real = double,
+          bool FREE = false>
 struct ChainRunner {
   using V = VecT<T, K, Real>;
   const ChainParams& p;
@@ -1039,7 +1044,9 @@ struct ChainRunner {
     auto est_row = [&]() { return p.est + static_cast<long long>(chain) * 4 * ld; };
     // the chain's current position lives in scratch row A_SEL between transitions
     row_from64(sv(A_SEL), theta_row);
-    if (!ADAPT && !(p.eval_budget > 0 && rl->keep_metric)) {
+    bool have_factor = false;
+    if constexpr (FREE) have_factor = rl->keep_metric != 0;
+    if (!ADAPT && !have_factor) {
       // Cholesky factor of the fixed metric, sqrt().inverse() (walnuts.hpp:647): constant
       // over the launch, so its square roots and divisions are paid once per chain
       double im64[K][2];
@@ -1060,7 +1067,10 @@ struct ChainRunner {
 
     // draw row of transition `it`; evaluated where it is used (limits and parameters come
     // from the constant bank and shared memory: nothing is kept live across a transition)
-    auto row_of = [&](int it) -> long long { return (p.rows ? rl->rows : p.draw_base) + it; };
+    auto row_of = [&](int it) -> long long {
+      if constexpr (FREE) return (p.rows ? rl->rows : p.draw_base) + it;
+      return p.draw_base + it;
+    };
     for (int it = 0; it < p.n_iter; ++it) {
       const uint32_t iter = u_iter;
       uint32_t sctr = 0;
@@ -1286,14 +1296,17 @@ struct ChainRunner {
   // call site and its hot loop is untouched; per transition the free-running mode adds the
   // chain record's round trip and one copy of the position row.
   __device__ __forceinline__ void advance(int chain) {
-    const bool free_run = p.eval_budget > 0;
-    unsigned long long evals0 = 0;
-    if (free_run) {
+    // nothing of this bookkeeping lives in registers across run(): the limits sit in shared
+    // memory, and whether the launch runs free is a kernel parameter (constant bank)
+    if (!FREE) { run(chain); return; }
+    if (p.eval_budget > 0) {
       if (tid == 0) {
         const ChainScalars& g = p.sc[chain];
         const long long done0 = ADAPT ? static_cast<long long>(g.warm_iter)
                                       : static_cast<long long>(g.lp_n);
         rl->budget = p.eval_budget - g.eval_debt;
+        rl->evals0 = g.grad_evals;
+        rl->spent = 0;
         rl->rows = p.rows ? p.rows[chain] : p.draw_base;
         long long cap = p.free_cap;
         if (p.iter_cap - done0 < cap) cap = p.iter_cap > done0 ? p.iter_cap - done0 : 0;
@@ -1305,16 +1318,13 @@ struct ChainRunner {
         rl->keep_metric = 0;
       }
       grp.sync();
-      evals0 = p.sc[chain].grad_evals;
     }
-    long long spent = 0;
     while (true) {
-      if (free_run && !(rl->done < rl->cap && spent < rl->budget)) break;
-      run(chain);  // ends with a barrier: thread 0's update of the record is visible
-      if (!free_run) return;
-      spent = static_cast<long long>(p.sc[chain].grad_evals - evals0);
-      grp.sync();  // every thread has read the limits this round
+      if (p.eval_budget > 0 && !(rl->done < rl->cap && rl->spent < rl->budget)) break;
+      run(chain);  // ends with a barrier: every thread is past its reads of the limits
+      if (p.eval_budget <= 0) return;
       if (tid == 0) {
+        rl->spent = static_cast<long long>(p.sc[chain].grad_evals - rl->evals0);
         rl->done += 1;
         rl->rows += 1;
         rl->keep_metric = 1;
@@ -1324,7 +1334,7 @@ struct ChainRunner {
     if (tid == 0) {
       // a chain that stopped at a cap (block full, last iteration of the phase) idles and
       // owes nothing; otherwise the excess of its last transition is carried over
-      const long long over = spent - rl->budget;
+      const long long over = rl->spent - rl->budget;
       p.sc[chain].eval_debt = (rl->done < rl->cap || over > 0) ? over : 0;
       if (p.rows && p.draws) p.rows[chain] = rl->rows;
     }
@@ -1334,7 +1344,13 @@ struct ChainRunner {
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------
-template <class Target, int T, int K, int CTA, int MINB, bool ADAPT, class Real = double>
+// FREE selects the free-running mode (ChainRunner::advance).  It is a separate kernel so
+// that the quota launch's code -- registers, layout, instruction-cache footprint -- is
+// exactly what it is without the mode: these kernels sit at their register caps and the
+// one-warp shapes are instruction-fetch bound (wrapping run() in the free-running loop
+// cost the D = 100 warm-up 14 % and the D = 1000 sampling kernel 200 bytes of spills).
+template <class Target, int T, int K, int CTA, int MINB, bool ADAPT, class Real = double,
+          bool FREE = false>
 __global__ void __launch_bounds__(CTA, MINB)
 walnuts_chain_kernel(const ChainParams p) {
   extern __shared__ double chain_smem[];  // [CTA / T][chain_smem_doubles(ld)]
@@ -1342,7 +1358,7 @@ walnuts_chain_kernel(const ChainParams p) {
   __shared__ ChainScalars sc_smem[CTA / T];
   __shared__ DecisionCache dc_smem[CTA / T];
   __shared__ AdamQueue aq_smem[ADAPT ? CTA / T : 1];
-  __shared__ RunLimits rl_smem[CTA / T];
+  __shared__ RunLimits rl_smem[FREE ? CTA / T : 1];
   __shared__ int next_chain;
   Group<T> grp;
   grp.lane = threadIdx.x & 31;
@@ -1360,7 +1376,7 @@ walnuts_chain_kernel(const ChainParams p) {
     slot = blockIdx.x;
   }
   double* scr = p.scratch + static_cast<long long>(slot) * p.scratch_stride;
-  ChainRunner<Target, T, K, ADAPT, Real> runner(
+  ChainRunner<Target, T, K, ADAPT, Real, FREE> runner(
       p, grp, scr, sc_smem[threadIdx.x / T],
       chain_smem + static_cast<int>(threadIdx.x / T) * chain_smem_doubles(p.ld));
   if (grp.tid == 0) {
@@ -1369,7 +1385,7 @@ walnuts_chain_kernel(const ChainParams p) {
   }
   grp.sync();
   runner.dc = &dc_smem[threadIdx.x / T];
-  runner.rl = &rl_smem[threadIdx.x / T];
+  if (FREE) runner.rl = &rl_smem[threadIdx.x / T];
   if (ADAPT) runner.aq = &aq_smem[threadIdx.x / T];
   while (true) {
     int chain;
@@ -1384,7 +1400,11 @@ walnuts_chain_kernel(const ChainParams p) {
       __syncthreads();
     }
     if (chain >= p.C) break;
-    runner.advance(p.order ? p.order[chain] : chain);
+    if constexpr (FREE) {
+      runner.advance(p.order ? p.order[chain] : chain);
+    } else {
+      runner.run(p.order ? p.order[chain] : chain);
+    }
   }
 }
 #endif  // __CUDACC__

@@ -352,9 +352,15 @@ static int sm_count(int device) {
   } while (0)
 #define WB200_LAUNCH_CHAIN(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)             \
   do {                                                                         \
-    if (p.adapt) {                                                             \
+    if (p.adapt && p.eval_budget > 0) {                                        \
+      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true, double, true> \
+          <<<s.grid_adapt, CTA_, dyn_smem, s.stream>>>(p);                     \
+    } else if (p.adapt) {                                                      \
       walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true>        \
           <<<s.grid_adapt, CTA_, dyn_smem, s.stream>>>(p);                     \
+    } else if (p.eval_budget > 0) {                                            \
+      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false, double, true> \
+          <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
     } else {                                                                   \
       walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false>       \
           <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
@@ -371,9 +377,15 @@ static int sm_count(int device) {
   } while (0)
 #define WB200_LAUNCH_CHAIN_F32(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)         \
   do {                                                                         \
-    if (p.adapt) {                                                             \
+    if (p.adapt && p.eval_budget > 0) {                                        \
+      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true, float, true> \
+          <<<s.grid_adapt, CTA_, dyn_smem, s.stream>>>(p);                     \
+    } else if (p.adapt) {                                                      \
       walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true, float> \
           <<<s.grid_adapt, CTA_, dyn_smem, s.stream>>>(p);                     \
+    } else if (p.eval_budget > 0) {                                            \
+      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false, float, true> \
+          <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
     } else {                                                                   \
       walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false, float> \
           <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
