@@ -1,5 +1,6 @@
 // Kernel instantiations and launchers of the device sampler.
 #include "engine.cuh"
+#include "engine_shapes.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -26,69 +27,6 @@ LaunchShape shape_for_dim(int D) {
   throw std::invalid_argument("num_params above 4096 is not supported by the "
                               "chain-resident kernel");
 }
-
-// (TARGET, T, K, CTA, min resident CTAs per SM -> register cap)
-// (TARGET, T, K, CTA, resident CTAs per SM asked of the adaptive / the sampling instance ->
-// register cap).  The sampling instance of the wide shapes fits 128 registers without
-// spilling since the start state moved to shared memory; the adaptive one needs 168.
-#ifndef WB200_MINB_32X2
-#define WB200_MINB_32X2 4
-#endif
-#ifndef WB200_MINB_128X4
-#define WB200_MINB_128X4 4
-#endif
-#ifndef WB200_MINB_128X4_ADAPT
-#define WB200_MINB_128X4_ADAPT 3
-#endif
-#define WB200_FOR_SHAPE(S, MACRO, TARGET)                                      \
-  do {                                                                         \
-    if ((S).T == 32 && (S).K == 1) { MACRO(TARGET, 32, 1, 128, 4, 4); }        \
-    else if ((S).T == 32 && (S).K == 2) { MACRO(TARGET, 32, 2, 128, WB200_MINB_32X2, WB200_MINB_32X2); } \
-    else if ((S).T == 64) { MACRO(TARGET, 64, 2, 64, 6, 6); }                  \
-    else if ((S).T == 128 && (S).K == 2) { MACRO(TARGET, 128, 2, 128, 3, 3); } \
-    else if ((S).T == 128 && (S).K == 4) { MACRO(TARGET, 128, 4, 128, WB200_MINB_128X4_ADAPT, WB200_MINB_128X4); } \
-    else if ((S).T == 256 && (S).K == 2) { MACRO(TARGET, 256, 2, 256, 2, 2); } \
-    else if ((S).T == 256 && (S).K == 4) { MACRO(TARGET, 256, 4, 256, 1, 1); } \
-    else { MACRO(TARGET, 512, 4, 512, 1, 1); }                                 \
-  } while (0)
-
-// fp32 mode: half the register footprint per element, so more resident CTAs
-#ifndef WB200_MINB_128X4_F32
-#define WB200_MINB_128X4_F32 5
-#endif
-#define WB200_FOR_SHAPE_F32(S, MACRO, TARGET)                                  \
-  do {                                                                         \
-    if ((S).T == 32 && (S).K == 1) { MACRO(TARGET, 32, 1, 128, 4, 4); }        \
-    else if ((S).T == 32 && (S).K == 2) { MACRO(TARGET, 32, 2, 128, 4, 4); }   \
-    else if ((S).T == 64) { MACRO(TARGET, 64, 2, 64, 6, 8); }                  \
-    else if ((S).T == 128 && (S).K == 2) { MACRO(TARGET, 128, 2, 128, 4, 5); } \
-    else if ((S).T == 128 && (S).K == 4) { MACRO(TARGET, 128, 4, 128, 4, WB200_MINB_128X4_F32); } \
-    else if ((S).T == 256 && (S).K == 2) { MACRO(TARGET, 256, 2, 256, 2, 2); } \
-    else if ((S).T == 256 && (S).K == 4) { MACRO(TARGET, 256, 4, 256, 1, 2); } \
-    else { MACRO(TARGET, 512, 4, 512, 1, 1); }                                 \
-  } while (0)
-
-#define WB200_FOR_TARGET_F32(KIND, S, MACRO)                                   \
-  do {                                                                         \
-    switch (KIND) {                                                            \
-      case kStdNormal: WB200_FOR_SHAPE_F32(S, MACRO, StdNormalTargetF); break; \
-      case kDiagGaussian: WB200_FOR_SHAPE_F32(S, MACRO, DiagGaussianTargetF); break; \
-      case kFunnel: WB200_FOR_SHAPE_F32(S, MACRO, FunnelTargetF); break;       \
-      default: throw std::invalid_argument("model kind has no chain-resident " \
-                                           "kernel");                          \
-    }                                                                          \
-  } while (0)
-
-#define WB200_FOR_TARGET(KIND, S, MACRO)                                       \
-  do {                                                                         \
-    switch (KIND) {                                                            \
-      case kStdNormal: WB200_FOR_SHAPE(S, MACRO, StdNormalTarget); break;      \
-      case kDiagGaussian: WB200_FOR_SHAPE(S, MACRO, DiagGaussianTarget); break;\
-      case kFunnel: WB200_FOR_SHAPE(S, MACRO, FunnelTarget); break;            \
-      default: throw std::invalid_argument("model kind has no chain-resident " \
-                                           "kernel");                          \
-    }                                                                          \
-  } while (0)
 
 // ---------------------------------------------------------------------------
 // Batched initialisation: InitConfigBuilder::positions(rng, scale)
@@ -319,24 +257,6 @@ __global__ void __launch_bounds__(CTA) orbit_kernel(const OrbitParams op) {
   if (grp.tid == 0) { op.logp[chain] = lp; op.joint[chain] = H; }
 }
 
-// ---------------------------------------------------------------------------
-// dynamic shared memory of a chain-kernel CTA: the parked start states and sub-tree
-// stacks of its resident chains
-static size_t chain_dyn_smem(const LaunchShape& shape, int ld) {
-  return static_cast<size_t>(shape.chains_per_cta) * chain_smem_doubles(ld) * sizeof(double);
-}
-
-template <class Kernel>
-static int blocks_per_sm(Kernel k, int cta, size_t dyn_smem) {
-  int n = 0;
-  if (dyn_smem > 48 * 1024) {
-    WB200_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(dyn_smem)));
-  }
-  WB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, cta, dyn_smem));
-  return std::max(n, 1);
-}
-
 static int sm_count(int device) {
   int n = 0;
   WB200_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
@@ -352,42 +272,11 @@ static int sm_count(int device) {
   } while (0)
 #define WB200_LAUNCH_CHAIN(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)             \
   do {                                                                         \
-    if (p.adapt && p.eval_budget > 0) {                                        \
-      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true, double, true> \
-          <<<s.grid_adapt, CTA_, dyn_smem, s.stream>>>(p);                     \
-    } else if (p.adapt) {                                                      \
+    if (p.adapt) {                                                             \
       walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true>        \
           <<<s.grid_adapt, CTA_, dyn_smem, s.stream>>>(p);                     \
-    } else if (p.eval_budget > 0) {                                            \
-      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false, double, true> \
-          <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
     } else {                                                                   \
       walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false>       \
-          <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
-    }                                                                          \
-  } while (0)
-#define WB200_OCC_F32(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)                  \
-  do {                                                                         \
-    occ_adapt = blocks_per_sm(                                                 \
-        walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true, float>, CTA_, \
-        dyn_smem);                                                             \
-    occ_sample = blocks_per_sm(                                                \
-        walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false, float>, CTA_, \
-        dyn_smem);                                                             \
-  } while (0)
-#define WB200_LAUNCH_CHAIN_F32(TARGET, T_, K_, CTA_, MINB_A_, MINB_S_)         \
-  do {                                                                         \
-    if (p.adapt && p.eval_budget > 0) {                                        \
-      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true, float, true> \
-          <<<s.grid_adapt, CTA_, dyn_smem, s.stream>>>(p);                     \
-    } else if (p.adapt) {                                                      \
-      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_A_, true, float> \
-          <<<s.grid_adapt, CTA_, dyn_smem, s.stream>>>(p);                     \
-    } else if (p.eval_budget > 0) {                                            \
-      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false, float, true> \
-          <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
-    } else {                                                                   \
-      walnuts_chain_kernel<TARGET<T_, K_>, T_, K_, CTA_, MINB_S_, false, float> \
           <<<s.grid, CTA_, dyn_smem, s.stream>>>(p);                           \
     }                                                                          \
   } while (0)
@@ -404,7 +293,7 @@ void occupancy_for(int kind, const LaunchShape& shape, int ld, int precision, in
   int occ_adapt = 1, occ_sample = 1;
   const size_t dyn_smem = chain_dyn_smem(shape, ld);
   if (precision == 1) {
-    WB200_FOR_TARGET_F32(kind, shape, WB200_OCC_F32);
+    occupancy_f32(kind, shape, dyn_smem, &occ_adapt, &occ_sample);
   } else {
     WB200_FOR_TARGET(kind, shape, WB200_OCC);
   }
@@ -471,8 +360,11 @@ void launch_chains(wb200_session& s, int n_iter, int adapt, bool store,
   }
   WB200_CUDA(cudaMemsetAsync(s.ticket.ptr, 0, sizeof(unsigned int), s.stream));
   WB200_CUDA(cudaEventRecord(s.ev0, s.stream));
-  if (s.precision == 1) {
-    WB200_FOR_TARGET_F32(s.kind, s.shape, WB200_LAUNCH_CHAIN_F32);
+  if (p.eval_budget > 0) {  // the free-running kernels (engine_free*.cu)
+    if (s.precision == 1) launch_chain_free_f32(s, p, dyn_smem);
+    else launch_chain_free(s, p, dyn_smem);
+  } else if (s.precision == 1) {
+    launch_chain_f32(s, p, dyn_smem);
   } else {
     WB200_FOR_TARGET(s.kind, s.shape, WB200_LAUNCH_CHAIN);
   }
