@@ -55,6 +55,22 @@ typedef void (*PRINT_CALLBACK)(const char* msg, size_t len, bool bad);
  *         tick continues with logp = -inf and a zero gradient (NoExceptLogpGrad,
  *         util.hpp:336-346), the failure is counted (wb200_session_logp_exceptions)
  *         and reported through the print callback.
+ * kind 5  the caller's own density as CUDA source text, compiled at run time (NVRTC) into
+ *         the chain-resident kernel: data0 = const char* source (zero-terminated), data1 =
+ *         N parameter doubles (host; N may be 0), fp64.  What LogpGrad (concepts.hpp:25-60)
+ *         is to the reference's host threads: the density becomes the `Target` of the
+ *         transition kernel, so the chain stays in registers across an orbit like the
+ *         built-in targets' (kind 4 streams the state through HBM once per gradient).
+ *         Element-wise (separable) densities define
+ *             __device__ void wb200_logp_grad(int d, double x, const double* par,
+ *                                             double& lp, double& g);
+ *         -- term d of the log density and its derivative at x.  Densities that need the
+ *         chain's all-reduce (like kind 2) define a Target template and name it:
+ *             template <int T, int K, class Real> struct MyTarget { init(...); grad(...); };
+ *             #define WB200_USER_TARGET MyTarget
+ *         (interface: walnuts_b200/csrc/chain_kernel.cuh, "Targets").  A source that does
+ *         not compile is a config error carrying the compiler's log.  Compiled kernels are
+ *         cached per (device, launch shape, source).
  */
 typedef int (*WB200_BATCH_LOGP_GRAD)(size_t num_chains, size_t num_params, size_t ld,
                                      const double* theta, double* grad, double* lp,
@@ -437,6 +453,11 @@ int wb200_device_summary(const double* draws_device, size_t num_chains,
 int wb200_logistic_logp_grad(const double* X, const double* y, size_t N, int D,
                              const double* theta, size_t C, double* logp, double* grad,
                              int repeats, float* ms_per_eval, WalnutpyError** err);
+
+/* kind 5: compile `source` for a model of num_params dimensions without touching a GPU
+ * (NVRTC only); the compiler's output (warnings) goes to log[log_size] if non-null */
+int wb200_compile_device_source(const char* source, int num_params, char* log,
+                                size_t log_size, WalnutpyError** err);
 
 const char* walnuts_b200_version(void);
 

@@ -260,6 +260,8 @@ session_sample_ticks = _sess("wb200_session_sample_ticks",
                              [session_p, ctypes.c_int, ctypes.c_int])
 session_warmup_ticks = _sess("wb200_session_warmup_ticks",
                              [session_p, ctypes.c_int, ctypes.c_int])
+compile_device_source = _sess("wb200_compile_device_source", [
+    ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t])
 session_run_evals = _sess("wb200_session_run_evals", [
     session_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int])
 session_iter_stats = _sess("wb200_session_iter_stats", [
@@ -383,7 +385,7 @@ EXPORTED_SYMBOLS = [
     "wb200_session_reserve_draws", "wb200_session_warmup", "wb200_session_freeze",
     "wb200_session_sample", "wb200_session_sync", "wb200_session_sample_ticks",
     "wb200_session_warmup_ticks",
-    "wb200_session_run_evals", "wb200_session_iter_stats",
+    "wb200_session_run_evals", "wb200_session_iter_stats", "wb200_compile_device_source",
     "wb200_session_chain_rows", "wb200_session_summary", "wb200_session_rhat_moments", "wb200_session_warmup_sums",
     "wb200_session_warmup_deviation", "wb200_session_lp_moments",
     "wb200_session_lp_moments_centered", "wb200_session_logp_exceptions",

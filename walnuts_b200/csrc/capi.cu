@@ -10,6 +10,8 @@
 
 #include "../host/config.hpp"
 #include "engine.cuh"
+#include "user_density.cuh"
+#include "user_density.cuh"
 #include "stream.cuh"
 
 namespace wb200 {
@@ -152,6 +154,22 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
       WB200_CUDA(cudaMemsetAsync(s->tparam.ptr, 0, s->ld * 8, s->stream));
       WB200_CUDA(cudaMemcpyAsync(s->tparam.ptr, prec, s->D * 8,
                                  cudaMemcpyHostToDevice, s->stream));
+    } else if (s->kind == kDeviceSource) {
+      // the caller's density as CUDA source, compiled into the chain-resident kernel
+      if (!model->data0) throw std::invalid_argument("kind 5 needs data0 = CUDA source text");
+      if (s->precision != 0) {
+        throw std::invalid_argument("a run-time compiled density runs in fp64");
+      }
+      if (model->N > 0 && !model->data1) {
+        throw std::invalid_argument("kind 5 with N > 0 needs data1 = N parameter doubles");
+      }
+      s->tparam.alloc(std::max<size_t>(model->N, 1));
+      WB200_CUDA(cudaMemsetAsync(s->tparam.ptr, 0, std::max<size_t>(model->N, 1) * 8, s->stream));
+      if (model->N > 0) {
+        WB200_CUDA(cudaMemcpyAsync(s->tparam.ptr, model->data1, model->N * 8,
+                                   cudaMemcpyHostToDevice, s->stream));
+      }
+      s->user = user_module(static_cast<const char*>(model->data0), s->shape, device);
     } else if (s->kind != kStdNormal && s->kind != kFunnel && s->kind != kLogistic &&
                s->kind != kBatchCallback) {
       throw std::invalid_argument("unsupported model kind for the device sampler");
@@ -165,6 +183,10 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
     const bool use_tick = s->kind == kLogistic || s->kind == kBatchCallback ||
                           (eng && std::string(eng) == "tick");
     if (use_tick) {
+      if (s->kind == kDeviceSource) {
+        throw std::invalid_argument("a run-time compiled density runs on the chain-resident "
+                                    "engine (WB200_ENGINE=tick is set)");
+      }
       if (s->precision == 1) {
         throw std::invalid_argument("fp32 mode is implemented by the chain-resident kernel "
                                     "(element-wise targets); the lock-step engine is fp64");
@@ -176,7 +198,16 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
     }
     // slots: resident groups of the chain kernel
     int occ_adapt = 1, occ_sample = 1;
-    occupancy_for(s->kind, s->shape, s->ld, s->precision, &occ_adapt, &occ_sample);
+    if (s->kind == kDeviceSource) {
+      const size_t dyn = static_cast<size_t>(s->shape.chains_per_cta) *
+                         chain_smem_doubles(s->ld) * sizeof(double);
+      occ_adapt = std::min(user_blocks_per_sm(s->user->adapt, s->shape.cta, dyn),
+                           user_blocks_per_sm(s->user->adapt_free, s->shape.cta, dyn));
+      occ_sample = std::min(user_blocks_per_sm(s->user->sample, s->shape.cta, dyn),
+                            user_blocks_per_sm(s->user->sample_free, s->shape.cta, dyn));
+    } else {
+      occupancy_for(s->kind, s->shape, s->ld, s->precision, &occ_adapt, &occ_sample);
+    }
     int sms = 0;
     WB200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const int need = (s->C + s->shape.chains_per_cta - 1) / s->shape.chains_per_cta;
@@ -639,8 +670,20 @@ int wb200_orbit(const WalnutModelDesc* model, size_t num_chains,
       WB200_CUDA(cudaMemset(tp.ptr, 0, ld * 8));
       WB200_CUDA(cudaMemcpy(tp.ptr, model->data0, D * 8, cudaMemcpyHostToDevice));
     }
+    std::shared_ptr<UserModule> user;
+    if (model->kind == kDeviceSource) {
+      if (!model->data0) throw std::invalid_argument("kind 5 needs data0 = CUDA source text");
+      int device = 0;
+      WB200_CUDA(cudaGetDevice(&device));
+      user = user_module(static_cast<const char*>(model->data0), shape, device);
+      tp.alloc(std::max<size_t>(model->N, 1));
+      if (model->N > 0) {
+        WB200_CUDA(cudaMemcpy(tp.ptr, model->data1, model->N * 8, cudaMemcpyHostToDevice));
+      }
+    }
     launch_orbit(model->kind, model->precision, D, ld, static_cast<int>(C), tp.ptr, th.ptr, rh.ptr,
-                 im.ptr, g.ptr, lp.ptr, jt.ptr, step, num_steps, st);
+                 im.ptr, g.ptr, lp.ptr, jt.ptr, step, num_steps, st,
+                 user ? user->orbit : nullptr);
     download_rows(theta_out, D, th.ptr, ld, C, st);
     download_rows(rho_out, D, rh.ptr, ld, C, st);
     download_rows(grad_out, D, g.ptr, ld, C, st);

@@ -30,8 +30,14 @@
 // bit; only cross-element sums (logp, kinetic energy, U-turn dots) differ, by
 // summation order.
 #pragma once
+#if defined(__CUDACC_RTC__)
+// run-time compilation of a user density (user_density.cu): no host headers
+using uint32_t = unsigned int;
+using uint64_t = unsigned long long;
+#else
 #include <cstdint>
 #include <cuda_runtime.h>
+#endif
 
 #if !defined(__CUDACC__)
 // g++ build of the very same state machine for tests/host_emu (one emulated
@@ -88,7 +94,7 @@ __device__ __forceinline__ double metric_from_sums(double S_draw, double S_score
 }
 
 enum TargetKind : int { kStdNormal = 0, kDiagGaussian = 1, kFunnel = 2,
-                        kLogistic = 3, kBatchCallback = 4 };
+                        kLogistic = 3, kBatchCallback = 4, kDeviceSource = 5 };
 
 // persistent per-chain scalars (SoA would not help: one group reads one record)
 struct ChainScalars {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -138,7 +139,7 @@ inline void download_rows(double* dst, int D, const double* src, int ld, size_t 
 
 }  // namespace wb200
 
-namespace wb200 { struct TickEngine; struct StreamState; }
+namespace wb200 { struct TickEngine; struct StreamState; struct UserModule; }
 
 struct wb200_session {
   int device = 0;
@@ -173,6 +174,7 @@ struct wb200_session {
   wb200::DeviceBuffer<long long> iter_stats;  // {min, max, sum} of per-chain iteration counts, total evals
   wb200::TickEngine* tick = nullptr;  // lock-step engine (logistic; WB200_ENGINE=tick)
   wb200::StreamState* acc = nullptr;  // streaming summary accumulators (stream.cu)
+  std::shared_ptr<wb200::UserModule> user;  // kind 5: the run-time compiled kernels
 
   wb200::ChainParams params(int n_iter, int adapt, bool store);
   long long* acc_rows();  // device [C]: staged rows per chain of the streaming block
@@ -204,10 +206,11 @@ void stream_update(wb200_session& s, const long long* rows_c, long long rows_uni
 void stream_flush(wb200_session& s);
 void tick_abort_inflight(wb200_session& s);
 unsigned long long tick_count(const wb200_session& s);
+// user_orbit: the orbit kernel of a run-time compiled density (kind 5), else null
 void launch_orbit(int kind, int precision, int D, int ld, int C, const double* tparam,
                   double* theta, double* rho, const double* inv_mass, double* grad,
                   double* logp, double* joint, double step, int num_steps,
-                  cudaStream_t stream);
+                  cudaStream_t stream, void* user_orbit = nullptr);
 void device_rhat_moments(const double* draws, int ld, int D,
                          const std::vector<long long>& start,
                          const std::vector<long long>& len, double* moments_host,

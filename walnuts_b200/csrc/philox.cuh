@@ -14,7 +14,9 @@
 //   kind 2  initial positions (config.hpp:259-268)
 //   kind 3  momentum for the initial step-size search (util.hpp:290-293)
 #pragma once
+#if !defined(__CUDACC_RTC__)
 #include <cstdint>
+#endif
 
 namespace wb200 {
 

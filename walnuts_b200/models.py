@@ -14,7 +14,8 @@ import numpy as np
 
 from ._ffi import WalnutModelDesc
 
-KINDS = {"std_normal": 0, "diag_gaussian": 1, "funnel": 2, "logistic": 3, "batch_callback": 4}
+KINDS = {"std_normal": 0, "diag_gaussian": 1, "funnel": 2, "logistic": 3, "batch_callback": 4,
+         "device_source": 5}
 
 # WB200_BATCH_LOGP_GRAD (include/walnuts_b200.h): num_chains, num_params, ld, theta, grad,
 # lp (device pointers), cuda_stream, data -> 0 on success
@@ -31,6 +32,8 @@ class DeviceModel:
     X: Optional[np.ndarray] = None           # logistic: [N][D]
     y: Optional[np.ndarray] = None           # logistic: [N]
     callback: Optional[object] = None        # batch_callback: a BATCH_LOGP_GRAD instance
+    source: Optional[str] = None             # device_source: CUDA source text
+    params: Optional[np.ndarray] = None      # device_source: the density's parameters
     dtype: str = "f64"                       # "f32": fp32 mode (element-wise targets)
     errors: list = field(default_factory=list, repr=False)  # exceptions raised inside it
     _keep: list = field(default_factory=list, repr=False)
@@ -56,6 +59,16 @@ class DeviceModel:
             d.data1 = y.ctypes.data
         elif self.kind == "batch_callback":
             d.data0 = ctypes.cast(self.callback, ctypes.c_void_p).value
+        elif self.kind == "device_source":
+            if self.dtype != "f64":
+                raise ValueError("a run-time compiled density runs in fp64")
+            src = ctypes.create_string_buffer(self.source.encode())
+            par = np.ascontiguousarray(
+                self.params if self.params is not None else np.zeros(0), dtype=np.float64)
+            self._keep += [src, par]
+            d.N = par.size
+            d.data0 = ctypes.cast(src, ctypes.c_void_p).value
+            d.data1 = par.ctypes.data if par.size else None
         return d
 
 
@@ -160,3 +173,22 @@ def torch_density(num_params: int, logp_fn, grad_fn=None) -> DeviceModel:
             lp.copy_(value.detach().reshape(C))
 
     return batch_callback(num_params, fn)
+
+
+def device_source(source: str, num_params: int, params=None) -> DeviceModel:
+    """The caller's own density as CUDA source, compiled at run time into the
+    chain-resident kernel (model kind 5, include/walnuts_b200.h) -- the device counterpart
+    of handing the reference a ``logp`` callable (pyfunc.py:45-83).  Element-wise densities
+    define ``__device__ void wb200_logp_grad(int d, double x, const double* par, double& lp,
+    double& g)``; ``params`` reaches it as ``par``."""
+    return DeviceModel("device_source", int(num_params), source=str(source),
+                       params=None if params is None else np.asarray(params, np.float64))
+
+
+def compile_device_source(source: str, num_params: int) -> str:
+    """Compile only (no GPU needed); returns the compiler's output, raises ``ValueError``
+    with its log if the source does not compile."""
+    from . import _ffi
+    log = ctypes.create_string_buffer(1 << 16)
+    _ffi.compile_device_source(source.encode(), int(num_params), log, len(log))
+    return log.value.decode()
