@@ -765,7 +765,7 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
             # transitions x 4096 chains) from the committed ncu --set full capture
             "traffic": (instr_per_eval("c2_sampling") or {}).get("dram_bytes_per_launch")
             if name == "c2" and ips == 10 and C == 4096 else None,
-            "traffic_source": "profiles/r2_ncu_chain_kernel_sampling_c2.csv",
+            "traffic_source": "profiles/r2_ncu_chain_sampling_c2.csv",
             "peak_source": peak_src,
             "kernel": wl["kernel"],
             "algorithmic_bytes_per_eval": alg_bytes,

@@ -22,6 +22,7 @@ LaunchShape shape_for_dim(int D) {
     // WB200_SHAPE_1024=256x2 selects the 8-warp variant (experiments)
     const char* e = std::getenv("WB200_SHAPE_1024");
     if (e && std::string(e) == "256x2") return {256, 2, 256, 1};
+    if (e && std::string(e) == "64x8") return {64, 8, 64, 1};
     return {128, 4, 128, 1};
   }
   if (D <= 2048) return {256, 4, 256, 1};

@@ -24,7 +24,8 @@ namespace wb200 {
   do {                                                                         \
     if ((S).T == 32 && (S).K == 1) { MACRO(TARGET, 32, 1, 128, 4, 4); }        \
     else if ((S).T == 32 && (S).K == 2) { MACRO(TARGET, 32, 2, 128, WB200_MINB_32X2, WB200_MINB_32X2); } \
-    else if ((S).T == 64) { MACRO(TARGET, 64, 2, 64, 6, 6); }                  \
+    else if ((S).T == 64 && (S).K == 2) { MACRO(TARGET, 64, 2, 64, 6, 6); }    \
+    else if ((S).T == 64) { MACRO(TARGET, 64, 8, 64, 4, 4); }                  \
     else if ((S).T == 128 && (S).K == 2) { MACRO(TARGET, 128, 2, 128, 3, 3); } \
     else if ((S).T == 128 && (S).K == 4) { MACRO(TARGET, 128, 4, 128, WB200_MINB_128X4_ADAPT, WB200_MINB_128X4); } \
     else if ((S).T == 256 && (S).K == 2) { MACRO(TARGET, 256, 2, 256, 2, 2); } \
@@ -40,7 +41,8 @@ namespace wb200 {
   do {                                                                         \
     if ((S).T == 32 && (S).K == 1) { MACRO(TARGET, 32, 1, 128, 4, 4); }        \
     else if ((S).T == 32 && (S).K == 2) { MACRO(TARGET, 32, 2, 128, 4, 4); }   \
-    else if ((S).T == 64) { MACRO(TARGET, 64, 2, 64, 6, 8); }                  \
+    else if ((S).T == 64 && (S).K == 2) { MACRO(TARGET, 64, 2, 64, 6, 8); }    \
+    else if ((S).T == 64) { MACRO(TARGET, 64, 8, 64, 4, 6); }                  \
     else if ((S).T == 128 && (S).K == 2) { MACRO(TARGET, 128, 2, 128, 4, 5); } \
     else if ((S).T == 128 && (S).K == 4) { MACRO(TARGET, 128, 4, 128, 4, WB200_MINB_128X4_F32); } \
     else if ((S).T == 256 && (S).K == 2) { MACRO(TARGET, 256, 2, 256, 2, 2); } \
