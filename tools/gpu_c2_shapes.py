@@ -12,7 +12,9 @@ import walnuts_b200 as wb  # noqa: E402
 
 D, C = 1000, 4096
 var = 10.0 ** (4 * np.arange(D) / (D - 1))
-with wb.Session(wb.models.diag_gaussian(var), C, seed=1, max_trajectory_doublings=10) as s:
+model = (wb.models.std_normal(D) if os.environ.get("WB200_TEST_MODEL") == "std_normal"
+         else wb.models.diag_gaussian(var))
+with wb.Session(model, C, seed=1, max_trajectory_doublings=10) as s:
     s.init(init_radius=2.0)
     s.reserve(10)
     c0 = s.counters()
