@@ -183,6 +183,12 @@ int wb200_session_create(const WalnutModelDesc* model, size_t num_chains,
     const bool use_tick = s->kind == kLogistic || s->kind == kBatchCallback ||
                           (eng && std::string(eng) == "tick");
     if (use_tick) {
+      // WB200_TICK_SHAPE=64x4: two warps per chain with eight elements per thread for
+      // 256 < D <= 512 on the lock-step engine (experiments; default four warps x four)
+      const char* tshape = std::getenv("WB200_TICK_SHAPE");
+      if (tshape && std::string(tshape) == "64x4" && s->D > 256 && s->D <= 512) {
+        s->shape = LaunchShape{64, 4, 64, 1};
+      }
       if (s->kind == kDeviceSource) {
         throw std::invalid_argument("a run-time compiled density runs on the chain-resident "
                                     "engine (WB200_ENGINE=tick is set)");

@@ -47,7 +47,8 @@ struct TickEngine {
   do {                                                                         \
     if ((S).T == 32 && (S).K == 1) { MACRO(32, 1, 128); }                      \
     else if ((S).T == 32 && (S).K == 2) { MACRO(32, 2, 128); }                 \
-    else if ((S).T == 64) { MACRO(64, 2, 64); }                                \
+    else if ((S).T == 64 && (S).K == 2) { MACRO(64, 2, 64); }                  \
+    else if ((S).T == 64) { MACRO(64, 4, 64); }                                \
     else if ((S).T == 128 && (S).K == 2) { MACRO(128, 2, 128); }               \
     else if ((S).T == 128 && (S).K == 4) { MACRO(128, 4, 128); }               \
     else if ((S).T == 256 && (S).K == 2) { MACRO(256, 2, 256); }               \
