@@ -59,7 +59,7 @@ COND = 1e4
 WARMUP_ITERS = 300
 MAX_DOUBLINGS = 10
 MAX_HALVINGS = 5
-SEED = 20250
+SEED = int(os.environ.get("WB200_BENCH_SEED", "20250"))  # (env: A/B experiments)
 ALG_BYTES_PER_EVAL = 7 * D * 8  # read theta, rho, grad, M^-1; write theta, rho, grad
 
 # element-wise workloads of run_ours / the reference arm.  c2 is the default line; c3
@@ -387,6 +387,9 @@ def bench_logistic(args, comm, strong, K, W, warmup_ticks, chains=None, cpu_leg=
         "min_ess": float(np.min(summ["ess"])),
         "min_ess_per_sec": float(np.min(summ["ess"])) / (total_ms * 1e-3 * (W + K) / K),
         "max_r_hat": float(np.max(summ["r_hat"])),
+        "median_r_hat": float(np.median(summ["r_hat"])),
+        "r_hat_quantiles_50_90_99": [float(q) for q in np.quantile(summ["r_hat"],
+                                                                   [0.5, 0.9, 0.99])],
         "summary_phase": {"seconds": summary_s, "chains": total, "draws": draws_total,
                           "payload_doubles": (2 * Dm + 3) + (3 + 32) * Dm,
                           "collective": ("NCCL all-reduce x2 (SUM) + MIN" if comm.on
