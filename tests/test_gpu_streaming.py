@@ -204,16 +204,19 @@ def test_cross_rank_streamed_summaries_equal_one_session_with_all_chains(tmp_pat
     assert two[0] == two[1]       # identical on every rank
 
 
-def test_multi_device_one_shot_call_equals_the_single_device_call(wb, oracle, monkeypatch):
+@pytest.mark.parametrize("blocks", ["free-running", "uniform"])
+def test_multi_device_one_shot_call_equals_the_single_device_call(wb, oracle, monkeypatch,
+                                                                  blocks):
     """walnutpie_sample_device_multi (one call, one host thread per GPU, controllers and
     summaries all-reduced by NCCL inside the library) against walnutpie_sample_device_summary
     on one device: same stop iterations, same per-chain step sizes and metrics, summaries
     equal to 1e-8 -- with early stopping enabled, so the all-reduced controllers decide.
-    On a single-GPU box the multi-device call runs with one device (no NCCL).  The
-    multi-device call advances all chains by blocks of equal iteration counts; the
-    single-device call is put in the same mode (its default is free-running chains)."""
+    On a single-GPU box the multi-device call runs with one device (no NCCL).  Both block
+    modes: free-running (default; budgets from the all-reduced totals, per-chain lengths)
+    and blocks of equal iteration counts."""
     import torch
-    monkeypatch.setenv("WB200_BLOCKS", "uniform")
+    if blocks == "uniform":
+        monkeypatch.setenv("WB200_BLOCKS", "uniform")
     D, C = 16, 48
     model = wb.models.diag_gaussian(np.linspace(0.3, 5.0, D))
     kw = dict(min_warmup_iter=20, max_warmup_iter=300, min_sampling_iter=40,
@@ -226,6 +229,11 @@ def test_multi_device_one_shot_call_equals_the_single_device_call(wb, oracle, mo
     print(f"\n{ndev} device(s): sampling stopped at {many['sampling_iters']} iterations, "
           f"min ESS {many['ess'].min():.1f}")
     assert many["sampling_iters"] == one["sampling_iters"]
+    np.testing.assert_array_equal(many["sampling_lengths"], one["sampling_lengths"])
+    if blocks == "uniform":
+        assert len(set(one["sampling_lengths"])) == 1
+    else:
+        assert one["sampling_lengths"].max() > one["sampling_lengths"].min()
     np.testing.assert_array_equal(many["stepsize"], one["stepsize"])
     np.testing.assert_array_equal(many["inv_metric"], one["inv_metric"])
     for k in ("mean", "variance", "r_hat", "ess", "mcse"):

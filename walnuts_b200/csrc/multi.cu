@@ -17,6 +17,8 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <atomic>
 #include <condition_variable>
 #include <cstring>
@@ -195,49 +197,116 @@ void run_rank(Rank& r, Shared& sh, const Args& a, int* warm_done_out, int* samp_
     if (min_iter == max_iter) return std::min(std::max(stride, 20), max_iter - done);
     return std::min(stride, max_iter - done);
   };
+  // Free-running phases (min < max on the chain-resident engine), exactly as in the
+  // single-device call (driver.cu): every chain of every device gets the same budget of
+  // gradient evaluations per block -- worked out from the all-reduced totals, so all
+  // devices compute the same budgets a single device holding all chains would -- and the
+  // controllers read the all-reduced {min, max, sum} of the per-chain iteration counts.
+  const char* blocks_env = std::getenv("WB200_BLOCKS");
+  const bool allow_free =
+      !r.s->tick && !(blocks_env && std::string(blocks_env) == "uniform");
+  double evals_seen = 0, iters_seen = 0;
+  auto free_budget = [&] {
+    const double per_iter = iters_seen > 0 ? evals_seen / iters_seen : 16.0;
+    return std::max<long long>(1, std::llround(per_iter * stride));
+  };
+  auto global_stats = [&](bool sampling, double (&st)[4]) {
+    long long local[4];
+    check(wb200_session_iter_stats(r.s, sampling ? 1 : 0, local, &e), e);
+    double mn = static_cast<double>(local[0]), mx = static_cast<double>(local[1]);
+    double sums2[2] = {static_cast<double>(local[2]), static_cast<double>(local[3])};
+    all_reduce_host(r, sh, &mn, 1, kNcclMin);
+    all_reduce_host(r, sh, &mx, 1, kNcclMax);
+    all_reduce_host(r, sh, sums2, 2, kNcclSum);
+    st[0] = mn; st[1] = mx; st[2] = sums2[0]; st[3] = sums2[1];
+  };
+  auto free_phase = [&](bool sampling, int min_iter, int max_iter, auto&& converged) {
+    double st[4];
+    global_stats(sampling, st);
+    double evals0 = st[3];
+    const double iters_before = iters_seen;
+    const double all_at_max = static_cast<double>(a.num_chains) * max_iter;
+    while (st[2] < all_at_max) {
+      check(wb200_session_run_evals(r.s, sampling ? 1 : 0, free_budget(), max_iter,
+                                    sampling ? 1 : 0, &e), e);
+      if (sh.interrupted.load()) throw wb200::InterruptException();
+      global_stats(sampling, st);
+      evals_seen += st[3] - evals0;
+      evals0 = st[3];
+      iters_seen = iters_before + st[2];
+      if (st[0] >= min_iter && st[2] < all_at_max && converged()) break;
+    }
+    return static_cast<int>(st[1]);
+  };
+  auto chain_counts = [&](std::vector<long long>& out) {  // sampling iterations per chain
+    std::vector<wb200::ChainScalars> h(C);
+    WB200_CUDA(cudaMemcpyAsync(h.data(), r.s->sc.ptr, C * sizeof(wb200::ChainScalars),
+                               cudaMemcpyDeviceToHost, r.s->stream));
+    WB200_CUDA(cudaStreamSynchronize(r.s->stream));
+    out.resize(C);
+    for (size_t c = 0; c < C; ++c) out[c] = static_cast<long long>(h[c].lp_n);
+  };
   // ---- warm-up (adapt.hpp:173-229 over all devices' chains)
   int warm_done = 0;
   wb200::DeviceBuffer<double> sums;
   sums.alloc(static_cast<size_t>(D) + 2);
-  while (warm_done < a.t.max_warmup_iter) {
+  auto warmup_converged = [&] {
+    double dev[2];
+    check(wb200_session_warmup_sums(r.s, sums.ptr, &e), e);
+    all_reduce_device(r, sh, sums.ptr, static_cast<size_t>(D) + 2, kNcclSum);
+    check(wb200_session_warmup_deviation(r.s, sums.ptr, dev, &e), e);
+    all_reduce_host(r, sh, dev, 2, kNcclMax);
+    return dev[0] <= a.t.mass_converge_tol && dev[1] <= a.t.step_size_converge_tol;
+  };
+  const bool free_warm = allow_free && a.t.min_warmup_iter < a.t.max_warmup_iter;
+  if (free_warm) {
+    warm_done = free_phase(false, a.t.min_warmup_iter, a.t.max_warmup_iter, warmup_converged);
+  }
+  while (!free_warm && warm_done < a.t.max_warmup_iter) {
     const int n = block(warm_done, a.t.min_warmup_iter, a.t.max_warmup_iter);
     check(wb200_session_warmup(r.s, n, 0, &e), e);
     warm_done += n;
     if (sh.interrupted.load()) throw wb200::InterruptException();
     if (warm_done >= a.t.min_warmup_iter && warm_done < a.t.max_warmup_iter) {
-      double dev[2];
-      check(wb200_session_warmup_sums(r.s, sums.ptr, &e), e);
-      all_reduce_device(r, sh, sums.ptr, static_cast<size_t>(D) + 2, kNcclSum);
-      check(wb200_session_warmup_deviation(r.s, sums.ptr, dev, &e), e);
-      all_reduce_host(r, sh, dev, 2, kNcclMax);
-      if (dev[0] <= a.t.mass_converge_tol && dev[1] <= a.t.step_size_converge_tol) break;
+      if (warmup_converged()) break;
     }
   }
   check(wb200_session_freeze(r.s, &e), e);
   check(wb200_session_stream_begin(r.s, a.max_lags, &e), e);
   // ---- sampling (sampler.hpp:118-158 over all devices' chains)
   int samp_done = 0;
-  while (samp_done < a.t.max_sampling_iter) {
+  auto sampling_converged = [&] {
+    double m0[4], m[4];
+    check(wb200_session_lp_moments(r.s, m0, &e), e);
+    all_reduce_host(r, sh, m0, 4, kNcclSum);
+    check(wb200_session_lp_moments_centered(r.s, m0[0] / m0[3], m, &e), e);
+    all_reduce_host(r, sh, m, 4, kNcclSum);
+    const double M = m[3];
+    const double r_hat =
+        std::sqrt(1 + ((m[1] - m[0] * m[0] / M) / (M - 1.0)) / (m[2] / M));
+    if (a.refresh != 0) {  // handlers.hpp:164-172
+      std::stringstream ss;
+      ss.precision(10);
+      ss << "Controller: R-hat at " << r_hat << std::endl;
+      say(ss.str());
+    }
+    return r_hat <= a.t.rhat_converge_tol;
+  };
+  const bool free_samp =
+      allow_free && (a.t.min_sampling_iter < a.t.max_sampling_iter || free_warm);
+  std::vector<long long> samp_rows;
+  if (free_samp) {
+    samp_done = free_phase(true, a.t.min_sampling_iter, a.t.max_sampling_iter,
+                           sampling_converged);
+    chain_counts(samp_rows);
+  }
+  while (!free_samp && samp_done < a.t.max_sampling_iter) {
     const int n = block(samp_done, a.t.min_sampling_iter, a.t.max_sampling_iter);
     check(wb200_session_sample(r.s, n, 1, &e), e);
     samp_done += n;
     if (sh.interrupted.load()) throw wb200::InterruptException();
     if (samp_done >= a.t.min_sampling_iter && samp_done < a.t.max_sampling_iter) {
-      double m0[4], m[4];
-      check(wb200_session_lp_moments(r.s, m0, &e), e);
-      all_reduce_host(r, sh, m0, 4, kNcclSum);
-      check(wb200_session_lp_moments_centered(r.s, m0[0] / m0[3], m, &e), e);
-      all_reduce_host(r, sh, m, 4, kNcclSum);
-      const double M = m[3];
-      const double r_hat =
-          std::sqrt(1 + ((m[1] - m[0] * m[0] / M) / (M - 1.0)) / (m[2] / M));
-      if (a.refresh != 0) {  // handlers.hpp:164-172
-        std::stringstream ss;
-        ss.precision(10);
-        ss << "Controller: R-hat at " << r_hat << std::endl;
-        say(ss.str());
-      }
-      if (r_hat <= a.t.rhat_converge_tol) break;
+      if (sampling_converged()) break;
     }
   }
   // ---- posterior summaries over ALL chains (stream.cu phases, two all-reduces)
@@ -259,7 +328,8 @@ void run_rank(Rank& r, Shared& sh, const Args& a, int* warm_done_out, int* samp_
   // ---- per-chain outputs of this shard (walnutpy.cpp:196-221; handlers.hpp:91-100)
   for (size_t c = 0; c < C; ++c) {
     a.final_lengths[r.offset + c] = 0;  // warm-up draws are not saved in this form
-    a.final_lengths[a.num_chains + r.offset + c] = samp_done;
+    a.final_lengths[a.num_chains + r.offset + c] =
+        free_samp ? static_cast<int>(samp_rows[c]) : samp_done;
   }
   check(wb200_session_get_state(
             r.s, nullptr, a.inv_metric_out ? a.inv_metric_out + r.offset * D : nullptr,
