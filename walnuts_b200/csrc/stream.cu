@@ -28,12 +28,50 @@ namespace wb200 {
 constexpr int kStreamTB = 128;  // dimensions per block
 
 // Fold `rows` new draws of every chain (staging rows row0 .. row0+rows) into its sums.
+// One thread owns one (chain, dimension) series: its T lag accumulators AND the window of
+// its last T values stay in registers.  The window is held in order of recency
+// (w[k] = the value k + 1 positions back), so every index below is a compile-time
+// constant: rows are processed in groups of kStreamGroup whose members meet each other as
+// ys[r - t] and older values as w[t - r - 1]; the window then shifts by the group size.
+// (The first version kept the window in shared memory under its absolute position mod T:
+// 31 shared loads per row and thread made the fold shared-memory bound -- 2.8 ms for 50
+// rows of 4096 x 1000 series against 0.35 ms of fp64 FMAs.)  Accumulation order per lag is
+// the row order, as before: bitwise the same sums.  `tail` keeps its layout in memory
+// (slot = position mod T), which the summary kernels read.
+constexpr int kStreamGroup = 8;
+
+template <int T, int G>
+__device__ __forceinline__ void stream_fold_rows(const double* x, long long ld, double r,
+                                                 double (&acc)[T], double (&w)[T], double& s1,
+                                                 long long i0, double* head_cd, long long hstride) {
+  double ys[G];
+#pragma unroll
+  for (int q = 0; q < G; ++q) {
+    const double y = x[q * ld] - r;
+    ys[q] = y;
+    s1 += y;
+    acc[0] += y * y;
+#pragma unroll
+    for (int t = 1; t < T; ++t) {
+      // (lags that reach back before the start of the chain are skipped, not multiplied
+      // by the window's zeros: a non-finite draw must not leak into them)
+      const double partner = t <= q ? ys[q - t] : w[t - q - 1];
+      if (t <= i0 + q) acc[t] += y * partner;
+    }
+    if (i0 + q < T) head_cd[(i0 + q) * hstride] = y;
+  }
+  // shift by G: the group's values become the most recent ones
+#pragma unroll
+  for (int k = T - 1; k >= 0; --k) {
+    w[k] = k < G ? ys[G - 1 - k] : w[k - G];
+  }
+}
+
 template <int T>
 __global__ void __launch_bounds__(kStreamTB)
 stream_update_kernel(const double* draws, long long draw_cap, int ld, const long long* rows_c,
                      long long rows_uniform, long long row0, const long long* n_c, double* ref,
                      double* S1, double* P, double* head, double* tail) {
-  __shared__ double win[T * kStreamTB];  // the last T values of this thread's series
   const int tx = threadIdx.x;
   const int d = blockIdx.y * kStreamTB + tx;
   const int c = blockIdx.x;  // chains on the x dimension of the grid: no 65 535 limit
@@ -50,32 +88,29 @@ stream_update_kernel(const double* draws, long long draw_cap, int ld, const long
   } else {
     r = ref[cd];
   }
-  double acc[T];
-  const long long have = n0 < T ? n0 : T;
+  double acc[T], w[T];
+  const long long lanes = static_cast<long long>(c) * T * ld + d;  // + t * ld
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    const long long o = (static_cast<long long>(c) * T + t) * ld + d;
-    acc[t] = n0 > 0 ? P[o] : 0.0;
-    win[t * kStreamTB + tx] = t < have ? tail[o] : 0.0;
+    acc[t] = n0 > 0 ? P[lanes + static_cast<long long>(t) * ld] : 0.0;
+    // w[t] = the value at position n0 - 1 - t (slot (n0 - 1 - t) mod T of `tail`)
+    const long long pos = n0 - 1 - t;
+    w[t] = pos >= 0 ? tail[lanes + (pos & (T - 1)) * ld] : 0.0;
   }
   double s1 = n0 > 0 ? S1[cd] : 0.0;
-  for (long long j = 0; j < B; ++j) {
-    const long long i = n0 + j;
-    const double y = x[j * ld] - r;
-    s1 += y;
-    acc[0] += y * y;
-#pragma unroll
-    for (int t = 1; t < T; ++t) {
-      if (t <= i) acc[t] += y * win[static_cast<int>((i - t) & (T - 1)) * kStreamTB + tx];
-    }
-    win[static_cast<int>(i & (T - 1)) * kStreamTB + tx] = y;
-    if (i < T) head[(static_cast<long long>(c) * T + i) * ld + d] = y;
+  long long j = 0;
+  for (; j + kStreamGroup <= B; j += kStreamGroup) {
+    stream_fold_rows<T, kStreamGroup>(x + j * ld, ld, r, acc, w, s1, n0 + j, head + lanes, ld);
   }
+  for (; j < B; ++j) {
+    stream_fold_rows<T, 1>(x + j * ld, ld, r, acc, w, s1, n0 + j, head + lanes, ld);
+  }
+  const long long n1 = n0 + B;
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    const long long o = (static_cast<long long>(c) * T + t) * ld + d;
-    P[o] = acc[t];
-    tail[o] = win[t * kStreamTB + tx];
+    P[lanes + static_cast<long long>(t) * ld] = acc[t];
+    const long long pos = n1 - 1 - t;  // the T most recent positions, each to its slot
+    if (pos >= 0) tail[lanes + (pos & (T - 1)) * ld] = w[t];
   }
   S1[cd] = s1;
 }
@@ -103,45 +138,82 @@ __global__ void stream_chain_stats_kernel(const long long* n_c, int ld, int D, i
       (P[(static_cast<long long>(c) * T) * ld + d] - nn * my * my) / (nn - 1.0);
 }
 
-// phase 1: out[d] = sum_k mu_k, out[D + d] = sum_k n_k mu_k  (chains with n >= 3)
-__global__ void stream_phase1_kernel(const long long* n_c, int C, int D, const double* mu,
-                                     double* out) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D) return;
-  double a = 0.0, b = 0.0;
-  for (int c = 0; c < C; ++c) {
-    const long long n = n_c[c];
-    if (n < 3) continue;
-    const double m = mu[static_cast<long long>(c) * D + d];
-    a += m;
-    b += static_cast<double>(n) * m;
+// Cross-chain sums per dimension, in two deterministic stages: blocks of 32 dimensions x 8
+// chain lanes sum a chunk of the chains each (lanes combined in lane order through shared
+// memory) into part[chunk][v][D]; stream_combine_kernel adds the chunks in chunk order.
+// (One thread per dimension walking all chains took 1.9 + 2.4 ms at c2 and most of the
+// 30 ms summary phase at c3, where D = 100 leaves 100 threads for 16 384 chains.)
+constexpr int kSumDims = 32, kSumLanes = 8;
+
+template <int NV>
+__device__ __forceinline__ void stream_block_sums(double (&v)[NV], int D, int d, double* part) {
+  __shared__ double sh[kSumLanes][NV][kSumDims];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) sh[threadIdx.y][k][threadIdx.x] = v[k];
+  __syncthreads();
+  if (threadIdx.y == 0 && d < D) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double a = sh[0][k][threadIdx.x];
+#pragma unroll
+      for (int l = 1; l < kSumLanes; ++l) a += sh[l][k][threadIdx.x];
+      part[(static_cast<long long>(blockIdx.y) * NV + k) * D + d] = a;
+    }
   }
-  out[d] = a;
-  out[D + d] = b;
 }
 
-// phase 2, centred: out[d] = sum_k (mu_k - mbar)^2, out[D + d] = sum_k s2_k,
-// out[2D + d] = sum_k [(n_k - 1) s2_k + n_k (mu_k - pm)^2]
-__global__ void stream_phase2_kernel(const long long* n_c, int C, int D, const double* mu,
-                                     const double* s2, const double* mbar, const double* pm,
-                                     double* out) {
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D) return;
-  double q = 0.0, w = 0.0, ss = 0.0;
-  const double mb = mbar[d], p = pm[d];
-  for (int c = 0; c < C; ++c) {
-    const long long n = n_c[c];
-    if (n < 3) continue;
-    const double nn = static_cast<double>(n);
-    const double m = mu[static_cast<long long>(c) * D + d];
-    const double v = s2[static_cast<long long>(c) * D + d];
-    q += (m - mb) * (m - mb);
-    w += v;
-    ss += (nn - 1.0) * v + nn * (m - p) * (m - p);
+__global__ void stream_combine_kernel(int chunks, int total, const double* part, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // total = NV * D
+  if (i >= total) return;
+  double a = 0.0;
+  for (int b = 0; b < chunks; ++b) a += part[static_cast<long long>(b) * total + i];
+  out[i] = a;
+}
+
+// phase 1: sums of mu_k and n_k mu_k over the chains with n >= 3
+__global__ void __launch_bounds__(kSumDims * kSumLanes)
+stream_phase1_kernel(const long long* n_c, int C, int D, int chains_per_chunk,
+                     const double* mu, double* part) {
+  const int d = blockIdx.x * kSumDims + threadIdx.x;
+  const int c0 = blockIdx.y * chains_per_chunk;
+  const int c1 = min(C, c0 + chains_per_chunk);
+  double v[2] = {0.0, 0.0};
+  if (d < D) {
+    for (int c = c0 + threadIdx.y; c < c1; c += kSumLanes) {
+      const long long n = n_c[c];
+      if (n < 3) continue;
+      const double m = mu[static_cast<long long>(c) * D + d];
+      v[0] += m;
+      v[1] += static_cast<double>(n) * m;
+    }
   }
-  out[d] = q;
-  out[D + d] = w;
-  out[2 * D + d] = ss;
+  stream_block_sums<2>(v, D, d, part);
+}
+
+// phase 2, centred: sum_k (mu_k - mbar)^2, sum_k s2_k,
+// sum_k [(n_k - 1) s2_k + n_k (mu_k - pm)^2]
+__global__ void __launch_bounds__(kSumDims * kSumLanes)
+stream_phase2_kernel(const long long* n_c, int C, int D, int chains_per_chunk,
+                     const double* mu, const double* s2, const double* mbar,
+                     const double* pm, double* part) {
+  const int d = blockIdx.x * kSumDims + threadIdx.x;
+  const int c0 = blockIdx.y * chains_per_chunk;
+  const int c1 = min(C, c0 + chains_per_chunk);
+  double v[3] = {0.0, 0.0, 0.0};
+  if (d < D) {
+    const double mb = mbar[d], p = pm[d];
+    for (int c = c0 + threadIdx.y; c < c1; c += kSumLanes) {
+      const long long n = n_c[c];
+      if (n < 3) continue;
+      const double nn = static_cast<double>(n);
+      const double m = mu[static_cast<long long>(c) * D + d];
+      const double var = s2[static_cast<long long>(c) * D + d];
+      v[0] += (m - mb) * (m - mb);
+      v[1] += var;
+      v[2] += (nn - 1.0) * var + nn * (m - p) * (m - p);
+    }
+  }
+  stream_block_sums<3>(v, D, d, part);
 }
 
 // macov[t * D + d] += sum over this block's chains of acov_k(t)
@@ -335,10 +407,17 @@ void stream_phase1(wb200_session& s, double* out_host) {
   const int D = s.D;
   stream_flush(s);
   stream_chain_stats(s);
-  DeviceBuffer<double> out;
+  DeviceBuffer<double> out, part;
   out.alloc(2 * static_cast<size_t>(D));
-  stream_phase1_kernel<<<(D + 127) / 128, 128, 0, s.stream>>>(st.n.ptr, s.C, D,
-                                                                      st.mu.ptr, out.ptr);
+  const int chunks = std::max(1, std::min(128, (s.C + 63) / 64));
+  const int per_chunk = (s.C + chunks - 1) / chunks;
+  part.alloc(static_cast<size_t>(chunks) * 2 * D);
+  stream_phase1_kernel<<<dim3((D + kSumDims - 1) / kSumDims, chunks),
+                         dim3(kSumDims, kSumLanes), 0, s.stream>>>(
+      st.n.ptr, s.C, D, per_chunk, st.mu.ptr, part.ptr);
+  WB200_CUDA(cudaGetLastError());
+  stream_combine_kernel<<<(2 * D + 127) / 128, 128, 0, s.stream>>>(chunks, 2 * D, part.ptr,
+                                                                    out.ptr);
   WB200_CUDA(cudaGetLastError());
   WB200_CUDA(cudaMemcpyAsync(out_host, out.ptr, 2 * D * 8, cudaMemcpyDeviceToHost,
                              s.stream));
@@ -363,8 +442,16 @@ void stream_phase2(wb200_session& s, const double* reduced1, double* out_host) {
                              s.stream));
   WB200_CUDA(cudaMemsetAsync(out.ptr, 0, out.count * 8, s.stream));
   if (st.mu.count == 0) stream_chain_stats(s);
-  stream_phase2_kernel<<<(D + 127) / 128, 128, 0, s.stream>>>(
-      st.n.ptr, s.C, D, st.mu.ptr, st.s2.ptr, cen.ptr, cen.ptr + D, out.ptr);
+  DeviceBuffer<double> part;
+  const int chunks = std::max(1, std::min(128, (s.C + 63) / 64));
+  const int per_chunk = (s.C + chunks - 1) / chunks;
+  part.alloc(static_cast<size_t>(chunks) * 3 * D);
+  stream_phase2_kernel<<<dim3((D + kSumDims - 1) / kSumDims, chunks),
+                         dim3(kSumDims, kSumLanes), 0, s.stream>>>(
+      st.n.ptr, s.C, D, per_chunk, st.mu.ptr, st.s2.ptr, cen.ptr, cen.ptr + D, part.ptr);
+  WB200_CUDA(cudaGetLastError());
+  stream_combine_kernel<<<(3 * D + 127) / 128, 128, 0, s.stream>>>(chunks, 3 * D, part.ptr,
+                                                                    out.ptr);
   WB200_CUDA(cudaGetLastError());
   const int cpb = 32;
   const dim3 grid((s.C + cpb - 1) / cpb, (D + kStreamTB - 1) / kStreamTB);

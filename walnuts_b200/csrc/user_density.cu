@@ -191,6 +191,13 @@ Shape4 shape4_for(const wb200::LaunchShape& sh) {
 
 std::mutex g_cache_mutex;
 std::map<std::string, std::shared_ptr<wb200::UserModule>> g_cache;
+// compiled once per (launch shape, source), loaded once per device
+struct Compiled {
+  std::vector<char> cubin;
+  std::vector<std::string> lowered;
+  std::string log;
+};
+std::map<std::string, std::shared_ptr<Compiled>> g_compiled;
 
 }  // namespace
 
@@ -275,14 +282,22 @@ std::vector<char> user_compile(const char* source, const LaunchShape& shape,
 
 std::shared_ptr<UserModule> user_module(const char* source, const LaunchShape& shape,
                                         int device) {
-  std::stringstream key;
-  key << device << ":" << shape.T << "x" << shape.K << ":" << source;
+  std::stringstream ckey, key;
+  ckey << shape.T << "x" << shape.K << ":" << source;
+  key << device << ":" << ckey.str();
   std::lock_guard<std::mutex> lock(g_cache_mutex);
   auto it = g_cache.find(key.str());
   if (it != g_cache.end()) return it->second;
-  std::vector<std::string> low;
+  std::shared_ptr<Compiled>& comp = g_compiled[ckey.str()];
+  if (!comp) {
+    auto c = std::make_shared<Compiled>();
+    c->cubin = user_compile(source, shape, &c->lowered, &c->log);
+    comp = c;
+  }
+  const std::vector<std::string>& low = comp->lowered;
+  const std::vector<char>& cubin = comp->cubin;
   auto m = std::make_shared<UserModule>();
-  const std::vector<char> cubin = user_compile(source, shape, &low, &m->log);
+  m->log = comp->log;
   Driver& d = driver();
   WB200_CUDA(cudaSetDevice(device));
   WB200_CUDA(cudaFree(nullptr));  // the primary context exists and is current
