@@ -401,7 +401,12 @@ static int sample_device_impl(
     check(wb200_session_create(model, C, run_seed, 0, &t, device, &s, &e), e);
     check(wb200_session_init(s, inits, init_radius, init_inv_metric, nullptr, &e), e);
     // summaries-only: the draw buffer is a staging block folded into running sums
-    const long long stage_rows = std::min<long long>(std::max(max_sampling_iter, 1), 50);
+    // (as many rows as fit in 6 GB, at least 50: every fold of the staging block reads and
+    // writes the chains' lag accumulators -- 4 GB at c2 -- so fewer, larger folds are cheaper)
+    const long long row_bytes = static_cast<long long>(C) * s->ld * 8;
+    const long long stage_rows = std::min<long long>(
+        std::max(max_sampling_iter, 1),
+        std::max<long long>(50, std::min<long long>(1000, (6ll << 30) / row_bytes)));
     check(wb200_session_reserve_draws(
               s, so ? stage_rows : static_cast<long long>(rows_per_chain), 0, &e), e);
 

@@ -41,13 +41,13 @@ constexpr int kStreamTB = 128;  // dimensions per block
 constexpr int kStreamGroup = 8;
 
 template <int T, int G>
-__device__ __forceinline__ void stream_fold_rows(const double* x, long long ld, double r,
+__device__ __forceinline__ void stream_fold_rows(const double (&xs)[G], double r,
                                                  double (&acc)[T], double (&w)[T], double& s1,
                                                  long long i0, double* head_cd, long long hstride) {
   double ys[G];
 #pragma unroll
   for (int q = 0; q < G; ++q) {
-    const double y = x[q * ld] - r;
+    const double y = xs[q] - r;
     ys[q] = y;
     s1 += y;
     acc[0] += y * y;
@@ -98,12 +98,27 @@ stream_update_kernel(const double* draws, long long draw_cap, int ld, const long
     w[t] = pos >= 0 ? tail[lanes + (pos & (T - 1)) * ld] : 0.0;
   }
   double s1 = n0 > 0 ? S1[cd] : 0.0;
+  // the next group's rows are in flight while this group's products are formed
   long long j = 0;
+  double cur[kStreamGroup], nxt[kStreamGroup];
+  if (kStreamGroup <= B) {
+#pragma unroll
+    for (int q = 0; q < kStreamGroup; ++q) cur[q] = x[q * static_cast<long long>(ld)];
+  }
   for (; j + kStreamGroup <= B; j += kStreamGroup) {
-    stream_fold_rows<T, kStreamGroup>(x + j * ld, ld, r, acc, w, s1, n0 + j, head + lanes, ld);
+    if (j + 2 * kStreamGroup <= B) {
+#pragma unroll
+      for (int q = 0; q < kStreamGroup; ++q) {
+        nxt[q] = x[(j + kStreamGroup + q) * static_cast<long long>(ld)];
+      }
+    }
+    stream_fold_rows<T, kStreamGroup>(cur, r, acc, w, s1, n0 + j, head + lanes, ld);
+#pragma unroll
+    for (int q = 0; q < kStreamGroup; ++q) cur[q] = nxt[q];
   }
   for (; j < B; ++j) {
-    stream_fold_rows<T, 1>(x + j * ld, ld, r, acc, w, s1, n0 + j, head + lanes, ld);
+    const double one[1] = {x[j * static_cast<long long>(ld)]};
+    stream_fold_rows<T, 1>(one, r, acc, w, s1, n0 + j, head + lanes, ld);
   }
   const long long n1 = n0 + B;
 #pragma unroll
