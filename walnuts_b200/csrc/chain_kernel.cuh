@@ -1222,11 +1222,15 @@ struct ChainRunner {
             }
             if (cur_sel == -1) V::store(sv(sb + ST_SEL), ld, tid, th);
             if (cur_sel == -2) copy_row(sv(sb + ST_SEL), s_ths);
-            // every thread stores the same pair (and later reads back a copy of it), so
-            // only a lane that has not yet read the old entry needs to be waited for
+            // one writer; a lane that has not yet read the old entry is waited for (above
+            // one warp the barrier inside merge_decision has done that, and the next read
+            // of the entry lies behind the next reduction's barrier)
             if constexpr (T <= 32) grp.sync();
-            st_logW[sp] = cur_logW;
-            st_lp[sp] = cur_lp;
+            if (tid == 0) {
+              st_logW[sp] = cur_logW;
+              st_lp[sp] = cur_lp;
+            }
+            if constexpr (T <= 32) grp.sync();
             ++sp;
           }
           sub_logW = cur_logW;
@@ -1288,6 +1292,9 @@ struct ChainRunner {
       }
     }
     row_to64(theta_row, sv(A_SEL));
+    // (a one-leaf transition of a one-warp group meets no barrier of its own -- shuffles
+    // only -- between the lanes' reads of the record above and this write)
+    if constexpr (T <= 32) grp.sync();
     if (tid == 0) {
       sc.grad_evals += evals;
       sc.iter = u_iter;
