@@ -299,7 +299,8 @@ int wb200_session_sample_ticks(wb200_session* s, int n_ticks, int store,
  * chains.  wb200_session_freeze abandons the transitions still in flight. */
 int wb200_session_warmup_ticks(wb200_session* s, int n_ticks, int store,
                                WalnutpyError** err);
-/* Chain-resident sessions: the free-running launch with the phase's iteration limit --
+/* The free-running launch with the phase's iteration limit (lock-step sessions: eval_budget
+ * ticks) --
  * sampling = 0 warm-up / 1 sampling; no chain goes beyond iter_cap iterations of the phase
  * in total (<= 0: no limit), as each reference chain stops at max_iter (adapt.hpp:116,
  * sampler.hpp:82).  wb200_session_iter_stats returns stats4 = {min, max, sum} over the

@@ -222,3 +222,38 @@ def test_one_shot_summary_call_reports_ragged_lengths(wb):
     assert lens.max() > lens.min()
     assert out["sampling_iters"] == lens.max()
     assert np.all(np.isfinite(out["mean"])) and np.all(out["ess"] > 0)
+
+
+def test_one_shot_call_runs_free_on_the_lock_step_engine(wb, monkeypatch):
+    """A logistic model (tensor-core gradient, lock-step ticks) with min < max: a block is
+    a budget of ticks, every chain stops on its own, and a chain that has reached max_iter
+    stays stopped; the posterior agrees with the run in blocks of equal iteration counts."""
+    from tests.test_gpu_parity import make_logistic
+    N, D, C = 400, 8, 96
+    X, y = make_logistic(N, D, 3)
+    model = wb.models.logistic(X, y)
+    kw = dict(num_chains=C, seed=6, min_warmup_iter=40, max_warmup_iter=120,
+              min_sampling_iter=30, max_sampling_iter=150, rhat_converge_tol=1.02,
+              mass_converge_tol=0.9, step_size_converge_tol=0.35, max_trajectory_doublings=8)
+    fit = wb.walnuts_device(model, save_warmup=True, **kw)
+    wl = np.array([len(f.warmup.warmup_draws) for f in fit])
+    sl = np.array([len(f) for f in fit])
+    assert wl.min() >= 40 and wl.max() <= 120 and sl.min() >= 30 and sl.max() <= 150
+    assert sl.max() > sl.min() or sl.max() == 150
+    assert wl.max() > wl.min() or wl.max() == 120
+    free = np.concatenate([np.asarray(f) for f in fit])
+    assert np.all(np.isfinite(free))
+    out = wb.walnuts_device_summary(model, **kw)        # the same run, draws streamed
+    np.testing.assert_array_equal(out["sampling_lengths"], sl)
+    np.testing.assert_allclose(out["mean"], free.mean(0), rtol=1e-9, atol=1e-12)
+    monkeypatch.setenv("WB200_BLOCKS", "uniform")
+    uni = wb.walnuts_device(model, **kw)
+    assert len({len(f) for f in uni}) == 1
+    pooled = np.concatenate([np.asarray(f) for f in uni])
+    se = np.sqrt(free.var(0) / 200 + pooled.var(0) / 200)    # generous: ESS >= 200 each
+    assert np.max(np.abs(free.mean(0) - pooled.mean(0)) / se) < 5.0
+    # all chains reach max_iter and stop there
+    fit = wb.walnuts_device(model, num_chains=C, seed=6, min_warmup_iter=20,
+                            max_warmup_iter=20, min_sampling_iter=10, max_sampling_iter=40,
+                            rhat_converge_tol=1.0 + 1e-9)
+    assert {len(f) for f in fit} == {40}

@@ -381,11 +381,25 @@ int wb200_session_run_evals(wb200_session* s, int sampling, long long eval_budge
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));
     if (!s->initialised) throw std::runtime_error("session is not initialised");
-    if (s->tick) throw std::runtime_error("run_evals is the chain-resident engine's "
-                                          "free-running launch; use *_ticks here");
     if (sampling && !s->frozen) throw std::runtime_error("sample before freeze");
     if (!sampling && s->frozen) throw std::runtime_error("warm-up after freeze");
     if (eval_budget <= 0) throw std::invalid_argument("eval_budget must be positive");
+    if (s->tick) {
+      // lock-step engine: a tick is one gradient evaluation of every chain
+      if (eval_budget > 0x7fffffffll) throw std::invalid_argument("eval_budget too large");
+      const int n_ticks = static_cast<int>(eval_budget);
+      if (store && s->draw_cap == 0) throw std::runtime_error("reserve draws first");
+      if (sampling && s->acc && store) {
+        stream_flush(*s);
+        tick_run_ticks(*s, n_ticks, 0, true, iter_cap);
+        tick_take_rows(*s, s->acc_rows());
+        stream_update(*s, s->acc_rows(), 0);
+        return;
+      }
+      tick_run_ticks(*s, n_ticks, sampling ? 0 : 1, store != 0, iter_cap);
+      if (store) s->ragged = true;
+      return;
+    }
     chain_free_run(s, eval_budget, iter_cap, sampling ? 0 : 1, store != 0);
   });
 }
@@ -395,7 +409,6 @@ int wb200_session_iter_stats(wb200_session* s, int sampling, long long* stats4,
   return catch_exceptions(err, [&] {
     WB200_CUDA(cudaSetDevice(s->device));
     if (!s->initialised) throw std::runtime_error("session is not initialised");
-    if (s->tick) throw std::runtime_error("iter_stats: chain-resident engine only");
     chain_iter_stats(*s, sampling != 0, stats4);
   });
 }

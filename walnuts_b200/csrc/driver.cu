@@ -547,7 +547,8 @@ static int sample_device_impl(
       }
       return std::min(stride, max_iter - done);
     };
-    // Free-running phases (chain-resident engine, min < max): as in the reference, where
+    // Free-running phases (min < max, both engines; on the lock-step engine a budget of
+    // gradient evaluations is that many ticks): as in the reference, where
     // every chain is a thread that runs at its own pace until the controller stops it
     // (adapt.hpp:110-129, sampler.hpp:79-94), chains advance by equal WORK per block -- a
     // budget of gradient evaluations worth `stride` average iterations -- and not by equal
@@ -557,7 +558,7 @@ static int sample_device_impl(
     // convergence or when every chain has reached max_iter (:219-221).
     // WB200_BLOCKS=uniform restores blocks of equal iteration counts.
     const char* blocks_env = std::getenv("WB200_BLOCKS");
-    const bool allow_free = !s->tick && !(blocks_env && std::string(blocks_env) == "uniform");
+    const bool allow_free = !(blocks_env && std::string(blocks_env) == "uniform");
     long long evals_seen = 0, iters_seen = 0;  // all chains, both phases: the mean cost
     long long warm_max = 0;
     std::vector<long long> warm_rows;  // per chain, when the warm-up ran free

@@ -197,7 +197,9 @@ void tick_destroy(wb200_session& s);
 void tick_init(wb200_session& s, bool have_mass, bool have_steps, bool have_positions,
                double init_radius);
 void tick_run(wb200_session& s, int n_iter, int adapt, bool store);
-void tick_run_ticks(wb200_session& s, int n_ticks, int adapt, bool store);
+// iter_cap > 0: no chain goes beyond that many iterations of the phase in total
+void tick_run_ticks(wb200_session& s, int n_ticks, int adapt, bool store,
+                    long long iter_cap = 0);
 void tick_chain_rows(wb200_session& s, long long* rows_host);
 // free-running + streaming: per-chain staged row counts -> rows_dev, then reset to 0
 void tick_take_rows(wb200_session& s, long long* rows_dev);

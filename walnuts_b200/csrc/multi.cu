@@ -203,8 +203,7 @@ void run_rank(Rank& r, Shared& sh, const Args& a, int* warm_done_out, int* samp_
   // devices compute the same budgets a single device holding all chains would -- and the
   // controllers read the all-reduced {min, max, sum} of the per-chain iteration counts.
   const char* blocks_env = std::getenv("WB200_BLOCKS");
-  const bool allow_free =
-      !r.s->tick && !(blocks_env && std::string(blocks_env) == "uniform");
+  const bool allow_free = !(blocks_env && std::string(blocks_env) == "uniform");
   double evals_seen = 0, iters_seen = 0;
   auto free_budget = [&] {
     const double per_iter = iters_seen > 0 ? evals_seen / iters_seen : 16.0;

@@ -546,10 +546,16 @@ void tick_run(wb200_session& s, int n_iter, int adapt, bool store) {
 }
 
 // free-running: chains that finished an iteration quota start over; nothing is reset
-__global__ void tick_resume_kernel(TickState* ts, int C, long long rows_floor) {
+// (a chain that has done the phase's iter_cap iterations stays stopped)
+__global__ void tick_resume_kernel(TickState* ts, const ChainScalars* sc, int C,
+                                   long long rows_floor, int adapt, long long iter_cap) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
-    if (ts[c].pc == PC_DONE) ts[c].pc = PC_START_TRANSITION;
+    const long long done = adapt ? static_cast<long long>(sc[c].warm_iter)
+                                 : static_cast<long long>(sc[c].lp_n);
+    if (ts[c].pc == PC_DONE && !(iter_cap > 0 && done >= iter_cap)) {
+      ts[c].pc = PC_START_TRANSITION;
+    }
     if (ts[c].rows < rows_floor) ts[c].rows = rows_floor;
   }
 }
@@ -561,11 +567,14 @@ __global__ void tick_rows_kernel(const TickState* ts, int C, long long* rows) {
 
 // exactly n_ticks lock-step ticks; every chain does as many transitions as fit
 // (ragged draw counts, like the reference's adaptive runs)
-void tick_run_ticks(wb200_session& s, int n_ticks, int adapt, bool store) {
+void tick_run_ticks(wb200_session& s, int n_ticks, int adapt, bool store,
+                    long long iter_cap) {
   TickEngine& e = *s.tick;
   TickParams tp = tick_params(s, -1, adapt, store);
+  tp.cp.iter_cap = iter_cap;
   const int grid = (s.C + s.shape.chains_per_cta - 1) / s.shape.chains_per_cta;
-  tick_resume_kernel<<<(s.C + 255) / 256, 256, 0, s.stream>>>(e.ts.ptr, s.C, s.rows_written);
+  tick_resume_kernel<<<(s.C + 255) / 256, 256, 0, s.stream>>>(
+      e.ts.ptr, s.sc.ptr, s.C, s.rows_written, adapt, iter_cap);
   WB200_CUDA(cudaEventRecord(s.ev0, s.stream));
   if (s.kind == kLogistic && e.logistic[1]) {
     // two half batches, each a self-contained tick / gradient chain on its own stream

@@ -575,7 +575,13 @@ struct TickRunner {
         }
         st.done_iters += 1;
         if (p.draws) st.rows = row + 1;
-        if (ragged ? (p.draws && st.rows >= p.draw_cap) : (st.done_iters >= p.n_iter)) {
+        // free-running: a chain stops when its rows are full or it has done the phase's
+        // iter_cap iterations (a reference chain stops at max_iter, sampler.hpp:82)
+        const long long phase_iters = p.adapt ? static_cast<long long>(sc.warm_iter)
+                                              : static_cast<long long>(sc.lp_n);
+        if (ragged ? ((p.draws && st.rows >= p.draw_cap) ||
+                      (p.iter_cap > 0 && phase_iters >= p.iter_cap))
+                   : (st.done_iters >= p.n_iter)) {
           st.pc = PC_DONE;
           // keep theta in sync with the chain kernel's convention
           V::store(p.theta + static_cast<long long>(chain) * ld, ld, tid, cur);

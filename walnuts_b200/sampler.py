@@ -103,11 +103,11 @@ def walnuts_device(
     Arguments, defaults, validation errors and the returned list of
     :class:`WalnutsOutputArray` follow ``walnuts_pyfunc`` (pyfunc.py:45-286).
     Differences: (i) ``logp`` is a :class:`DeviceModel`; (ii) with ``min < max`` the
-    chains of an element-wise model run free like the reference's threads -- by equal
+    chains run free like the reference's threads -- by equal
     work (gradient evaluations) per block, so final lengths differ by chain as in the
-    reference (docs/py.rst:13-20) but are reproducible; lock-step (logistic, callback)
-    models and ``WB200_BLOCKS=uniform`` stop all chains at the same iteration, decided
-    every ``publish_stride`` (5) iterations; (iii) random numbers come
+    reference (docs/py.rst:13-20) but are reproducible; ``WB200_BLOCKS=uniform`` stops all
+    chains at the same iteration, decided every ``publish_stride`` (5) iterations;
+    (iii) random numbers come
     from a counter-based Philox stream keyed by ``(seed + id + num_chains,
     chain)``, not from ``std::mt19937_64``.
     """
