@@ -28,3 +28,15 @@ with wb.Session(wb.models.funnel(D), C, seed=1, max_trajectory_doublings=10,
     c2 = s.counters()
     ev = c2["grad_evals"] - c1["grad_evals"]
     print(f"sampling 20 x 10 iterations: {ms:.1f} ms, {ev / ms / 1e3:.1f} M evals/s")
+    budget = int(ev / C / 20)
+    for _ in range(3):
+        s.sample_ticks(budget, store=False)
+    c3 = s.counters()
+    s.timer_start()
+    for _ in range(20):
+        s.sample_ticks(budget, store=False)
+    ms = s.timer_stop_ms()
+    c4 = s.counters()
+    ev = c4["grad_evals"] - c3["grad_evals"]
+    print(f"free-running 20 x {budget} evaluations per chain: {ms:.1f} ms, "
+          f"{ev / ms / 1e3:.1f} M evals/s")
