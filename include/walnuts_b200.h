@@ -116,8 +116,17 @@ void walnuts_b200_default_tuning(WalnutTuning* t);
  *   inits            nullable [C][D]; else N(0, init_radius^2) (walnutpy.cpp:186-190)
  *   init_inv_metric  nullable [C][D]; used as the initial MASS, bug-compatible
  *                    with walnutpy.cpp:64-70
- *   out              [C][max_sampling_iter + save_warmup*max_warmup_iter][D]
- *   final_lengths    [2C] warm-up lengths then sampling lengths
+ *   out              [C][max_sampling_iter + save_warmup*max_warmup_iter][D]; a chain's
+ *                    block holds its saved warm-up draws followed directly by its sampling
+ *                    draws (walnutpy.cpp:196-203)
+ *   final_lengths    [2C] warm-up lengths then sampling lengths, PER CHAIN: with
+ *                    min_iter < max_iter the chains run free like the reference's threads
+ *                    (adapt.hpp:110-129, sampler.hpp:79-94) -- by equal work, a budget of
+ *                    gradient evaluations per block -- and stop on their own; the
+ *                    controllers keep the reference's rules (no decision before every
+ *                    chain has min_iter, stop on convergence or when all are at max_iter).
+ *                    Environment WB200_BLOCKS=uniform: blocks of publish_stride
+ *                    iterations, all chains stop together.
  */
 int walnutpie_sample_device(
     const WalnutModelDesc* model, int num_params, const double* inits,
