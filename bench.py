@@ -523,6 +523,14 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------
+def sess_ld(D):
+    """an upper bound of the padded row length (doubles) of a D-dimensional session"""
+    ld = 64
+    while ld < D:
+        ld *= 2
+    return ld
+
+
 def one_shot(model, wl, C, rank, n_warm, n_samp, summaries, inits):
     """The C-ABI one-shot call with pinned host buffers on this rank's GPU; returns
     (seconds, gradient evaluations, h2d bytes, d2h bytes, result)."""
@@ -549,9 +557,6 @@ def one_shot(model, wl, C, rank, n_warm, n_samp, summaries, inits):
         result = {k: np.array(v) for k, v in out.items()}
         result["truncated"] = cut
     else:
-        import psutil
-        if C * n_samp * Dw * 8 > 0.5 * psutil.virtual_memory().available:
-            raise SystemExit("not enough host memory for the e2e output buffer")
         out = _ffi.pinned_empty((C, n_samp, Dw))
         t0 = time.perf_counter()
         _ffi._ffi_sample_device(*head, *tail, False, out, out.size, lengths, stepsize, None, 0,
@@ -588,7 +593,13 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
     # rows of the quota steps, then room for the free-running steps (ragged: chains with
     # short orbits complete several times the average number of transitions)
     free_factor = 8 if wl["kind"] == "funnel" else 2
-    sess.reserve((W + K) * ips * (1 + free_factor))
+    Kf = min(K, 20)                       # timed free-running steps (bounded for large K)
+    row_bytes = C * sess_ld(Dw) * 8       # one draw row of every chain
+    free_rows = (W + Kf) * ips * free_factor
+    free_mem = torch.cuda.mem_get_info(local_rank)[0]
+    if ((W + K) * ips + free_rows) * row_bytes > 0.6 * free_mem:
+        raise SystemExit(f"--steps {K}: the stored draws of the timed steps do not fit the GPU")
+    sess.reserve((W + K) * ips + free_rows)
     # ---- untimed set-up: adaptive warm-up (device time reported separately)
     sess.sync()
     c0 = sess.counters()
@@ -641,7 +652,7 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
     f0 = sess.counters()
     comm.barrier()
     sess.timer_start()
-    for _ in range(K):
+    for _ in range(Kf):
         sess.sample_ticks(budget)
     free_ms = sess.timer_stop_ms()
     torch.cuda.synchronize()
@@ -654,7 +665,8 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
     (free_min_ess,) = comm.reduce([float(np.min(free_summary["ess"]))], "sum")
     free_running = {
         "value": free_evals / (free_max_ms * 1e-3), "unit": "grad_evals/s",
-        "ms_per_step": free_max_ms / K, "eval_budget_per_chain_and_step": budget,
+        "ms_per_step": free_max_ms / Kf, "steps": Kf,
+        "eval_budget_per_chain_and_step": budget,
         "gpu_launches": int(f1["kernel_launches"] - f0["kernel_launches"]),
         "draws_per_chain_min_max": [int(free_counts.min()), int(free_counts.max())],
         "min_ess": free_min_ess, "max_r_hat": float(np.max(free_summary["r_hat"])),
@@ -716,6 +728,10 @@ def bench_elementwise(args, comm, name, K, W, ips, cpu_leg=True, all_draws_leg=T
            "min_ess": float(np.min(e2e_summary["ess"])),
            "max_r_hat": float(np.max(e2e_summary["r_hat"]))}
     e2e_all = None
+    import psutil
+    if all_draws_leg and C * e2e_samp * Dw * 8 * (world if world <= 8 else 8) > \
+            0.5 * psutil.virtual_memory().available:
+        all_draws_leg = False   # (every rank of the node pins its own buffer)
     if all_draws_leg:
         comm.barrier()
         dt, ev, h2d, d2h, _ = one_shot(model, wl, C, rank, n_warm, e2e_samp, False, inits)
