@@ -601,7 +601,11 @@ struct TickRunner {
 
 #if defined(__CUDACC__)
 template <int T, int K, int CTA>
-__global__ void __launch_bounds__(CTA, (CTA <= 128 ? 512 / CTA : 1)) walnuts_tick_kernel(const TickParams tp) {
+#ifndef WB200_TICK_THREADS_PER_SM
+#define WB200_TICK_THREADS_PER_SM 512  // resident threads asked for (register cap 128)
+#endif
+__global__ void __launch_bounds__(CTA, (CTA <= 128 ? WB200_TICK_THREADS_PER_SM / CTA : 1))
+walnuts_tick_kernel(const TickParams tp) {
   __shared__ double red_smem[group_smem_doubles<T>()];
   Group<T> grp;
   grp.lane = threadIdx.x & 31;
