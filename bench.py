@@ -134,6 +134,26 @@ class ClockSampler:
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        # NVML in-process where available (a query takes ~0.1 ms, so short timed regions
+        # still get tens of samples); the nvidia-smi query of the profiling recipe otherwise
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40),
+                    ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+            while not self._stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = get_reasons(h)
+                self.rows.append([str(sm), str(mx), "0"] +
+                                 ["Active" if r & b else "Not Active" for _, b in bits])
+                self._stop.wait(0.005)
+            return
+        except Exception:
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(
