@@ -315,8 +315,8 @@ class Session:
 
     def run_evals(self, eval_budget: int, *, sampling: bool, iter_cap: int = 0,
                   store: bool = True):
-        """Chain-resident sessions: one free-running launch of ``eval_budget`` gradient
-        evaluations per chain in which no chain exceeds ``iter_cap`` iterations of the
+        """One free-running launch of ``eval_budget`` gradient evaluations per chain (lock-step
+        sessions: that many ticks) in which no chain exceeds ``iter_cap`` iterations of the
         phase in total (0: no limit) -- a reference chain stops at ``max_iter``."""
         _ffi.session_run_evals(self._h, int(sampling), int(eval_budget), int(iter_cap),
                                int(store))
