@@ -189,15 +189,17 @@ Shape4 shape4_for(const wb200::LaunchShape& sh) {
   return out;
 }
 
+// (heap-allocated and never destroyed: the modules live as long as the process, and no
+// destructor calls into the driver while the process is being torn down)
 std::mutex g_cache_mutex;
-std::map<std::string, std::shared_ptr<wb200::UserModule>> g_cache;
+auto& g_cache = *new std::map<std::string, std::shared_ptr<wb200::UserModule>>();
 // compiled once per (launch shape, source), loaded once per device
 struct Compiled {
   std::vector<char> cubin;
   std::vector<std::string> lowered;
   std::string log;
 };
-std::map<std::string, std::shared_ptr<Compiled>> g_compiled;
+auto& g_compiled = *new std::map<std::string, std::shared_ptr<Compiled>>();
 
 }  // namespace
 
