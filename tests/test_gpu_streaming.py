@@ -240,3 +240,23 @@ def test_multi_device_one_shot_call_equals_the_single_device_call(wb, oracle, mo
         np.testing.assert_allclose(many[k], one[k], rtol=1e-8, atol=1e-12, err_msg=k)
     with pytest.raises(ValueError, match="more devices than chains"):
         wb.walnuts_device_summary(model, num_chains=1, devices=[0, 0], **kw)
+
+
+def test_multi_device_call_on_the_lock_step_engine(wb):
+    """the same for a logistic model (lock-step ticks, tensor-core gradient): free-running
+    blocks are budgets of ticks, the stop decisions and per-chain lengths of the
+    multi-device call equal the single-device call's"""
+    import torch
+    from tests.test_gpu_parity import make_logistic
+    X, y = make_logistic(300, 8, 11)
+    model = wb.models.logistic(X, y)
+    kw = dict(num_chains=48, seed=3, min_warmup_iter=30, max_warmup_iter=100,
+              min_sampling_iter=30, max_sampling_iter=120, rhat_converge_tol=1.03,
+              mass_converge_tol=0.9, step_size_converge_tol=0.35, max_trajectory_doublings=8)
+    one = wb.walnuts_device_summary(model, **kw)
+    ndev = min(torch.cuda.device_count(), 2)
+    many = wb.walnuts_device_summary(model, devices=list(range(ndev)), **kw)
+    np.testing.assert_array_equal(many["sampling_lengths"], one["sampling_lengths"])
+    np.testing.assert_array_equal(many["stepsize"], one["stepsize"])
+    for k in ("mean", "variance", "r_hat", "ess", "mcse"):
+        np.testing.assert_allclose(many[k], one[k], rtol=1e-8, atol=1e-12, err_msg=k)
