@@ -257,3 +257,17 @@ def test_one_shot_call_runs_free_on_the_lock_step_engine(wb, monkeypatch):
                             max_warmup_iter=20, min_sampling_iter=10, max_sampling_iter=40,
                             rhat_converge_tol=1.0 + 1e-9)
     assert {len(f) for f in fit} == {40}
+
+
+@pytest.mark.parametrize("C,D", [(1, 1), (2, 3), (5, 129)])
+def test_free_running_one_shot_edge_sizes(wb, C, D):
+    """one chain (no R-hat: runs to max_iter, as the reference's NaN comparison does), one
+    dimension, a dimension just above a shape boundary"""
+    fit = wb.walnuts_device(wb.models.std_normal(D), num_chains=C, seed=2, min_warmup_iter=10,
+                            max_warmup_iter=40, min_sampling_iter=10, max_sampling_iter=45,
+                            save_warmup=True)
+    for f in fit:
+        assert 10 <= len(f) <= 45 and 10 <= len(f.warmup.warmup_draws) <= 40
+        assert np.all(np.isfinite(np.asarray(f))) and np.asarray(f).shape[1] == D
+    if C == 1:
+        assert len(fit[0]) == 45
